@@ -1,0 +1,177 @@
+/*
+ * team_b200.h - C ABI of the B200-native TEAM head (libteam_b200.so).
+ *
+ * The reference (ericzhengz/TEAM-Temporal-Evolution-Aware-Multimodal-model) is pure
+ * Python/torch and has no FFI of its own; every entry point below replaces the tensor
+ * math of the reference method cited next to it (file:line relative to the reference
+ * root) and is what a ctypes binding inside that method would call.
+ *
+ * Conventions
+ *   - return 0 on success, a negative TEAM_E* code otherwise; team_last_error() gives a
+ *     thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; row-major,
+ *     contiguous, 16-byte aligned.  The caller owns all memory (outputs + workspace);
+ *     team_*_workspace_bytes() sizes the workspace.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, no global mutable state, re-entrant across streams.
+ *   - feature width is fixed to TEAM_D = 512 (CLIP ViT-B/16, utils/inc_net.py:21).
+ */
+#ifndef TEAM_B200_H
+#define TEAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEAM_D 512
+#define TEAM_NUM_STATES 10          /* utils/inc_net.py:361 */
+#define TEAM_MAX_TASKS 64
+
+#define TEAM_OK 0
+#define TEAM_EINVAL (-1)            /* bad argument / unsupported shape */
+#define TEAM_ECUDA (-2)             /* CUDA runtime error (message in team_last_error) */
+#define TEAM_EWORKSPACE (-3)        /* workspace too small */
+#define TEAM_EUNSUPPORTED (-4)      /* needs an sm_100 device */
+
+#define TEAM_DTYPE_F32 0
+#define TEAM_DTYPE_BF16 1
+
+/* precision modes of the head */
+#define TEAM_MODE_F32 0             /* all GEMMs in fp32 FFMA (parity mode, 1e-5) */
+#define TEAM_MODE_BF16 1            /* large GEMMs on tcgen05 with bf16 operands, fp32 accumulate */
+
+const char* team_last_error(void);
+int team_version(void);
+/* 0 if the current device is sm_100 (B200), TEAM_EUNSUPPORTED otherwise */
+int team_device_check(void);
+
+/* ------------------------------------------------------------------ prototype build
+ * Deterministic, atomic-free keyed segmented sum (K9/K17).
+ * Replaces: Learner.cal_prototype reduction loop   models/proof.py:258-276
+ *           simplecil.Learner.replace_fc loop      models/simplecil.py:48-55
+ *           per-state batch centres                utils/state_distance.py:98-103
+ * key(i) = (labels[i]-class_base)*num_states + states[i]   if states != NULL
+ *        =  labels[i]-class_base                            otherwise
+ * Rows whose label is outside [class_base, class_base+num_classes) or whose state is
+ * outside [0,num_states) are skipped.  If normalize_rows != 0 every row is L2-normalised
+ * (F.normalize, eps 1e-12) before accumulation (convnet.encode_image(normalize=True),
+ * models/proof.py:248).  sums[K,512] fp32 and counts[K] int64 are OVERWRITTEN
+ * (K = num_classes * max(num_states,1)).  Result is bit-reproducible run to run.
+ */
+size_t team_segsum_workspace_bytes(int64_t n_rows, int64_t num_keys);
+int team_segsum(const void* x, int x_dtype, const int64_t* labels, const int64_t* states,
+                int64_t n_rows, int64_t class_base, int64_t num_classes, int64_t num_states,
+                int normalize_rows, float* sums, int64_t* counts,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* means[k,:] = sums[k,:]/counts[k] for counts[k]>0; rows with counts==0 are left untouched
+ * (empty classes keep their previous prototype, models/proof.py:261).  If class_sums /
+ * class_counts are non-NULL they receive the per-class totals over states
+ * (num_groups = num_keys/group) and class_means the per-class means. */
+int team_segmean_finalize(const float* sums, const int64_t* counts, int64_t num_keys,
+                          float* means, int64_t group, float* class_means,
+                          int64_t* class_counts, void* stream);
+
+/* ------------------------------------------------------------------ cosine classifier
+ * logits[n,c] = sigma * <x_n/|x_n|, w_c/|w_c|>    (K8)
+ * Replaces: CosineLinear.forward                    convs/linears.py:51-61
+ *           final stage of forward_for_classification models/proof.py:526-535 (sigma = 1)
+ * logits (fp32 [N,C]) and argmax (int64 [N], first maximal index like torch.max) are
+ * each optional (NULL to skip).  sigma_dev may be NULL (= 1).
+ */
+int team_cosine_logits(const void* x, int x_dtype, int64_t n_rows, const float* w,
+                       int64_t num_classes, const float* sigma_dev, float* logits,
+                       int64_t* argmax, void* stream);
+
+/* ------------------------------------------------------------------ the fusion head
+ * forward_tri_modal + forward_for_classification, fwd and bwd.
+ * Replaces: Proof_Net.encode_image/encode_text/encode_state/encode_prototpyes
+ *               utils/inc_net.py:401-422, :518-526
+ *           Proof_Net.forward_tri_modal               utils/inc_net.py:528-580
+ *           MultiHeadAttention.forward (sel_attn)      convs/projections.py:64-87
+ *           Learner.forward_for_classification         models/proof.py:519-536
+ *           and their autograd backward (models/proof.py:444).
+ */
+typedef struct team_head_weights {
+    int32_t num_tasks;                       /* T */
+    int32_t prompts_per_task;                /* context_prompt_length_per_task */
+    const float* w_img[TEAM_MAX_TASKS];      /* projs_img[t].MLP[0].weight [512,512] */
+    const float* b_img[TEAM_MAX_TASKS];      /* projs_img[t].MLP[0].bias   [512] */
+    const float* w_text[TEAM_MAX_TASKS];
+    const float* b_text[TEAM_MAX_TASKS];
+    const float* w_state[TEAM_MAX_TASKS];
+    const float* b_state[TEAM_MAX_TASKS];
+    const float* prompts[TEAM_MAX_TASKS];    /* context_prompts[t] [prompts_per_task,512] */
+    const float* state_emb;                  /* state_embedder.state_embeddings.weight [10,512] */
+    const float* w_q;                        /* sel_attn.w_qs.weight [512,512] */
+    const float* w_k;
+    const float* w_v;
+    const float* w_fc;                       /* sel_attn.fc.weight */
+    const float* b_fc;
+    const float* ln_g;                       /* sel_attn.layer_norm.weight */
+    const float* ln_b;
+    const float* prototypes;                 /* img_prototypes [C,512] */
+    int32_t num_classes;                     /* C */
+    int32_t reserved;
+} team_head_weights;
+
+typedef struct team_head_grads {            /* all OVERWRITTEN by team_head_tri_bwd */
+    float* w_img;  float* b_img;             /* newest task only (utils/inc_net.py:494-507) */
+    float* w_text; float* b_text;
+    float* w_state; float* b_state;
+    float* prompts;                          /* all prompt rows [T*prompts_per_task,512]; may be NULL */
+    float* state_emb;                        /* [10,512] */
+    float* w_q; float* w_k; float* w_v;
+    float* w_fc; float* b_fc;
+    float* ln_g; float* ln_b;
+} team_head_grads;
+
+size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, int32_t num_prompts,
+                                 int32_t num_text_cls, int mode);
+
+/* image_feat/text_feat [B,512] fp32 (post-CLIP features; per-sample text), state_ids [B] int64.
+ * Outputs (fp32): out_image [B,512], out_text [B,512] (the [B,1,512] view is the caller's),
+ * out_state [B,512], out_proto [B,512].
+ * If text_cls != NULL (fp32 [num_text_cls,512]) also computes the no-grad classification
+ * logits cls_logits [B,num_text_cls] = normalize(encode_image(x)) @ normalize(encode_text(t)).T
+ * and, if cls_argmax != NULL, their row argmax.
+ * The workspace keeps the intermediates team_head_tri_bwd needs and must stay untouched
+ * between the two calls. */
+int team_head_tri_fwd(const team_head_weights* w, int mode, int64_t batch,
+                      const float* image_feat, const float* text_feat, const int64_t* state_ids,
+                      const float* text_cls, int64_t num_text_cls,
+                      float* out_image, float* out_text, float* out_state, float* out_proto,
+                      float* cls_logits, int64_t* cls_argmax,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+int team_head_tri_bwd(const team_head_weights* w, int mode, int64_t batch,
+                      const float* image_feat, const float* text_feat, const int64_t* state_ids,
+                      const float* g_image, const float* g_text, const float* g_state,
+                      const float* g_proto, const team_head_grads* grads,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* encode_* alone (utils/inc_net.py:401-422, :518-526): out = [normalize](sum_t x W_t^T + b_t).
+ * which: 0 image, 1 text, 2 state (x = state_ids int64, embedding gather fused), 3 prototypes
+ * (x ignored, rows = img_prototypes). */
+int team_head_encode(const team_head_weights* w, int mode, int which, const void* x,
+                     int64_t n_rows, int normalize, float* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ generic GEMM (tests/bench)
+ * C[M,N] = alpha * op(A) op(B) + beta * C (+ bias[N]);  fp32 SIMT path.
+ * ta: 0 -> A is [M,K] row-major (lda), 1 -> A is [K,M] row-major.
+ * tb: 0 -> B is [K,N] row-major (ldb), 1 -> B is [N,K] row-major. */
+int team_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha,
+                  const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                  float* C, int64_t ldc, const float* bias, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* C[M,N] fp32 = A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major), tcgen05 + TMA + TMEM. */
+int team_gemm_bf16_nt(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                      const void* B, int64_t ldb, float* C, int64_t ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEAM_B200_H */

@@ -1,0 +1,114 @@
+"""ctypes binding of ``libteam_b200.so`` (declared in ``include/team_b200.h``).
+
+The library handle is module-global (never stored on an ``nn.Module``) so that the
+reference's ``copy.deepcopy(self._network)`` (models/proof.py:297) keeps working.
+There is deliberately no fallback: if the shared library is missing or a call fails a
+``TeamB200Error`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libteam_b200.so")
+
+D = 512
+NUM_STATES = 10
+MAX_TASKS = 64
+DTYPE_F32, DTYPE_BF16 = 0, 1
+MODE_F32, MODE_BF16 = 0, 1
+
+EXPORTS = [
+    "team_last_error", "team_version", "team_device_check",
+    "team_segsum_workspace_bytes", "team_segsum", "team_segmean_finalize",
+    "team_cosine_logits",
+]
+
+
+class TeamB200Error(RuntimeError):
+    pass
+
+
+class HeadWeights(C.Structure):
+    _fields_ = ([("num_tasks", C.c_int32), ("prompts_per_task", C.c_int32)] +
+                [(n, C.c_void_p * MAX_TASKS) for n in
+                 ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts")] +
+                [(n, C.c_void_p) for n in
+                 ("state_emb", "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "prototypes")] +
+                [("num_classes", C.c_int32), ("reserved", C.c_int32)])
+
+
+class HeadGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts", "state_emb",
+                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b")]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(lib):
+    vp, i64, i32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
+    lib.team_last_error.restype = C.c_char_p
+    lib.team_last_error.argtypes = []
+    lib.team_version.restype = i32
+    lib.team_device_check.restype = i32
+    lib.team_segsum_workspace_bytes.restype = sz
+    lib.team_segsum_workspace_bytes.argtypes = [i64, i64]
+    lib.team_segsum.restype = i32
+    lib.team_segsum.argtypes = [vp, i32, vp, vp, i64, i64, i64, i64, i32, vp, vp, vp, sz, vp]
+    lib.team_segmean_finalize.restype = i32
+    lib.team_segmean_finalize.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp]
+    lib.team_cosine_logits.restype = i32
+    lib.team_cosine_logits.argtypes = [vp, i32, i64, vp, i64, vp, vp, vp, vp]
+    if hasattr(lib, "team_gemm_f32"):
+        lib.team_gemm_f32.restype = i32
+        lib.team_gemm_f32.argtypes = [i32, i32, i64, i64, i64, C.c_float, vp, i64, vp, i64, C.c_float,
+                                      vp, i64, vp, vp, sz, vp]
+    if hasattr(lib, "team_gemm_bf16_nt"):
+        lib.team_gemm_bf16_nt.restype = i32
+        lib.team_gemm_bf16_nt.argtypes = [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]
+    if hasattr(lib, "team_head_workspace_bytes"):
+        lib.team_head_workspace_bytes.restype = sz
+        lib.team_head_workspace_bytes.argtypes = [i64, C.c_int32, C.c_int32, C.c_int32, i32]
+        lib.team_head_tri_fwd.restype = i32
+        lib.team_head_tri_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, vp, vp, i64,
+                                          vp, vp, vp, vp, vp, vp, vp, sz, vp]
+        lib.team_head_tri_bwd.restype = i32
+        lib.team_head_tri_bwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, vp, vp, vp, vp, vp,
+                                          C.POINTER(HeadGrads), vp, sz, vp]
+        lib.team_head_encode.restype = i32
+        lib.team_head_encode.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, sz, vp]
+
+
+def lib():
+    """The loaded shared library; raises TeamB200Error if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise TeamB200Error(
+                        f"{LIB_PATH} not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU/PyTorch fallback)")
+                handle = C.CDLL(LIB_PATH)
+                _declare(handle)
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().team_last_error().decode("utf-8", "replace")
+        raise TeamB200Error(f"{what} failed with code {rc}: {msg}")
+
+
+def require_device():
+    """Fail loudly unless torch sees a CUDA device of compute capability 10.x."""
+    import torch
+    if not torch.cuda.is_available():
+        raise TeamB200Error("team_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(lib().team_device_check(), "team_device_check")

@@ -1,0 +1,65 @@
+// Shared helpers for the TEAM head kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/team_b200.h"
+
+namespace team {
+
+constexpr int D = TEAM_D;               // 512
+constexpr int NUM_SMS = 148;            // B200
+constexpr float LN_EPS = 1e-5f;
+constexpr float NORM_EPS = 1e-12f;
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define TEAM_CUDA_CHECK(expr)                                   \
+    do {                                                        \
+        cudaError_t _e = (expr);                                \
+        if (_e != cudaSuccess) return team::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define TEAM_LAUNCH_CHECK(name)                                 \
+    do {                                                        \
+        cudaError_t _e = cudaGetLastError();                    \
+        if (_e != cudaSuccess) return team::cuda_fail(_e, name); \
+    } while (0)
+
+#define TEAM_REQUIRE(cond, ...)                                 \
+    do {                                                        \
+        if (!(cond)) { team::set_error(__VA_ARGS__); return TEAM_EINVAL; } \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// 128-bit streaming load that does not pollute L1 (inputs read exactly once).
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace team

@@ -1,0 +1,235 @@
+// Forward kernels of the fusion head (Proof_Net.forward_tri_modal, utils/inc_net.py:528-580;
+// sel_attn, convs/projections.py:64-87) in the factorised form of DESIGN.md section 3:
+//   * the C prototype rows, P prompt rows and the 10 state-table rows ("step rows") are
+//     projected ONCE per step instead of once per sample;
+//   * fc is folded into V (VF = V Wfc^T), so attention outputs are convex combinations of
+//     VF rows and fc is never applied to the 3+C returned rows of every sample;
+//   * queries that are step rows (prototype outputs, state output) reuse a per-step
+//     softmax partial (m, Z, NF) over the M shared keys; only 3 own keys are per sample.
+#pragma once
+#include "head_kernels.cuh"
+
+namespace team {
+
+// ------------------------------------------------------------------ sum_t W_t, sum_t b_t
+__global__ void __launch_bounds__(256)
+sum_weights_kernel(PtrList W, PtrList Bv, float* __restrict__ Wout, float* __restrict__ bout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // float4 index
+    if (i < D * D / 4) {
+        float4 s = reinterpret_cast<const float4*>(W.p[0])[i];
+        for (int t = 1; t < W.n; ++t) {
+            const float4 a = reinterpret_cast<const float4*>(W.p[t])[i];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+        reinterpret_cast<float4*>(Wout)[i] = s;
+    }
+    if (i < D / 4) {
+        float4 s = reinterpret_cast<const float4*>(Bv.p[0])[i];
+        for (int t = 1; t < Bv.n; ++t) {
+            const float4 a = reinterpret_cast<const float4*>(Bv.p[t])[i];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+        reinterpret_cast<float4*>(bout)[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------ row L2-normalise (F.normalize)
+// X[r] = Z[r] / max(|Z[r]|, 1e-12); inv[r] = 1/max(|Z[r]|,eps).  warp per row.  If gather != null the
+// source row is Z[gather[r]] (embedding lookup).  dst_map: row r is written to X[dst_off + r].
+__global__ void __launch_bounds__(256)
+rows_normalize_kernel(const float* __restrict__ Z, int64_t n_rows, float* __restrict__ X, float* __restrict__ inv,
+                      int do_normalize) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    float4 v[4];
+    ld_row(Z + r * D, lane, v);
+    float s = 1.0f;
+    if (do_normalize) {
+        const float ss = warp_sum(dot_part(v, v));
+        s = 1.0f / fmaxf(sqrtf(ss), NORM_EPS);
+        scale_row(v, s);
+    }
+    st_row(X + r * D, lane, v);
+    if (inv != nullptr && lane == 0) inv[r] = s;
+}
+
+// out[r] = table[clamp(ids[r])]  (state-embedding style gather of 512-wide rows)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, int64_t n_rows, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    float4 v[4];
+    ld_row(table + (size_t)clamp_state(ids[r]) * D, lane, v);
+    st_row(out + r * D, lane, v);
+}
+
+// prompts of all tasks -> S rows [C, C+P); zero rows [Ns, Nsp)
+__global__ void __launch_bounds__(128)
+fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float* __restrict__ S) {
+    const int r = blockIdx.x;                    // 0 .. P + (Nsp-Ns) - 1
+    const int P = prompts.n * ppt;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int dst;
+    if (r < P) {
+        v = reinterpret_cast<const float4*>(prompts.p[r / ppt] + (size_t)(r % ppt) * D)[threadIdx.x];
+        dst = C + r;
+    } else {
+        dst = Ns + (r - P);
+    }
+    reinterpret_cast<float4*>(S + (size_t)dst * D)[threadIdx.x] = v;
+}
+
+// ------------------------------------------------------------------ per-step softmax partials of step-row queries
+// For every step row r: m_r = max_j<M TT[r][j]/tau, P[r][j] = exp(TT[r][j]/tau - m_r) (0 for j>=M), Z_r = sum_j P.
+__global__ void __launch_bounds__(256)
+table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restrict__ mt, float* __restrict__ Zt,
+                  float* __restrict__ Pt) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= Nsp) return;
+    float mx = -INFINITY;
+    for (int j = lane; j < M; j += 32) mx = fmaxf(mx, TT[(size_t)r * Nsp + j] * INV_TAU);
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < Nsp; j += 32) {
+        float p = 0.f;
+        if (j < M) { p = expf(TT[(size_t)r * Nsp + j] * INV_TAU - mx); z += p; }
+        Pt[(size_t)r * Nsp + j] = p;
+    }
+    z = warp_sum(z);
+    if (lane == 0) { mt[r] = mx; Zt[r] = z; }
+}
+
+// ------------------------------------------------------------------ softmax of the own (image/text) query rows
+// keys: M shared step rows, the sample's state-table row (column M+sid), own image key, own text key.
+__global__ void __launch_bounds__(256)
+attn_own_kernel(HeadDims d, const float* __restrict__ SQ, const float* __restrict__ QKVo,
+                const int64_t* __restrict__ state_ids, float* __restrict__ Aext, float* __restrict__ aown) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= d.B2) return;
+    const int b = row < d.B ? row : row - d.B;
+    const int scol = d.M + clamp_state(state_ids[b]);
+    float4 q[4], k[4];
+    ld_row(QKVo + (size_t)row * 3 * D, lane, q);
+    ld_row(QKVo + (size_t)b * 3 * D + D, lane, k);
+    const float s_img = warp_sum(dot_part(q, k)) * INV_TAU;
+    ld_row(QKVo + (size_t)(d.B + b) * 3 * D + D, lane, k);
+    const float s_txt = warp_sum(dot_part(q, k)) * INV_TAU;
+    float mx = fmaxf(s_img, s_txt);
+    for (int j = lane; j < d.Nsp; j += 32)
+        if (j < d.M || j == scol) mx = fmaxf(mx, SQ[(size_t)row * d.Nsp + j] * INV_TAU);
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < d.Nsp; j += 32) {
+        float p = 0.f;
+        if (j < d.M || j == scol) { p = expf(SQ[(size_t)row * d.Nsp + j] * INV_TAU - mx); z += p; }
+        Aext[(size_t)row * d.Nsp + j] = p;
+    }
+    const float p_img = expf(s_img - mx), p_txt = expf(s_txt - mx);
+    z = warp_sum(z) + p_img + p_txt;
+    const float iz = 1.0f / z;
+    for (int j = lane; j < d.Nsp; j += 32) Aext[(size_t)row * d.Nsp + j] *= iz;
+    if (lane == 0) { aown[2 * row] = p_img * iz; aown[2 * row + 1] = p_txt * iz; }
+}
+
+// ------------------------------------------------------------------ fc-space output + residual + LayerNorm, own rows
+__global__ void __launch_bounds__(256)
+ln_own_fwd_kernel(HeadDims d, float* __restrict__ Ybo, const float* __restrict__ aown,
+                  const float* __restrict__ VFo, const float* __restrict__ Xo, const float* __restrict__ bfc,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ lnstat,
+                  float* __restrict__ out_image, float* __restrict__ out_text) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= d.B2) return;
+    const int b = row < d.B ? row : row - d.B;
+    float4 y[4], t[4], g[4], be[4], xh[4], o[4];
+    ld_row(Ybo + (size_t)row * D, lane, y);
+    ld_row(VFo + (size_t)b * D, lane, t);
+    axpy_row(y, aown[2 * row], t);
+    ld_row(VFo + (size_t)(d.B + b) * D, lane, t);
+    axpy_row(y, aown[2 * row + 1], t);
+    st_row(Ybo + (size_t)row * D, lane, y);               // Ybar (without bias): needed by the backward
+    ld_row(bfc, lane, t); add_row(y, t);
+    ld_row(Xo + (size_t)row * D, lane, t); add_row(y, t);
+    ld_row(gamma, lane, g); ld_row(beta, lane, be);
+    float rstd;
+    ln_forward(y, g, be, xh, rstd, o);
+    st_row((row < d.B ? out_image : out_text) + (size_t)b * D, lane, o);
+    (void)lnstat;
+}
+
+// ------------------------------------------------------------------ table-query rows (prototype + state outputs)
+// One warp evaluates one table-query row j of sample b: j < C -> prototype row j, j == C -> the state row.
+struct TableRowCtx {
+    float c_w;        // c / den   (weight of the shared partial)
+    float a_i, a_t, a_s;   // attention on own image / text / state keys
+    int r;            // step-row id of this query
+};
+
+__device__ __forceinline__ void table_row_forward(const HeadDims& d, int b, int j, int srow, int lane,
+        const float* __restrict__ SK, const float* __restrict__ TT, const float* __restrict__ mt,
+        const float* __restrict__ Zt, const float* __restrict__ NFt, const float* __restrict__ VFo,
+        const float* __restrict__ VFs, TableRowCtx& cx, float4 (&ybar)[4]) {
+    const int r = j < d.C ? j : srow;
+    cx.r = r;
+    const float s_i = SK[(size_t)b * d.Nsp + r] * INV_TAU;
+    const float s_t = SK[(size_t)(d.B + b) * d.Nsp + r] * INV_TAU;
+    const float s_s = TT[(size_t)r * d.Nsp + srow] * INV_TAU;
+    const float mr = mt[r];
+    const float m2 = fmaxf(fmaxf(mr, s_i), fmaxf(s_t, s_s));
+    const float c = expf(mr - m2), p_i = expf(s_i - m2), p_t = expf(s_t - m2), p_s = expf(s_s - m2);
+    const float w = 1.0f / (c * Zt[r] + p_i + p_t + p_s);
+    cx.c_w = c * w; cx.a_i = p_i * w; cx.a_t = p_t * w; cx.a_s = p_s * w;
+    float4 t[4];
+    ld_row(NFt + (size_t)r * D, lane, ybar); scale_row(ybar, cx.c_w);
+    ld_row(VFo + (size_t)b * D, lane, t); axpy_row(ybar, cx.a_i, t);
+    ld_row(VFo + (size_t)(d.B + b) * D, lane, t); axpy_row(ybar, cx.a_t, t);
+    ld_row(VFs + (size_t)srow * D, lane, t); axpy_row(ybar, cx.a_s, t);
+}
+
+__global__ void __launch_bounds__(TR_WARPS * 32)
+table_rows_fwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __restrict__ TT,
+                      const float* __restrict__ mt, const float* __restrict__ Zt, const float* __restrict__ NFt,
+                      const float* __restrict__ VFo, const float* __restrict__ VFs, const float* __restrict__ S,
+                      const float* __restrict__ bfc, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const int64_t* __restrict__ state_ids, float* __restrict__ out_proto,
+                      float* __restrict__ out_state) {
+    __shared__ __align__(16) float slot[TR_WARPS][D];          // 16 KB
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 g[4], be[4], bf[4];
+    ld_row(gamma, lane, g); ld_row(beta, lane, be); ld_row(bfc, lane, bf);
+    const int rounds = (d.C + 1 + TR_WARPS - 1) / TR_WARPS;
+    const float invC = 1.0f / (float)d.C;
+    for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
+        const int srow = d.M + clamp_state(state_ids[b]);
+        float2 acc = make_float2(0.f, 0.f);                       // columns 2t, 2t+1 of the prototype mean
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int j = rd * TR_WARPS + warp;
+            if (j <= d.C) {
+                TableRowCtx cx;
+                float4 u[4], t[4], xh[4], o[4];
+                table_row_forward(d, b, j, srow, lane, SK, TT, mt, Zt, NFt, VFo, VFs, cx, u);
+                add_row(u, bf);
+                ld_row(S + (size_t)cx.r * D, lane, t); add_row(u, t);
+                float rstd;
+                ln_forward(u, g, be, xh, rstd, o);
+                if (j < d.C) st_row(slot[warp], lane, o);
+                else st_row(out_state + (size_t)b * D, lane, o);
+            }
+            __syncthreads();
+            const int nvalid = min(TR_WARPS, d.C - rd * TR_WARPS);
+            for (int w = 0; w < nvalid; ++w) {
+                const float2 a = reinterpret_cast<const float2*>(slot[w])[threadIdx.x];
+                acc.x += a.x; acc.y += a.y;
+            }
+            __syncthreads();
+        }
+        if (d.C > 1) { acc.x *= invC; acc.y *= invC; }
+        reinterpret_cast<float2*>(out_proto + (size_t)b * D)[threadIdx.x] = acc;
+    }
+}
+
+}  // namespace team

@@ -1,0 +1,314 @@
+// K9/K17 - deterministic, atomic-free keyed segmented sum over [N,512] feature rows.
+//
+// Replaces the Python class/state loops of models/proof.py:258-276 (cal_prototype),
+// models/simplecil.py:48-55 (replace_fc) and utils/state_distance.py:98-103.
+//
+// HBM-bound: every feature row (2 KB fp32 / 1 KB bf16) is read exactly once with 128-bit
+// (64-bit for bf16) streaming loads; algorithmic bytes = 512*e + 8 (label) [+ 8 (state)]
+// per row.  Layout of the reduction:
+//   pass 1  grid = (8*n_clusters, n_slabs), 128 threads.  A CTA streams a contiguous chunk
+//           of rows.  Thread t owns columns [4t,4t+4) of every key accumulator in shared
+//           memory, so the per-key sums are built in row order with no atomics and no
+//           inter-thread races -> bit-reproducible.  8 rows are in flight per thread.
+//           The 8 CTAs of a thread-block cluster then fold their accumulators through
+//           distributed shared memory in rank order (one partial per cluster instead of
+//           per CTA: 8x less partial traffic).
+//   pass 2  partials [n_clusters,K,512] are summed in cluster order (fixed tree).
+// Counts are int64 and exact.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+namespace team {
+
+constexpr int SEG_THREADS = 128;
+constexpr int SEG_UNROLL = 8;
+constexpr int SEG_CLUSTER = 8;
+constexpr int SEG_SLAB_KEYS = 24;      // 24 keys * 2 KB = 48 KB smem -> 4 CTAs / SM
+
+template <typename T> struct RowLoad;
+template <> struct RowLoad<float> {
+    static __device__ __forceinline__ float4 load(const float* row, int t) { return ld_stream_f4(row + 4 * t); }
+};
+template <> struct RowLoad<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 load(const __nv_bfloat16* row, int t) {
+        uint2 u = ld_stream_u2(row + 4 * t);
+        return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    }
+};
+
+template <typename T, bool NORM>
+__global__ void __launch_bounds__(SEG_THREADS)
+segsum_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels,
+                      const int64_t* __restrict__ states, int64_t n_rows, int64_t rows_per_cta,
+                      int64_t class_base, int num_classes, int num_states, int K, int slab_keys,
+                      float* __restrict__ part_sums, long long* __restrict__ part_counts) {
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    float4* acc = reinterpret_cast<float4*>(seg_smem);                       // [slab_keys][128] float4
+    int* cnt = reinterpret_cast<int*>(seg_smem + (size_t)slab_keys * D * sizeof(float));   // [slab_keys]
+    float* red = reinterpret_cast<float*>(cnt + slab_keys);                  // [2][4][SEG_UNROLL]
+    const int t = threadIdx.x;
+    const int k0 = blockIdx.y * slab_keys;
+    const int nk = min(slab_keys, K - k0);
+    for (int i = t; i < slab_keys * (D / 4); i += SEG_THREADS) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < slab_keys) cnt[t] = 0;
+    __syncthreads();
+
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t r1 = min(n_rows, r0 + rows_per_cta);
+    int buf = 0;
+    for (int64_t r = r0; r < r1; r += SEG_UNROLL) {
+        int key[SEG_UNROLL];
+        float4 v[SEG_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SEG_UNROLL; ++u) {
+            key[u] = -1;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int64_t row = r + u;
+            if (row < r1) {
+                const int64_t c = __ldg(labels + row) - class_base;
+                int64_t k = -1;
+                if (c >= 0 && c < num_classes) {
+                    if (states != nullptr) {
+                        const int64_t s = __ldg(states + row);
+                        if (s >= 0 && s < num_states) k = c * num_states + s;
+                    } else {
+                        k = c;
+                    }
+                }
+                k -= k0;
+                if (k >= 0 && k < nk) key[u] = (int)k;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SEG_UNROLL; ++u)
+            if (key[u] >= 0) v[u] = RowLoad<T>::load(x + (r + u) * D, t);
+        if (NORM) {
+            float ss[SEG_UNROLL];
+#pragma unroll
+            for (int u = 0; u < SEG_UNROLL; ++u) {
+                ss[u] = v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w;
+                ss[u] = warp_sum(ss[u]);
+            }
+            if ((t & 31) == 0) {
+#pragma unroll
+                for (int u = 0; u < SEG_UNROLL; ++u) red[(buf * 4 + (t >> 5)) * SEG_UNROLL + u] = ss[u];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < SEG_UNROLL; ++u) {
+                const float tot = red[(buf * 4 + 0) * SEG_UNROLL + u] + red[(buf * 4 + 1) * SEG_UNROLL + u] +
+                                  red[(buf * 4 + 2) * SEG_UNROLL + u] + red[(buf * 4 + 3) * SEG_UNROLL + u];
+                const float inv = 1.0f / fmaxf(sqrtf(tot), NORM_EPS);
+                v[u].x *= inv; v[u].y *= inv; v[u].z *= inv; v[u].w *= inv;
+            }
+            buf ^= 1;
+        }
+#pragma unroll
+        for (int u = 0; u < SEG_UNROLL; ++u) {
+            if (key[u] >= 0) {
+                float4 a = acc[key[u] * (D / 4) + t];
+                a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+                acc[key[u] * (D / 4) + t] = a;
+                if (t == 0) cnt[key[u]] += 1;
+            }
+        }
+    }
+    // fold the 8 CTAs of the cluster in rank order through distributed shared memory
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    const unsigned rank = cluster.block_rank();
+    const int cluster_id = blockIdx.x / SEG_CLUSTER;
+    // rank r owns float4 columns [16r, 16r+16) of every key
+    for (int i = t; i < nk * 16; i += SEG_THREADS) {
+        const int k = i >> 4, c4 = (int)rank * 16 + (i & 15);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < SEG_CLUSTER; ++q) {
+            const float4* remote = cluster.map_shared_rank(acc, q);
+            const float4 a = remote[k * (D / 4) + c4];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+        reinterpret_cast<float4*>(part_sums)[((size_t)cluster_id * K + k0 + k) * (D / 4) + c4] = s;
+    }
+    if (rank == 0 && t < nk) {
+        long long c = 0;
+        for (int q = 0; q < SEG_CLUSTER; ++q) c += cluster.map_shared_rank(cnt, q)[t];
+        part_counts[(size_t)cluster_id * K + k0 + t] = c;
+    }
+    cluster.sync();     // keep smem alive until every peer has read it
+}
+
+// pass 2: fixed-order sum over clusters.  grid = K, 512 threads = 128 float4 columns x 4 lanes
+// of cluster partials; lane g sums clusters g, g+4, ... then the 4 lanes fold in order.
+__global__ void __launch_bounds__(512)
+segsum_final_kernel(const float* __restrict__ part_sums, const long long* __restrict__ part_counts,
+                    int n_clusters, int K, float* __restrict__ sums, int64_t* __restrict__ counts) {
+    __shared__ float4 fold[4][128];
+    const int k = blockIdx.x, c4 = threadIdx.x & 127, g = threadIdx.x >> 7;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = g; q < n_clusters; q += 4) {
+        const float4 a = reinterpret_cast<const float4*>(part_sums)[((size_t)q * K + k) * (D / 4) + c4];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    fold[g][c4] = s;
+    __syncthreads();
+    if (g == 0) {
+        float4 r = fold[0][c4];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { r.x += fold[q][c4].x; r.y += fold[q][c4].y; r.z += fold[q][c4].z; r.w += fold[q][c4].w; }
+        reinterpret_cast<float4*>(sums)[(size_t)k * (D / 4) + c4] = r;
+    }
+    if (threadIdx.x == 0) {
+        long long c = 0;
+        for (int q = 0; q < n_clusters; ++q) c += part_counts[(size_t)q * K + k];
+        counts[k] = c;
+    }
+}
+
+// means[k] = sums[k]/counts[k] (count>0 only); optional per-group (class) totals over `group` keys.
+__global__ void __launch_bounds__(128)
+segmean_kernel(const float* __restrict__ sums, const int64_t* __restrict__ counts, int K,
+               float* __restrict__ means, int group, float* __restrict__ class_means,
+               int64_t* __restrict__ class_counts) {
+    const int c4 = threadIdx.x;
+    if (class_means == nullptr && class_counts == nullptr) {
+        const int k = blockIdx.x;
+        const int64_t n = counts[k];
+        if (n > 0 && means != nullptr) {
+            float4 s = reinterpret_cast<const float4*>(sums)[(size_t)k * (D / 4) + c4];
+            const float fn = (float)n;
+            reinterpret_cast<float4*>(means)[(size_t)k * (D / 4) + c4] = make_float4(s.x / fn, s.y / fn, s.z / fn, s.w / fn);
+        }
+        return;
+    }
+    const int gidx = blockIdx.x;            // one CTA per group (class)
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t ntot = 0;
+    for (int j = 0; j < group; ++j) {
+        const int k = gidx * group + j;
+        const int64_t n = counts[k];
+        if (n > 0) {
+            const float4 s = reinterpret_cast<const float4*>(sums)[(size_t)k * (D / 4) + c4];
+            tot.x += s.x; tot.y += s.y; tot.z += s.z; tot.w += s.w;
+            ntot += n;
+            if (means != nullptr) {
+                const float fn = (float)n;
+                reinterpret_cast<float4*>(means)[(size_t)k * (D / 4) + c4] = make_float4(s.x / fn, s.y / fn, s.z / fn, s.w / fn);
+            }
+        }
+    }
+    if (ntot > 0 && class_means != nullptr) {
+        const float fn = (float)ntot;
+        reinterpret_cast<float4*>(class_means)[(size_t)gidx * (D / 4) + c4] = make_float4(tot.x / fn, tot.y / fn, tot.z / fn, tot.w / fn);
+    }
+    if (c4 == 0 && class_counts != nullptr) class_counts[gidx] = ntot;
+}
+
+static void seg_plan(int64_t n_rows, int64_t K, int* n_clusters, int* n_slabs, int* slab_keys, int64_t* rows_per_cta) {
+    *slab_keys = (int)(K < SEG_SLAB_KEYS ? K : SEG_SLAB_KEYS);
+    *n_slabs = (int)((K + *slab_keys - 1) / *slab_keys);
+    // aim for >= 256 rows per CTA, at most ~4 CTAs per SM across all slabs
+    int64_t max_ctas = (int64_t)NUM_SMS * 4 / *n_slabs;
+    if (max_ctas < SEG_CLUSTER) max_ctas = SEG_CLUSTER;
+    int64_t ctas = (n_rows + 255) / 256;
+    if (ctas > max_ctas) ctas = max_ctas;
+    int64_t ncl = (ctas + SEG_CLUSTER - 1) / SEG_CLUSTER;
+    if (ncl < 1) ncl = 1;
+    *n_clusters = (int)ncl;
+    int64_t total = ncl * SEG_CLUSTER;
+    int64_t rpc = (n_rows + total - 1) / total;
+    rpc = (rpc + SEG_UNROLL - 1) / SEG_UNROLL * SEG_UNROLL;
+    if (rpc < SEG_UNROLL) rpc = SEG_UNROLL;
+    *rows_per_cta = rpc;
+}
+
+template <typename T, bool NORM>
+static int seg_launch(const void* x, const int64_t* labels, const int64_t* states, int64_t n_rows,
+                      int64_t class_base, int num_classes, int num_states, int K, int n_clusters,
+                      int n_slabs, int slab_keys, int64_t rows_per_cta, float* part_sums,
+                      long long* part_counts, cudaStream_t st) {
+    const size_t smem = (size_t)slab_keys * D * sizeof(float) + (size_t)slab_keys * sizeof(int) +
+                        2 * 4 * SEG_UNROLL * sizeof(float);
+    auto kern = segsum_partial_kernel<T, NORM>;
+    TEAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_clusters * SEG_CLUSTER, n_slabs, 1);
+    cfg.blockDim = dim3(SEG_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = SEG_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const T* xp = reinterpret_cast<const T*>(x);
+    TEAM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, xp, labels, states, n_rows, rows_per_cta, class_base,
+                                       num_classes, num_states, K, slab_keys, part_sums, part_counts));
+    return TEAM_OK;
+}
+
+}  // namespace team
+
+using namespace team;
+
+extern "C" size_t team_segsum_workspace_bytes(int64_t n_rows, int64_t num_keys) {
+    int ncl, nsl, sk;
+    int64_t rpc;
+    if (num_keys < 1) num_keys = 1;
+    seg_plan(n_rows, num_keys, &ncl, &nsl, &sk, &rpc);
+    return align_up((size_t)ncl * num_keys * D * sizeof(float), 256) + align_up((size_t)ncl * num_keys * sizeof(long long), 256);
+}
+
+extern "C" int team_segsum(const void* x, int x_dtype, const int64_t* labels, const int64_t* states,
+                           int64_t n_rows, int64_t class_base, int64_t num_classes, int64_t num_states,
+                           int normalize_rows, float* sums, int64_t* counts, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+    TEAM_REQUIRE(n_rows >= 0 && num_classes >= 1, "team_segsum: n_rows=%lld num_classes=%lld", (long long)n_rows, (long long)num_classes);
+    TEAM_REQUIRE(x_dtype == TEAM_DTYPE_F32 || x_dtype == TEAM_DTYPE_BF16, "team_segsum: bad dtype %d", x_dtype);
+    TEAM_REQUIRE(sums != nullptr && counts != nullptr && (labels != nullptr || n_rows == 0), "team_segsum: null output/labels");
+    if (states == nullptr) num_states = 1;
+    TEAM_REQUIRE(num_states >= 1 && num_classes * num_states <= (1 << 20), "team_segsum: too many keys");
+    const int K = (int)(num_classes * num_states);
+    int ncl, nsl, sk;
+    int64_t rpc;
+    seg_plan(n_rows, K, &ncl, &nsl, &sk, &rpc);
+    const size_t need = team_segsum_workspace_bytes(n_rows, K);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("team_segsum: workspace %zu < %zu", workspace_bytes, need);
+        return TEAM_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* part_sums = reinterpret_cast<float*>(workspace);
+    long long* part_counts = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) +
+                                                          align_up((size_t)ncl * K * D * sizeof(float), 256));
+    int rc;
+    if (x_dtype == TEAM_DTYPE_F32) {
+        rc = normalize_rows ? seg_launch<float, true>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st)
+                            : seg_launch<float, false>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st);
+    } else {
+        rc = normalize_rows ? seg_launch<__nv_bfloat16, true>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st)
+                            : seg_launch<__nv_bfloat16, false>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st);
+    }
+    if (rc != TEAM_OK) return rc;
+    segsum_final_kernel<<<K, 512, 0, st>>>(part_sums, part_counts, ncl, K, sums, counts);
+    TEAM_LAUNCH_CHECK("segsum_final_kernel");
+    return TEAM_OK;
+}
+
+extern "C" int team_segmean_finalize(const float* sums, const int64_t* counts, int64_t num_keys,
+                                     float* means, int64_t group, float* class_means,
+                                     int64_t* class_counts, void* stream) {
+    TEAM_REQUIRE(num_keys >= 1 && sums && counts, "team_segmean_finalize: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (class_means == nullptr && class_counts == nullptr) {
+        segmean_kernel<<<(int)num_keys, 128, 0, st>>>(sums, counts, (int)num_keys, means, 1, nullptr, nullptr);
+    } else {
+        TEAM_REQUIRE(group >= 1 && num_keys % group == 0, "team_segmean_finalize: group %lld does not divide %lld", (long long)group, (long long)num_keys);
+        segmean_kernel<<<(int)(num_keys / group), 128, 0, st>>>(sums, counts, (int)num_keys, means, (int)group, class_means, class_counts);
+    }
+    TEAM_LAUNCH_CHECK("segmean_kernel");
+    return TEAM_OK;
+}

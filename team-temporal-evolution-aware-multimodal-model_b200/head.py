@@ -1,0 +1,182 @@
+"""Host side of the fusion head: ``torch.autograd.Function`` over ``team_head_tri_fwd`` /
+``team_head_tri_bwd`` (the C ABI in include/team_b200.h).
+
+Mirrors what ``Proof_Net.forward_tri_modal`` (utils/inc_net.py:528-580) and
+``Learner.forward_for_classification`` (models/proof.py:519-536) compute, with the same
+parameter tensors.  torch only provides device memory, the stream and the autograd tape.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import capi
+
+MODE_F32, MODE_BF16 = capi.MODE_F32, capi.MODE_BF16
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor, dev) -> torch.Tensor:
+    t = t.detach()
+    if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(device=dev, dtype=torch.float32).contiguous()
+    return t
+
+
+class HeadParamPack:
+    """Flat, ordered view of the head parameters (reference state_dict names)."""
+
+    def __init__(self, w_img: Sequence[torch.Tensor], b_img, w_text, b_text, w_state, b_state,
+                 prompts: Sequence[torch.Tensor], state_emb, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b):
+        self.T = len(w_img)
+        if not (1 <= self.T <= capi.MAX_TASKS):
+            raise ValueError(f"number of tasks {self.T} out of [1,{capi.MAX_TASKS}]")
+        for lst in (b_img, w_text, b_text, w_state, b_state, prompts):
+            if len(lst) != self.T:
+                raise ValueError("per-task parameter lists must have equal length")
+        self.ppt = int(prompts[0].shape[0])
+        self.flat: List[torch.Tensor] = (list(w_img) + list(b_img) + list(w_text) + list(b_text) +
+                                         list(w_state) + list(b_state) + list(prompts) +
+                                         [state_emb, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b])
+
+    @staticmethod
+    def from_state_dict(p: Dict[str, torch.Tensor]) -> "HeadParamPack":
+        T = 0
+        while f"projs_img.{T}.MLP.0.weight" in p:
+            T += 1
+        g = lambda fmt: [p[fmt.format(t)] for t in range(T)]
+        return HeadParamPack(
+            g("projs_img.{}.MLP.0.weight"), g("projs_img.{}.MLP.0.bias"),
+            g("projs_text.{}.MLP.0.weight"), g("projs_text.{}.MLP.0.bias"),
+            g("projs_state.{}.MLP.0.weight"), g("projs_state.{}.MLP.0.bias"),
+            g("context_prompts.{}"), p["state_embedder.state_embeddings.weight"],
+            p["sel_attn.w_qs.weight"], p["sel_attn.w_ks.weight"], p["sel_attn.w_vs.weight"],
+            p["sel_attn.fc.weight"], p["sel_attn.fc.bias"],
+            p["sel_attn.layer_norm.weight"], p["sel_attn.layer_norm.bias"])
+
+
+def _fill_weights(T: int, ppt: int, flat: Sequence[torch.Tensor], protos: torch.Tensor) -> capi.HeadWeights:
+    hw = capi.HeadWeights()
+    hw.num_tasks, hw.prompts_per_task = T, ppt
+    names = ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts")
+    for k, n in enumerate(names):
+        arr = getattr(hw, n)
+        for t in range(T):
+            arr[t] = flat[k * T + t].data_ptr()
+    tail = flat[7 * T:]
+    for n, t in zip(("state_emb", "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b"), tail):
+        setattr(hw, n, t.data_ptr())
+    hw.prototypes = protos.data_ptr()
+    hw.num_classes = int(protos.shape[0])
+    return hw
+
+
+class _TriModalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, text, state_ids, protos, text_cls, mode, T, ppt, *params):
+        capi.require_device()
+        dev = image.device
+        if not image.is_cuda:
+            raise capi.TeamB200Error("forward_tri_modal needs CUDA tensors (no CPU fallback)")
+        B = image.shape[0]
+        image = _f32c(image, dev); text = _f32c(text, dev); protos = _f32c(protos, dev)
+        sid = state_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+        if image.shape != (B, capi.D) or text.shape != (B, capi.D) or sid.shape != (B,):
+            raise ValueError("image/text must be [B,512] with per-sample text, state_ids [B]")
+        flat = [_f32c(p, dev) for p in params]
+        hw = _fill_weights(T, ppt, flat, protos)
+        n_cls = 0 if text_cls is None else int(text_cls.shape[0])
+        if text_cls is not None:
+            text_cls = _f32c(text_cls, dev)
+        L = capi.lib()
+        nbytes = L.team_head_workspace_bytes(B, hw.num_classes, T * ppt, n_cls, mode)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        outs = torch.empty((4, B, capi.D), dtype=torch.float32, device=dev)
+        logits = torch.empty((B, n_cls), dtype=torch.float32, device=dev) if n_cls else None
+        amax = torch.empty((B,), dtype=torch.int64, device=dev) if n_cls else None
+        capi.check(L.team_head_tri_fwd(
+            C.byref(hw), mode, B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
+            text_cls.data_ptr() if n_cls else None, n_cls,
+            outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+            logits.data_ptr() if n_cls else None, amax.data_ptr() if n_cls else None,
+            ws.data_ptr(), nbytes, _stream_ptr()), "team_head_tri_fwd")
+        ctx.hold = (image, text, sid, protos, flat, ws)
+        ctx.meta = (mode, T, ppt, B, nbytes)
+        ctx.set_materialize_grads(True)
+        res = (outs[0], outs[1].view(B, 1, capi.D), outs[2], outs[3])
+        if n_cls:
+            ctx.mark_non_differentiable(logits, amax)
+            return res + (logits, amax)
+        return res
+
+    @staticmethod
+    def backward(ctx, g_img, g_txt, g_st, g_pr, *unused):
+        image, text, sid, protos, flat, ws = ctx.hold
+        mode, T, ppt, B, nbytes = ctx.meta
+        dev = image.device
+        hw = _fill_weights(T, ppt, flat, protos)
+        P = T * ppt
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        g = {"w_img": mk(capi.D, capi.D), "b_img": mk(capi.D), "w_text": mk(capi.D, capi.D), "b_text": mk(capi.D),
+             "w_state": mk(capi.D, capi.D), "b_state": mk(capi.D), "prompts": mk(max(P, 1), capi.D),
+             "state_emb": mk(capi.NUM_STATES, capi.D), "w_q": mk(capi.D, capi.D), "w_k": mk(capi.D, capi.D),
+             "w_v": mk(capi.D, capi.D), "w_fc": mk(capi.D, capi.D), "b_fc": mk(capi.D),
+             "ln_g": mk(capi.D), "ln_b": mk(capi.D)}
+        hg = capi.HeadGrads()
+        for k, v in g.items():
+            setattr(hg, k, v.data_ptr())
+        cots = [_f32c(x.reshape(B, capi.D), dev) for x in (g_img, g_txt, g_st, g_pr)]
+        capi.check(capi.lib().team_head_tri_bwd(
+            C.byref(hw), mode, B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
+            cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr(),
+            C.byref(hg), ws.data_ptr(), nbytes, _stream_ptr()), "team_head_tri_bwd")
+        need = ctx.needs_input_grad[8:]
+        out: List[Optional[torch.Tensor]] = []
+        names = ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state")
+        for k, n in enumerate(names):           # W = sum_t W_t  =>  dW_t = dW for every unfrozen t
+            for t in range(T):
+                out.append(g[n] if need[k * T + t] else None)
+        for t in range(T):
+            out.append(g["prompts"][t * ppt:(t + 1) * ppt] if need[6 * T + t] else None)
+        for i, n in enumerate(("state_emb", "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b")):
+            out.append(g[n] if need[7 * T + i] else None)
+        return (None,) * 8 + tuple(out)
+
+
+def forward_tri_modal(pack: HeadParamPack, image: torch.Tensor, text: torch.Tensor,
+                      state_ids: torch.Tensor, img_prototypes: torch.Tensor, *,
+                      text_cls: Optional[torch.Tensor] = None, mode: int = MODE_F32):
+    """(image[B,512], text[B,1,512], state[B,512], proto[B,512]) [+ (cls_logits[B,Tc], argmax[B])].
+    ``image``/``text`` are post-CLIP 512-d features (per-sample text)."""
+    return _TriModalFn.apply(image, text, state_ids, img_prototypes, text_cls, mode, pack.T, pack.ppt,
+                             *pack.flat)
+
+
+def encode(pack: HeadParamPack, which: str, x: Optional[torch.Tensor], img_prototypes: Optional[torch.Tensor] = None,
+           normalize: bool = False, mode: int = MODE_F32) -> torch.Tensor:
+    """encode_image / encode_text / encode_state / encode_prototpyes without autograd
+    (utils/inc_net.py:401-422, :518-526)."""
+    capi.require_device()
+    idx = {"image": 0, "text": 1, "state": 2, "prototypes": 3}[which]
+    dev = pack.flat[0].device
+    flat = [_f32c(p, dev) for p in pack.flat]
+    protos = _f32c(img_prototypes, dev) if img_prototypes is not None else torch.zeros((1, capi.D), device=dev)
+    hw = _fill_weights(pack.T, pack.ppt, flat, protos)
+    if idx == 3:
+        n, xp = protos.shape[0], None
+    elif idx == 2:
+        x = x.detach().to(device=dev, dtype=torch.int64).contiguous(); n, xp = x.shape[0], x.data_ptr()
+    else:
+        x = _f32c(x, dev); n, xp = x.shape[0], x.data_ptr()
+    L = capi.lib()
+    nbytes = L.team_head_workspace_bytes(1, hw.num_classes, pack.T * pack.ppt, 0, mode)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    out = torch.empty((n, capi.D), dtype=torch.float32, device=dev)
+    capi.check(L.team_head_encode(C.byref(hw), mode, idx, xp, n, int(normalize), out.data_ptr(),
+                                  ws.data_ptr(), nbytes, _stream_ptr()), "team_head_encode")
+    return out

@@ -1,0 +1,109 @@
+"""Thin torch-tensor wrappers over the C ABI for the bandwidth-bound ops of the path:
+the keyed segmented sum (prototype build) and the cosine classifier.
+
+torch is used only for device memory and the current stream; all arithmetic happens in
+``libteam_b200.so``.  Inputs must be CUDA tensors - there is no CPU fallback."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import capi
+
+
+def _stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_rows(x: torch.Tensor, name: str):
+    if not x.is_cuda:
+        raise capi.TeamB200Error(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if x.dim() != 2 or x.shape[1] != capi.D:
+        raise ValueError(f"{name} must be [N,{capi.D}], got {tuple(x.shape)}")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"{name} must be float32 or bfloat16, got {x.dtype}")
+    return x.contiguous()
+
+
+def _dt(x):
+    return capi.DTYPE_F32 if x.dtype == torch.float32 else capi.DTYPE_BF16
+
+
+def keyed_sums(x: torch.Tensor, labels: torch.Tensor, states: Optional[torch.Tensor] = None, *,
+               class_base: int = 0, num_classes: int, num_states: int = capi.NUM_STATES,
+               normalize_rows: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Deterministic keyed segmented sum.  Returns (sums [K,512] fp32, counts [K] int64) with
+    K = num_classes * (num_states if states is given else 1); key = (label-class_base)*S + state.
+    Reference: models/proof.py:258-276, models/simplecil.py:48-55, utils/state_distance.py:98-103."""
+    capi.require_device()
+    x = _chk_rows(x, "x")
+    n = x.shape[0]
+    labels = labels.to(device=x.device, dtype=torch.int64).contiguous()
+    if labels.shape != (n,):
+        raise ValueError("labels must be [N]")
+    if states is not None:
+        states = states.to(device=x.device, dtype=torch.int64).contiguous()
+        if states.shape != (n,):
+            raise ValueError("states must be [N]")
+    S = num_states if states is not None else 1
+    K = num_classes * S
+    sums = torch.empty((K, capi.D), dtype=torch.float32, device=x.device)
+    counts = torch.empty((K,), dtype=torch.int64, device=x.device)
+    L = capi.lib()
+    ws_bytes = L.team_segsum_workspace_bytes(n, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    capi.check(L.team_segsum(x.data_ptr(), _dt(x), labels.data_ptr(),
+                             states.data_ptr() if states is not None else None,
+                             n, class_base, num_classes, S, int(normalize_rows),
+                             sums.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr()),
+               "team_segsum")
+    return sums, counts
+
+
+def keyed_means(sums: torch.Tensor, counts: torch.Tensor, out: Optional[torch.Tensor] = None,
+                group: int = 0, class_out: Optional[torch.Tensor] = None):
+    """means[k] = sums[k]/counts[k] where counts[k] > 0 (other rows of ``out`` untouched).
+    With ``group`` > 0 also folds every ``group`` consecutive keys into per-class means
+    (written into ``class_out`` rows with a non-zero total) and returns the class counts."""
+    capi.require_device()
+    K = sums.shape[0]
+    if out is None:
+        out = torch.zeros_like(sums)
+    L = capi.lib()
+    if group:
+        ng = K // group
+        if class_out is None:
+            class_out = torch.zeros((ng, capi.D), dtype=torch.float32, device=sums.device)
+        ccounts = torch.empty((ng,), dtype=torch.int64, device=sums.device)
+        capi.check(L.team_segmean_finalize(sums.data_ptr(), counts.data_ptr(), K, out.data_ptr(), group,
+                                           class_out.data_ptr(), ccounts.data_ptr(), _stream_ptr()),
+                   "team_segmean_finalize")
+        return out, class_out, ccounts
+    capi.check(L.team_segmean_finalize(sums.data_ptr(), counts.data_ptr(), K, out.data_ptr(), 1,
+                                       None, None, _stream_ptr()), "team_segmean_finalize")
+    return out
+
+
+def cosine_logits(x: torch.Tensor, weight: torch.Tensor, sigma: Optional[torch.Tensor] = None, *,
+                  want_logits: bool = True, want_argmax: bool = False):
+    """sigma * normalize(x) @ normalize(weight).T (+ first-index argmax), one pass over x.
+    Reference: convs/linears.py:51-61; models/proof.py:526-535."""
+    capi.require_device()
+    x = _chk_rows(x, "x")
+    w = weight.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    if w.dim() != 2 or w.shape[1] != capi.D:
+        raise ValueError("weight must be [C,512]")
+    n, c = x.shape[0], w.shape[0]
+    logits = torch.empty((n, c), dtype=torch.float32, device=x.device) if want_logits else None
+    amax = torch.empty((n,), dtype=torch.int64, device=x.device) if want_argmax else None
+    sg = None
+    if sigma is not None:
+        sg = sigma.detach().to(device=x.device, dtype=torch.float32).reshape(-1)[:1].contiguous()
+    capi.check(capi.lib().team_cosine_logits(
+        x.data_ptr(), _dt(x), n, w.data_ptr(), c, sg.data_ptr() if sg is not None else None,
+        logits.data_ptr() if logits is not None else None,
+        amax.data_ptr() if amax is not None else None, _stream_ptr()), "team_cosine_logits")
+    if want_logits and want_argmax:
+        return logits, amax
+    return logits if want_logits else amax

@@ -1,0 +1,92 @@
+"""GPU parity of the fusion head (forward_tri_modal fwd + bwd, classification logits) through
+the C ABI against the CPU oracle and the reference-generated golden vectors.
+fp32 mode bar: outputs and gradients <= 1e-5 relative (norm-wise), argmax exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import synth
+from oracle import team_oracle as O
+from oracle.cases import CASES, case_inputs, grad_subsample
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.detach().double().cpu(); b = torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def run_head(params, batch, protos, cots, mode, with_cls=True):
+    from team_b200 import head
+    dev = torch.device("cuda")
+    p = {k: v.to(dev).requires_grad_(v.is_floating_point() and v.dim() > 0) for k, v in params.items()}
+    pack = head.HeadParamPack.from_state_dict(p)
+    outs = head.forward_tri_modal(pack, batch["image"].to(dev), batch["text"].to(dev), batch["state"].to(dev),
+                                  protos.to(dev), text_cls=batch["text_cls"].to(dev) if with_cls else None, mode=mode)
+    names = O.trainable_names(params)
+    grads = torch.autograd.grad(outs[:4], [p[n] for n in names], grad_outputs=[c.to(dev) for c in cots],
+                                allow_unused=True)
+    return outs, dict(zip(names, grads))
+
+
+@pytest.mark.parametrize("name", ["head_T1_B6", "head_T3_B5_5state", "head_T10_B4"])
+def test_head_f32_vs_golden(name, golden):
+    from team_b200 import head
+    case, g = CASES[name], golden(name)
+    ci = case_inputs(case)
+    outs, grads = run_head(ci["params"], ci["batch"], ci["protos"], ci["cots"], head.MODE_F32)
+    for key, o in zip(("image", "text", "state", "proto"), outs[:4]):
+        assert tuple(o.shape) == g[key].shape, key
+        assert rel(o, g[key]) < 1e-5, (key, rel(o, g[key]))
+    assert rel(outs[4], g["cls_logits"]) < 1e-5
+    assert np.array_equal(outs[5].cpu().numpy(), g["cls_logits"].argmax(1))
+    for n, gr in grads.items():
+        e = rel(grad_subsample(gr), g["grad:" + n])
+        assert e < 2e-5, (n, e)
+
+
+@pytest.mark.parametrize("T,B,five", [(1, 64, False), (10, 96, True), (4, 300, False)])
+def test_head_f32_vs_oracle(T, B, five):
+    from team_b200 import head
+    C = 2 * T
+    params = synth.make_params(T, seed=100 + T)
+    protos = synth.make_prototypes(C, seed=7)
+    batch = synth.make_batch(B, C, step=T, five_state=five)
+    cots = synth.make_cotangents(B, step=T)
+    outs, grads = run_head(params, batch, protos, cots, head.MODE_F32)
+    p64 = {k: v.double().requires_grad_(v.dim() > 0) for k, v in params.items()}
+    ref = O.forward_tri_modal(p64, batch["image"].double(), batch["text"].double(), batch["state"], protos.double())
+    for key, o, r in zip(("image", "text", "state", "proto"), outs[:4], ref[:4]):
+        assert rel(o, r) < 1e-5, (key, rel(o, r))
+    names = O.trainable_names(params)
+    gref = torch.autograd.grad(ref[:4], [p64[n] for n in names], grad_outputs=[c.double() for c in cots])
+    for n, gr in zip(names, gref):
+        assert rel(grads[n], gr) < 2e-5, (n, rel(grads[n], gr))
+    logits = O.forward_for_classification({k: v.detach() for k, v in p64.items()}, batch["image"].double(),
+                                          batch["text_cls"].double())
+    assert rel(outs[4], logits) < 1e-5
+    top2 = logits.topk(2, dim=1).values if C > 1 else None
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-5
+    assert torch.equal(outs[5].cpu()[safe], logits.argmax(1)[safe])
+    # deterministic: a second run is bit-identical
+    outs2, grads2 = run_head(params, batch, protos, cots, head.MODE_F32)
+    for a, b in zip(outs[:4], outs2[:4]):
+        assert torch.equal(a, b)
+    for n in names:
+        assert torch.equal(grads[n], grads2[n]), n
+
+
+def test_encode_paths():
+    from team_b200 import head
+    T, C = 3, 6
+    params = synth.make_params(T, seed=5)
+    dev = torch.device("cuda")
+    pack = head.HeadParamPack.from_state_dict({k: v.to(dev) for k, v in params.items()})
+    batch = synth.make_batch(33, C, step=9)
+    protos = synth.make_prototypes(C, seed=3)
+    for norm in (False, True):
+        assert rel(head.encode(pack, "image", batch["image"].to(dev), normalize=norm), O.encode_image(batch["image"], params, norm)) < 1e-5
+        assert rel(head.encode(pack, "text", batch["text"].to(dev), normalize=norm), O.encode_text(batch["text"], params, norm)) < 1e-5
+        assert rel(head.encode(pack, "state", batch["state"].to(dev), normalize=norm), O.encode_state(batch["state"], params, norm)) < 1e-5
+        assert rel(head.encode(pack, "prototypes", None, protos.to(dev), normalize=norm), O.encode_prototypes(protos, params, norm)) < 1e-5
