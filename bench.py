@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py - TEAM head fwd+bwd throughput on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference algorithm (oracle port) on the host CPU
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): PROOF/TEAM
+head fwd+bwd, 10 incremental tasks (C=20 classes, P=100 prompts, L=123 tokens), batch 1024
+per GPU, synthetic IIMinsects202-shaped 512-d features, reference-initialised weights.
+One step = no-grad classification logits (models/proof.py:415-418) + forward_tri_modal
+(:424-425) + VJP with fixed N(0,1) cotangents on the four feature outputs (stands for :444),
+plus, for N>1, the NCCL all-reduce of the flat 1.85 M-element head-gradient bucket.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "team_head_fwd_bwd_samples_per_sec"
+UNIT = "samples/s"
+NUM_TASKS = 10
+ROT = 64                         # rotating input slots: 64 x (2 x 2 MiB + cotangents 8 MiB) >> 126 MB L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="team", choices=["team", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
+    ap.add_argument("--tasks", type=int, default=NUM_TASKS)
+    ap.add_argument("--mode", default=os.environ.get("TEAM_BENCH_MODE", "bf16"), choices=["bf16", "f32"])
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_step_fn(tasks: int, batch: int):
+    """The reference algorithm on the host CPU: oracle port (torch CPU fp32, as-written math:
+    replicated shared rows, full LxL attention) - the same step definition as the GPU arm."""
+    import torch
+    from oracle import synth
+    from oracle import team_oracle as O
+    C = synth.CLASSES_PER_TASK * tasks
+    params = synth.make_params(tasks, seed=42, perturb_ln=False)
+    names = O.trainable_names(params)
+    p = {k: (v.clone().requires_grad_(k in names)) for k, v in params.items()}
+    protos = synth.make_prototypes(C)
+    b = synth.make_batch(batch, C, step=0)
+    cots = synth.make_cotangents(batch, step=0)
+
+    def step():
+        return O.head_step_fwd_bwd(p, b, protos, cots, names)
+    return step
+
+
+def time_cpu(tasks: int, sample_batch: int, steps: int, warmup: int):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fn = cpu_reference_step_fn(tasks, sample_batch)
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return {"value": sample_batch / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of a {sample_batch}-sample batch (T={tasks}, C={2 * tasks}, L={3 + 12 * tasks}), "
+                      f"oracle port of the reference head in torch-CPU fp32, {cores} threads, {dt * 1e3:.1f} ms/step"}, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(a.batch, 256)
+    cb, dt = time_cpu(a.tasks, sample, a.steps, max(1, min(a.warmup, 2)))
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": max(1, min(a.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"TEAM head fwd+bwd, T={a.tasks}, batch {sample} sample of {a.batch} per step, CPU",
+                       "tasks": a.tasks, "batch_per_step": sample},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_team(a):
+    import torch
+    import torch.distributed as dist
+    from oracle import synth                    # input generation only
+    from team_b200 import capi, head
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    capi.require_device()
+    L = capi.lib()
+    mode = head.MODE_BF16 if a.mode == "bf16" else head.MODE_F32
+    T, B = a.tasks, a.batch
+    C = synth.CLASSES_PER_TASK * T
+    warmup = max(a.warmup, 3)
+
+    params = synth.make_params(T, seed=42, perturb_ln=False)      # reference initialisers, same on every rank
+    pdev = {k: v.to(dev) for k, v in params.items()}
+    pack = head.HeadParamPack.from_state_dict(pdev)
+    protos = synth.make_prototypes(C).to(dev)
+    # rotating inputs (distinct per rank), resident in HBM, total >> L2
+    rot = min(ROT, max(8, a.steps + warmup))
+    imgs, txts, sids, cots = [], [], [], []
+    for i in range(rot):
+        b = synth.make_batch(B, C, step=rank * 1000 + i)
+        imgs.append(b["image"].to(dev)); txts.append(b["text"].to(dev)); sids.append(b["state"].to(dev))
+        c = synth.make_cotangents(B, step=rank * 1000 + i)
+        cots.append([c[0].to(dev), c[1].reshape(B, 512).to(dev), c[2].to(dev), c[3].to(dev)])
+    text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
+    runner = head.HeadStepRunner(pack, protos, B, C, mode)
+    stream = torch.cuda.Stream(device=dev)
+
+    def eager_step(i):
+        j = i % rot
+        runner.step(imgs[j], txts[j], sids[j], text_cls, cots[j])
+
+    # launches per step (counted by the library itself)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        eager_step(0)
+        c0 = L.team_launch_count()
+        eager_step(1)
+        launches_per_step = L.team_launch_count() - c0
+    torch.cuda.synchronize()
+
+    graphs = None
+    if not a.no_graph:
+        graphs = []
+        with torch.cuda.stream(stream):
+            for j in range(rot):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    runner.step(imgs[j], txts[j], sids[j], text_cls, cots[j])
+                graphs.append(g)
+        torch.cuda.synchronize()
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % rot].replay()
+        else:
+            eager_step(i)
+        if world > 1:
+            dist.all_reduce(runner.flat_grads)        # gradient bucket: the only per-step collective
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(a.steps):
+            step(warmup + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / a.steps
+    value = world * B * a.steps / (ms / 1e3)
+
+    # ---- roofline of the dominant kernel: CUDA events around every launch of the GEMM kernels, K extra eager steps
+    pk = peaks()
+    roof = None
+    kind = 1 if mode == head.MODE_BF16 else 0
+    nprof = min(a.steps, 10)
+    tms, tfl, tby, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    with torch.cuda.stream(stream):
+        stats = {}
+        for k in (1, 0):
+            L.team_prof_enable(1)
+            for i in range(nprof):
+                eager_step(warmup + a.steps + i)
+            L.team_prof_enable(0)
+            capi.check(L.team_prof_collect(k, ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(tby), ctypes.byref(nl)),
+                       "team_prof_collect")
+            stats[k] = (tms.value, tfl.value, tby.value, nl.value)
+    dom = kind if stats[kind][3] > 0 else 0
+    dms, dfl, dby, dn = stats[dom]
+    if dn > 0 and dms > 0:
+        ach = dfl / (dms * 1e-3) / 1e12
+        peak = pk["tensor_sustained"]
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None,
+                "kernel": "gemm_bf16_tcgen05_kernel" if dom == 1 else "gemm_f32_kernel (fp32 FFMA; no tensor pipe)",
+                "launches_timed": dn, "avg_launch_us": dms * 1e3 / dn,
+                "share_of_step": (dms / nprof) / ms_per_step,
+                "algorithmic_flops_per_launch": dfl / dn,
+                "peak_source": f"bf16 dense sustained, {pk['src']}",
+                "how": f"CUDA events around each launch of the kernel on the launching stream, {nprof} extra eager steps "
+                       "after the timed region"}
+
+    # ---- end to end through the public API, host buffers in, scalar out
+    e2e = None
+    if not a.no_e2e:
+        names = ["projs_img", "projs_text", "projs_state"]
+        pe = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in pdev.items()}
+        for k in pe:      # freeze old tasks like freeze_projection_weight_new (utils/inc_net.py:494-507)
+            for n in names:
+                if k.startswith(n) and not k.startswith(f"{n}.{T - 1}."):
+                    pe[k].requires_grad_(False)
+            if k.startswith("context_prompts.") and k != f"context_prompts.{T - 1}":
+                pe[k].requires_grad_(False)
+            if "temporal_gcn" in k or k == "convnet.logit_scale":
+                pe[k].requires_grad_(False)
+        pack_e = head.HeadParamPack.from_state_dict(pe)
+        trainable = [v for v in pe.values() if v.requires_grad]
+        nrot = min(rot, 16)
+        h_img = [imgs[j].cpu().pin_memory() for j in range(nrot)]
+        h_txt = [txts[j].cpu().pin_memory() for j in range(nrot)]
+        h_sid = [sids[j].cpu().pin_memory() for j in range(nrot)]
+        h_lab = [synth.make_batch(B, C, step=rank * 1000 + j)["label"].pin_memory() for j in range(nrot)]
+
+        def e2e_step(i):
+            j = i % nrot
+            x = h_img[j].to(dev, non_blocking=True); t = h_txt[j].to(dev, non_blocking=True)
+            s = h_sid[j].to(dev, non_blocking=True); y = h_lab[j].to(dev, non_blocking=True)
+            for v in trainable:
+                v.grad = None
+            o = head.forward_tri_modal(pack_e, x, t, s, protos, text_cls=text_cls, mode=mode)
+            cj = cots[j]
+            torch.autograd.backward(o[:4], [cj[0], cj[1].view(B, 1, 512), cj[2], cj[3]])
+            if world > 1:
+                flat = torch.cat([v.grad.reshape(-1) for v in trainable])
+                dist.all_reduce(flat)
+            return int((o[5] == y).sum().item())          # D2H: number of correct predictions of the step
+
+        with torch.cuda.stream(stream):
+            for i in range(3):
+                e2e_step(i)
+            barrier()
+            ksteps = min(a.steps, 30)
+            t0 = time.perf_counter()
+            for i in range(ksteps):
+                e2e_step(3 + i)
+            barrier()
+            dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": world * B * ksteps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": B * 512 * 4 * 2 + B * 8 * 2, "d2h_bytes_per_step": 8,
+               "steps": ksteps, "api": "team_b200.head.forward_tri_modal + torch.autograd.backward (pinned host inputs)"}
+
+    cb = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb, _ = time_cpu(T, min(B, 256), 3, 1)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.mode, "data": "synthetic",
+                "config": {"workload": f"TEAM/PROOF head fwd+bwd (BASELINE configs[2]): T={T} tasks, C={C} classes, "
+                                       f"P={10 * T} prompts, L={3 + 12 * T} tokens, batch {B} per GPU",
+                           "tasks": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2",
+                           "cuda_graphs": graphs is not None,
+                           "alg_flops_per_sample_survey": 55.07e6},
+                "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches_per_step) * a.steps,
+                "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_team(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,12 @@ const char* team_last_error(void);
 int team_version(void);
 /* 0 if the current device is sm_100 (B200), TEAM_EUNSUPPORTED otherwise */
 int team_device_check(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long team_launch_count(void);
+/* optional per-launch CUDA-event timing of the GEMM kernels (kind 0 = fp32 FFMA GEMM, 1 = tcgen05 bf16 GEMM);
+ * team_prof_collect synchronises, sums and clears.  Not for use under stream capture. */
+int team_prof_enable(int on);
+int team_prof_collect(int kind, double* total_ms, double* total_flops, double* total_bytes, long long* launches);
 
 /* ------------------------------------------------------------------ prototype build
  * Deterministic, atomic-free keyed segmented sum (K9/K17).
@@ -167,7 +173,17 @@ int team_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha,
                   const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                   float* C, int64_t ldc, const float* bias, void* workspace,
                   size_t workspace_bytes, void* stream);
-/* C[M,N] fp32 = A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major), tcgen05 + TMA + TMEM. */
+/* tcgen05 + TMA + TMEM GEMM: C[M,N] fp32 = alpha * op(A) op(B) (+bias[N]) (+beta*C), bf16 operands.
+ * a_mn = 0: A stored [M,K] row-major (K-major); a_mn = 1: A stored [K,M] row-major (M-major).
+ * b_mn = 0: B stored [N,K] row-major (K-major); b_mn = 1: B stored [K,N] row-major (N-major).
+ * A_lo (optional) is the low half of a two-term bf16 split of an fp32 A: C = (A + A_lo) B. */
+int team_gemm_bf16(int a_mn, int b_mn, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+                   const void* A_lo, int64_t lda, const void* B, int64_t ldb, float beta, float* C,
+                   int64_t ldc, const float* bias, void* workspace, size_t workspace_bytes, void* stream);
+/* fp32 [rows,cols] -> bf16 hi (and optional lo residual) */
+int team_f32_to_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, void* hi, void* lo,
+                     int64_t ldd, void* stream);
+/* C[M,N] fp32 = A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major). */
 int team_gemm_bf16_nt(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                       const void* B, int64_t ldb, float* C, int64_t ldc, void* stream);
 

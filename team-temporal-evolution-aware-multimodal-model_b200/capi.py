@@ -56,6 +56,12 @@ def _declare(lib):
     lib.team_last_error.argtypes = []
     lib.team_version.restype = i32
     lib.team_device_check.restype = i32
+    lib.team_launch_count.restype = C.c_longlong
+    lib.team_launch_count.argtypes = []
+    lib.team_prof_enable.restype = i32
+    lib.team_prof_enable.argtypes = [i32]
+    lib.team_prof_collect.restype = i32
+    lib.team_prof_collect.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib.team_segsum_workspace_bytes.restype = sz
     lib.team_segsum_workspace_bytes.argtypes = [i64, i64]
     lib.team_segsum.restype = i32
@@ -68,6 +74,12 @@ def _declare(lib):
         lib.team_gemm_f32.restype = i32
         lib.team_gemm_f32.argtypes = [i32, i32, i64, i64, i64, C.c_float, vp, i64, vp, i64, C.c_float,
                                       vp, i64, vp, vp, sz, vp]
+    if hasattr(lib, "team_gemm_bf16"):
+        lib.team_gemm_bf16.restype = i32
+        lib.team_gemm_bf16.argtypes = [i32, i32, i64, i64, i64, C.c_float, vp, vp, i64, vp, i64, C.c_float,
+                                       vp, i64, vp, vp, sz, vp]
+        lib.team_f32_to_bf16.restype = i32
+        lib.team_f32_to_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
     if hasattr(lib, "team_gemm_bf16_nt"):
         lib.team_gemm_bf16_nt.restype = i32
         lib.team_gemm_bf16_nt.argtypes = [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]

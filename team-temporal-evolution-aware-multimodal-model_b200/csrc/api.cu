@@ -1,8 +1,11 @@
 // Error plumbing + device check for the C ABI (include/team_b200.h).
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace team {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -29,3 +32,5 @@ extern "C" int team_device_check(void) {
     }
     return TEAM_OK;
 }
+
+extern "C" long long team_launch_count(void) { return team::g_launches.load(); }

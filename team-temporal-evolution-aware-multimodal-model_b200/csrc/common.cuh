@@ -16,6 +16,7 @@ constexpr float NORM_EPS = 1e-12f;
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();
 
 #define TEAM_CUDA_CHECK(expr)                                   \
     do {                                                        \
@@ -23,8 +24,10 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return team::cuda_fail(_e, #expr); \
     } while (0)
 
+// one per kernel launch: counts it (team_launch_count) and checks the launch status
 #define TEAM_LAUNCH_CHECK(name)                                 \
     do {                                                        \
+        team::count_launch();                                   \
         cudaError_t _e = cudaGetLastError();                    \
         if (_e != cudaSuccess) return team::cuda_fail(_e, name); \
     } while (0)

@@ -4,6 +4,7 @@
 // dimension, optional split-K with a fixed-order (deterministic) second pass.
 #include "common.cuh"
 #include "gemm.cuh"
+#include "prof.cuh"
 
 namespace team {
 
@@ -154,11 +155,13 @@ int gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int64_t N, int64_t K,
 #define TEAM_GEMM_LAUNCH(TA_, TB_)                                                                       \
     gemm_f32_kernel<TA_, TB_><<<grid, 256, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, B, ldb, beta, \
                                                     C, ldc, bias, kps, partial)
+    const int pslot = prof_enabled() ? prof_begin(st, 0, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N)) : -1;
     if (!ta && tb) TEAM_GEMM_LAUNCH(false, true);
     else if (!ta && !tb) TEAM_GEMM_LAUNCH(false, false);
     else if (ta && !tb) TEAM_GEMM_LAUNCH(true, false);
     else TEAM_GEMM_LAUNCH(true, true);
 #undef TEAM_GEMM_LAUNCH
+    if (pslot >= 0) prof_end(st, pslot);
     TEAM_LAUNCH_CHECK("gemm_f32_kernel");
     if (splits > 1) {
         const int64_t tot = M * N;

@@ -112,11 +112,14 @@ static int step_rows_forward(HeadCtx& cx, const team_head_weights* hw) {
     HG(false, true, d.C, D, D, 1.f, hw->prototypes, D, w.Wsum[0], D, 0.f, w.Ztab, D, w.bsum[0]);
     HG(false, true, 10, D, D, 1.f, hw->state_emb, D, w.Wsum[2], D, 0.f, w.Ztab + (size_t)d.C * D, D, w.bsum[2]);
     rows_normalize_kernel<<<(d.C + 7) / 8, 256, 0, cx.st>>>(w.Ztab, d.C, w.S, w.invS, 1);
+    TEAM_LAUNCH_CHECK("rows_normalize_kernel");
     rows_normalize_kernel<<<2, 256, 0, cx.st>>>(w.Ztab + (size_t)d.C * D, 10, w.S + (size_t)d.M * D, w.invS + d.M, 1);
+    TEAM_LAUNCH_CHECK("rows_normalize_kernel");
     const int fill_rows = d.P + (d.Nsp - d.Ns);
-    if (fill_rows > 0)
+    if (fill_rows > 0) {
         fill_prompt_rows_kernel<<<fill_rows, 128, 0, cx.st>>>(plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S);
-    TEAM_LAUNCH_CHECK("step rows");
+        TEAM_LAUNCH_CHECK("fill_prompt_rows_kernel");
+    }
     int rc = qkv_forward(cx, hw, w.S, d.Nsp, w.QKVs);
     if (rc) return rc;
     HG(false, true, d.Nsp, D, D, 1.f, w.QKVs + 2 * D, 3 * D, hw->w_fc, D, 0.f, w.VFs, D, nullptr);
@@ -199,6 +202,7 @@ static int colsum(HeadCtx& cx, const float* X, int64_t rows, float* out, int acc
     if (chunks < 1) chunks = 1;
     const int64_t rpc = (rows + chunks - 1) / chunks;
     colsum_partial_kernel<<<chunks, 128, 0, cx.st>>>(X, rows, rpc, cx.w.colsum_partials);
+    TEAM_LAUNCH_CHECK("colsum_partial_kernel");
     colsum_final_kernel<<<1, 128, 0, cx.st>>>(cx.w.colsum_partials, chunks, out, accumulate);
     TEAM_LAUNCH_CHECK("colsum");
     return TEAM_OK;
@@ -224,13 +228,16 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     table_rows_bwd_kernel<<<tgrid, TR_WARPS * 32, tsm, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs, w.S, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, g_proto, g_state, w.dSK, w.dVFo, w.tab_partials);
     TEAM_LAUNCH_CHECK("table_rows_bwd_kernel");
     reduce_partials_kernel<<<(unsigned)((to.len / 4 + 63) / 64), 256, 0, cx.st>>>(w.tab_partials, tgrid, to.len / 4, w.tab_reduced);
+    TEAM_LAUNCH_CHECK("reduce_partials_kernel");
     expand_table_kernel<<<d.Nsp, 128, 0, cx.st>>>(d, w.tab_reduced, w.Rfull, w.Gfull, w.hfull, w.dTT, w.dVFs);
     TEAM_LAUNCH_CHECK("expand_table_kernel");
     // ---- own query rows
     int ogrid = (d.B + 7) / 8;
     if (ogrid > d.nctas) ogrid = d.nctas;
     ln_own_bwd_kernel<<<ogrid, 256, 0, cx.st>>>(d, w.Ybo, w.Xo, w.VFo, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo, w.dXo, w.rowdot, w.dsown, w.dVFo, w.own_partials);
+    TEAM_LAUNCH_CHECK("ln_own_bwd_kernel");
     reduce_partials_kernel<<<(OWN_PARTIAL_LEN / 4 + 63) / 64, 256, 0, cx.st>>>(w.own_partials, ogrid, OWN_PARTIAL_LEN / 4, w.own_reduced);
+    TEAM_LAUNCH_CHECK("reduce_partials_kernel");
     finalize_ln_grads_kernel<<<1, 128, 0, cx.st>>>(d, w.tab_reduced, w.own_reduced, gr->ln_g, gr->ln_b, gr->b_fc);
     TEAM_LAUNCH_CHECK("ln_own_bwd");
     // dA = dYo VFs^T  (into the SQ buffer), dVFs += Aext^T dYo, dS = Aext.*(dA - rowdot)/tau
@@ -275,6 +282,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     }
     // ---- normalisations and the newest projections
     nrm_bwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(w.dXo, d.B2, w.Xo, w.invo, nullptr, d.B2, 0);
+    TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
     // proto rows [0,C) and state rows [M,M+10) of dS_rows -> compact dZtab [C+10]
     nrm_bwd_kernel<<<(d.Rt + 7) / 8, 256, 0, cx.st>>>(w.dZtab, d.Rt, w.S, w.invS, w.Rfull, d.C, d.P);
     TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
@@ -312,6 +320,7 @@ extern "C" int team_head_encode(const team_head_weights* hw, int mode, int which
         TEAM_REQUIRE(x != nullptr, "head encode: null state ids");
         HG(false, true, 10, D, D, 1.f, hw->state_emb, D, cx.w.Wsum[2], D, 0.f, cx.w.Ztab, D, cx.w.bsum[2]);
         rows_normalize_kernel<<<2, 256, 0, cx.st>>>(cx.w.Ztab, 10, cx.w.Ztab, nullptr, normalize);
+        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
         gather_rows_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, cx.st>>>(cx.w.Ztab, reinterpret_cast<const int64_t*>(x), n_rows, out);
         TEAM_LAUNCH_CHECK("gather_rows_kernel");
         return TEAM_OK;

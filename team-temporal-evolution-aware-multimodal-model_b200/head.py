@@ -180,3 +180,91 @@ def encode(pack: HeadParamPack, which: str, x: Optional[torch.Tensor], img_proto
     capi.check(L.team_head_encode(C.byref(hw), mode, idx, xp, n, int(normalize), out.data_ptr(),
                                   ws.data_ptr(), nbytes, _stream_ptr()), "team_head_encode")
     return out
+
+
+GRAD_LAYOUT = (("w_img", capi.D * capi.D), ("b_img", capi.D), ("w_text", capi.D * capi.D), ("b_text", capi.D),
+               ("w_state", capi.D * capi.D), ("b_state", capi.D), ("state_emb", capi.NUM_STATES * capi.D),
+               ("w_q", capi.D * capi.D), ("w_k", capi.D * capi.D), ("w_v", capi.D * capi.D),
+               ("w_fc", capi.D * capi.D), ("b_fc", capi.D), ("ln_g", capi.D), ("ln_b", capi.D))
+
+
+class HeadStepRunner:
+    """Pre-allocated fwd+bwd step over the C ABI (no autograd tape, no allocation per step), the
+    form a training loop or a CUDA graph replays.  All trainable-parameter gradients land in ONE
+    flat fp32 buffer (``flat_grads``: the 1.85 M-element bucket that is all-reduced under data
+    parallelism)."""
+
+    def __init__(self, pack: HeadParamPack, img_prototypes: torch.Tensor, batch: int, num_text_cls: int,
+                 mode: int = MODE_F32):
+        capi.require_device()
+        dev = pack.flat[0].device
+        self.dev, self.B, self.mode, self.n_cls = dev, batch, mode, num_text_cls
+        self.pack = pack
+        self.flat = [_f32c(p, dev) for p in pack.flat]
+        self.protos = _f32c(img_prototypes, dev)
+        self.hw = _fill_weights(pack.T, pack.ppt, self.flat, self.protos)
+        L = capi.lib()
+        self.nbytes = L.team_head_workspace_bytes(batch, self.hw.num_classes, pack.T * pack.ppt, num_text_cls, mode)
+        self.ws = torch.empty((self.nbytes,), dtype=torch.uint8, device=dev)
+        self.outs = torch.empty((4, batch, capi.D), dtype=torch.float32, device=dev)
+        self.logits = torch.empty((batch, max(num_text_cls, 1)), dtype=torch.float32, device=dev)
+        self.argmax = torch.empty((batch,), dtype=torch.int64, device=dev)
+        P = pack.T * pack.ppt
+        n = sum(sz for _, sz in GRAD_LAYOUT) + max(P, 1) * capi.D
+        self.flat_grads = torch.zeros((n,), dtype=torch.float32, device=dev)
+        self.hg = capi.HeadGrads()
+        self.grad_views: Dict[str, torch.Tensor] = {}
+        off = 0
+        for name, sz in GRAD_LAYOUT + (("prompts", max(P, 1) * capi.D),):
+            v = self.flat_grads[off:off + sz]
+            self.grad_views[name] = v
+            setattr(self.hg, name, v.data_ptr())
+            off += sz
+
+    def forward(self, image, text, sid, text_cls=None):
+        n_cls = self.n_cls if text_cls is not None else 0
+        capi.check(capi.lib().team_head_tri_fwd(
+            C.byref(self.hw), self.mode, self.B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
+            text_cls.data_ptr() if n_cls else None, n_cls,
+            self.outs[0].data_ptr(), self.outs[1].data_ptr(), self.outs[2].data_ptr(), self.outs[3].data_ptr(),
+            self.logits.data_ptr() if n_cls else None, self.argmax.data_ptr() if n_cls else None,
+            self.ws.data_ptr(), self.nbytes, _stream_ptr()), "team_head_tri_fwd")
+
+    def backward(self, image, text, sid, cots):
+        capi.check(capi.lib().team_head_tri_bwd(
+            C.byref(self.hw), self.mode, self.B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
+            cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr(),
+            C.byref(self.hg), self.ws.data_ptr(), self.nbytes, _stream_ptr()), "team_head_tri_bwd")
+
+    def step(self, image, text, sid, text_cls, cots):
+        self.forward(image, text, sid, text_cls)
+        self.backward(image, text, sid, cots)
+
+
+def smoke_check():
+    """Tiny head fwd+bwd on cuda:0 against the CPU oracle (called by __graft_entry__.smoke)."""
+    from oracle import synth
+    from oracle import team_oracle as O
+    T, B = 2, 16
+    C_ = 2 * T
+    params = synth.make_params(T, seed=3)
+    protos = synth.make_prototypes(C_)
+    batch = synth.make_batch(B, C_, step=0)
+    cots = synth.make_cotangents(B)
+    dev = torch.device("cuda:0")
+    p = {k: v.to(dev).requires_grad_(v.dim() > 0) for k, v in params.items()}
+    pack = HeadParamPack.from_state_dict(p)
+    names = O.trainable_names(params)
+    pr = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in params.items()}
+    ref = O.forward_tri_modal(pr, batch["image"], batch["text"], batch["state"], protos)
+    gref = torch.autograd.grad(ref[:4], [pr[n] for n in names], grad_outputs=list(cots))
+    for mode, tol in ((MODE_F32, 2e-5), (MODE_BF16, 2e-2)):
+        outs = forward_tri_modal(pack, batch["image"].to(dev), batch["text"].to(dev), batch["state"].to(dev),
+                                 protos.to(dev), text_cls=batch["text_cls"].to(dev), mode=mode)
+        grads = torch.autograd.grad(outs[:4], [p[n] for n in names], grad_outputs=[c.to(dev) for c in cots])
+        worst = 0.0
+        for a, b in list(zip(outs[:4], ref[:4])) + list(zip(grads, gref)):
+            e = float((a.detach().cpu().double() - b.detach().double()).norm() / b.detach().double().norm())
+            worst = max(worst, e)
+        assert worst < tol, (mode, worst)
+        print(f"smoke: head fwd+bwd mode={'f32' if mode == MODE_F32 else 'bf16'} max rel err {worst:.2e} OK")

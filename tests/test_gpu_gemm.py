@@ -1,0 +1,88 @@
+"""GPU unit tests of the two GEMM engines through the C ABI: the fp32 FFMA GEMM and the
+tcgen05/TMA/TMEM bf16 GEMM (all four operand-major combinations, ragged M/N/K, split-K,
+alpha/beta/bias epilogue, two-term bf16 split of A).  Reference: fp64 matmul of the same
+(bf16-rounded) operands, so the only difference is fp32 accumulation order -> 2e-6."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = a.double().cpu(); b = b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (130, 70, 33), (2048, 512, 512), (512, 512, 2048), (144, 144, 512)])
+def test_gemm_f32(ta, tb, M, N, K):
+    from team_b200 import capi
+    capi.require_device()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g).cuda()
+    B = torch.randn((N, K) if tb else (K, N), generator=g).cuda()
+    Cm = torch.randn((M, N), generator=g).cuda()
+    bias = torch.randn((N,), generator=g).cuda()
+    ref = 0.5 * ((A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())) + bias.double() + 2.0 * Cm.double()
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    capi.check(capi.lib().team_gemm_f32(ta, tb, M, N, K, 0.5, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                        2.0, Cm.data_ptr(), N, bias.data_ptr(), ws.data_ptr(), ws.numel(), _st()))
+    assert rel(Cm, ref) < 2e-6
+
+
+SHAPES = [(128, 64, 64), (128, 128, 128), (256, 192, 512), (2048, 1536, 512), (200, 72, 136), (144, 144, 512),
+          (512, 512, 2048), (2048, 144, 512), (144, 512, 2048), (1000, 520, 200)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_bf16_tcgen05(a_mn, b_mn, M, N, K):
+    from team_b200 import capi
+    capi.require_device()
+    g = torch.Generator().manual_seed(7 * M + 3 * N + K + a_mn * 2 + b_mn)
+    # leading dimensions must be multiples of 8 elements: pad the stored matrices
+    pad = lambda n: (n + 7) // 8 * 8
+    A = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), generator=g).to(torch.bfloat16).cuda()
+    Av = A[:, :M] if a_mn else A[:, :K]
+    Bv = B[:, :N] if b_mn else B[:, :K]
+    ref = (Av.double().t() if a_mn else Av.double()) @ (Bv.double() if b_mn else Bv.double().t())
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    capi.check(capi.lib().team_gemm_bf16(a_mn, b_mn, M, N, K, 1.0, A.data_ptr(), None, A.stride(0), B.data_ptr(),
+                                         B.stride(0), 0.0, out.data_ptr(), N, None, ws.data_ptr(), ws.numel(), _st()),
+               "team_gemm_bf16")
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 2e-6, rel(out, ref)
+
+
+def test_gemm_bf16_epilogue_and_split():
+    from team_b200 import capi
+    capi.require_device()
+    M, N, K = 384, 200, 512
+    g = torch.Generator().manual_seed(1)
+    Af = torch.randn((M, K), generator=g).cuda()
+    Bq = torch.randn((N, K), generator=g).to(torch.bfloat16).cuda()
+    Cm = torch.randn((M, N), generator=g).cuda()
+    bias = torch.randn((N,), generator=g).cuda()
+    hi = torch.empty((M, K), dtype=torch.bfloat16, device="cuda")
+    lo = torch.empty((M, K), dtype=torch.bfloat16, device="cuda")
+    L = capi.lib()
+    capi.check(L.team_f32_to_bf16(Af.data_ptr(), K, M, K, hi.data_ptr(), lo.data_ptr(), K, _st()))
+    assert torch.equal(hi, Af.to(torch.bfloat16))
+    assert torch.equal(lo, (Af - hi.float()).to(torch.bfloat16))
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    C0 = Cm.clone()
+    capi.check(L.team_gemm_bf16(0, 0, M, N, K, 0.25, hi.data_ptr(), lo.data_ptr(), K, Bq.data_ptr(), K, -1.5,
+                                Cm.data_ptr(), N, bias.data_ptr(), ws.data_ptr(), ws.numel(), _st()))
+    ref = 0.25 * ((hi.double() + lo.double()) @ Bq.double().t()) + bias.double() - 1.5 * C0.double()
+    assert rel(Cm, ref) < 2e-6
+    # two-term split recovers the fp32 operand to ~2^-17
+    ref32 = 0.25 * (Af.double() @ Bq.double().t()) + bias.double() - 1.5 * C0.double()
+    assert rel(Cm, ref32) < 3e-5
