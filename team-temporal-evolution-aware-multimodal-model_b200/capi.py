@@ -118,9 +118,15 @@ def check(rc: int, what: str = ""):
         raise TeamB200Error(f"{what} failed with code {rc}: {msg}")
 
 
+_device_ok = set()
+
+
 def require_device():
-    """Fail loudly unless torch sees a CUDA device of compute capability 10.x."""
+    """Fail loudly unless torch sees a CUDA device of compute capability 10.x (checked once per device)."""
     import torch
     if not torch.cuda.is_available():
         raise TeamB200Error("team_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    check(lib().team_device_check(), "team_device_check")
+    dev = torch.cuda.current_device()
+    if dev not in _device_ok:
+        check(lib().team_device_check(), "team_device_check")
+        _device_ok.add(dev)

@@ -399,7 +399,13 @@ int to_bf16(cudaStream_t st, const float* src, int64_t lds, int64_t rows, int co
     return TEAM_OK;
 }
 
-size_t tc_operand_bytes(const HeadDims& d) { (void)d; return 0; }
+size_t tc_operand_bytes(const HeadDims& d) {
+    // generous bound on the bf16 copies one fwd or bwd call makes (see BfCache in head.cu)
+    const size_t B2 = d.B2, Nsp = d.Nsp;
+    const size_t elems = B2 * (20 * (size_t)D + 8 * Nsp) + Nsp * (16 * (size_t)D + 6 * Nsp) + 16 * (size_t)D * D +
+                         (size_t)(d.Rt + d.C + 64 + (d.Tc > 0 ? d.Tc : 0)) * 4 * D;
+    return align_up(elems * 2 + 96 * 256, 256);
+}
 
 }  // namespace team
 

@@ -55,12 +55,72 @@ void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     w->total_bytes = off;
 }
 
+// bf16 shadow copies of GEMM operands (mode BF16), valid for the duration of one fwd or bwd call.
+// An operand is converted the first time a GEMM asks for it; sub-views of an already converted
+// parent (same leading dimension) are served from the parent.  The orchestration below only asks
+// for an operand after its final write, so no invalidation is needed.
+struct BfCache {
+    struct Ent { const float* base; int64_t rows, cols, ld; char* bf; };
+    Ent e[96];
+    int n = 0;
+    char* area = nullptr;
+    size_t cap = 0, used = 0;
+};
+
 struct HeadCtx {
     cudaStream_t st;
     int mode;
     HeadDims d;
     HeadWS w;
+    BfCache bc;
 };
+
+static int bf16_view(HeadCtx& cx, const float* p, int64_t rows, int64_t cols, int64_t ld, const void** out) {
+    BfCache& c = cx.bc;
+    for (int i = 0; i < c.n; ++i) {
+        const BfCache::Ent& e = c.e[i];
+        if (e.ld != ld || p < e.base) continue;
+        const int64_t off = p - e.base;
+        const int64_t r0 = off / ld, c0 = off % ld;
+        if (r0 + rows <= e.rows && c0 + cols <= e.cols) { *out = e.bf + off * 2; return TEAM_OK; }
+    }
+    const size_t bytes = align_up((size_t)((rows - 1) * ld + cols) * 2, 256);
+    if (c.n >= 96 || c.used + bytes > c.cap) {
+        set_error("head: bf16 operand staging exhausted (%zu + %zu > %zu, %d entries)", c.used, bytes, c.cap, c.n);
+        return TEAM_EWORKSPACE;
+    }
+    char* dst = c.area + c.used;
+    c.used += bytes;
+    int rc = to_bf16(cx.st, p, ld, rows, (int)cols, dst, nullptr, ld);
+    if (rc) return rc;
+    c.e[c.n++] = BfCache::Ent{p, rows, cols, ld, dst};
+    *out = dst;
+    return TEAM_OK;
+}
+
+// convert a whole parent buffer now (its column sub-views are then served from it)
+static int bf16_parent(HeadCtx& cx, const float* p, int64_t rows, int64_t cols) {
+    if (cx.mode != TEAM_MODE_BF16) return TEAM_OK;
+    const void* unused;
+    return bf16_view(cx, p, rows, cols, cols, &unused);
+}
+
+// C[M,N] = alpha op(A) op(B) + beta C (+bias).  ta: A stored [K,M]; tb: B stored [N,K].
+// F32 mode: fp32 FFMA GEMM.  BF16 mode: operands rounded to bf16 once, tcgen05 GEMM, fp32 accumulate.
+static int hgemm(HeadCtx& cx, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
+                 int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias) {
+    const bool tc_ok = cx.mode == TEAM_MODE_BF16 && (lda % 8 == 0) && (ldb % 8 == 0) && K >= 1 &&
+                       ((reinterpret_cast<uintptr_t>(A) & 31) == 0) && ((reinterpret_cast<uintptr_t>(B) & 31) == 0) &&
+                       ((ta ? M : K) % 4 == 0) && ((tb ? K : N) % 4 == 0);
+    if (!tc_ok) return gemm_f32(cx.st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
+    TcGemm g;
+    g.a_mn = ta; g.b_mn = !tb; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
+    g.A2 = nullptr; g.lda = lda; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
+    int rc = bf16_view(cx, A, ta ? K : M, ta ? M : K, lda, &g.A);
+    if (rc) return rc;
+    if ((rc = bf16_view(cx, B, tb ? N : K, tb ? K : N, ldb, &g.B))) return rc;
+    return gemm_bf16_tc(cx.st, g, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
+}
 
 static int validate(const team_head_weights* hw, int mode, int64_t batch) {
     TEAM_REQUIRE(hw != nullptr, "head: null weights");
@@ -80,10 +140,10 @@ static PtrList plist(const float* const* p, int n) {
     return l;
 }
 
-#define HG(...)                                                                            \
-    do {                                                                                   \
-        int _rc = gemm_f32(cx.st, __VA_ARGS__, cx.w.gemm_ws, cx.w.gemm_ws_bytes);          \
-        if (_rc != TEAM_OK) return _rc;                                                    \
+#define HG(...)                                       \
+    do {                                              \
+        int _rc = hgemm(cx, __VA_ARGS__);             \
+        if (_rc != TEAM_OK) return _rc;               \
     } while (0)
 
 static int sum_projections(HeadCtx& cx, const team_head_weights* hw) {
@@ -122,6 +182,7 @@ static int step_rows_forward(HeadCtx& cx, const team_head_weights* hw) {
     }
     int rc = qkv_forward(cx, hw, w.S, d.Nsp, w.QKVs);
     if (rc) return rc;
+    if ((rc = bf16_parent(cx, w.QKVs, d.Nsp, 3 * D))) return rc;
     HG(false, true, d.Nsp, D, D, 1.f, w.QKVs + 2 * D, 3 * D, hw->w_fc, D, 0.f, w.VFs, D, nullptr);
     HG(false, true, d.Nsp, d.Nsp, D, 1.f, w.QKVs, 3 * D, w.QKVs + D, 3 * D, 0.f, w.TT, d.Nsp, nullptr);
     table_prep_kernel<<<(d.Nsp + 7) / 8, 256, 0, cx.st>>>(w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt);
@@ -143,6 +204,9 @@ static int setup(HeadCtx& cx, const team_head_weights* hw, int mode, int64_t bat
         return TEAM_EWORKSPACE;
     }
     TEAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "head: workspace must be 256-byte aligned");
+    cx.bc.n = 0; cx.bc.used = 0;
+    cx.bc.area = reinterpret_cast<char*>(cx.w.bf16_area);
+    cx.bc.cap = cx.w.bf16_bytes;
     return TEAM_OK;
 }
 
@@ -177,6 +241,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     rows_normalize_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(w.Xo, d.B2, w.Xo, w.invo, 1);
     TEAM_LAUNCH_CHECK("rows_normalize_kernel");
     if ((rc = qkv_forward(cx, hw, w.Xo, d.B2, w.QKVo))) return rc;
+    if ((rc = bf16_parent(cx, w.QKVo, d.B2, 3 * D))) return rc;
     HG(false, true, d.B2, D, D, 1.f, w.QKVo + 2 * D, 3 * D, hw->w_fc, D, 0.f, w.VFo, D, nullptr);
     HG(false, true, d.B2, d.Nsp, D, 1.f, w.QKVo, 3 * D, w.QKVs + D, 3 * D, 0.f, w.SQ, d.Nsp, nullptr);
     HG(false, true, d.B2, d.Nsp, D, 1.f, w.QKVo + D, 3 * D, w.QKVs, 3 * D, 0.f, w.SK, d.Nsp, nullptr);
@@ -221,6 +286,8 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     const HeadDims& d = cx.d;
     HeadWS& w = cx.w;
     const TabOff to = tab_offsets(d);
+    if ((rc = bf16_parent(cx, w.QKVo, d.B2, 3 * D))) return rc;
+    if ((rc = bf16_parent(cx, w.QKVs, d.Nsp, 3 * D))) return rc;
     // ---- table-query rows (prototype / state outputs)
     const int tgrid = d.B < d.nctas ? d.B : d.nctas;
     const size_t tsm = (size_t)(3 * TR_WARPS * D + 10 * D + 3 * D + d.Rt * 11) * sizeof(float);
@@ -272,6 +339,8 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     HG(true, false, D, D, d.B2, 1.f, w.dVFo, D, Vo, 3 * D, 0.f, gr->w_fc, D, nullptr);              // dWfc = dVFo^T Vo
     HG(true, false, D, D, d.Nsp, 1.f, w.dVFs, D, Vs, 3 * D, 1.f, gr->w_fc, D, nullptr);             //      + dVFs^T Vs
     // ---- q/k/v projections
+    if ((rc = bf16_parent(cx, w.dQKVo, d.B2, 3 * D))) return rc;
+    if ((rc = bf16_parent(cx, w.dQKVs, d.Nsp, 3 * D))) return rc;
     const float* Wqkv[3] = {hw->w_q, hw->w_k, hw->w_v};
     float* dWqkv[3] = {gr->w_q, gr->w_k, gr->w_v};
     for (int i = 0; i < 3; ++i) {

@@ -90,3 +90,48 @@ def test_encode_paths():
         assert rel(head.encode(pack, "text", batch["text"].to(dev), normalize=norm), O.encode_text(batch["text"], params, norm)) < 1e-5
         assert rel(head.encode(pack, "state", batch["state"].to(dev), normalize=norm), O.encode_state(batch["state"], params, norm)) < 1e-5
         assert rel(head.encode(pack, "prototypes", None, protos.to(dev), normalize=norm), O.encode_prototypes(protos, params, norm)) < 1e-5
+
+
+def _quantised_operand_params(params):
+    """bf16-mode operand contract: the projections are summed in fp32 and rounded to bf16
+    once; biases stay fp32.  Returned as a single-task parameter set for the oracle."""
+    T = O.num_tasks(params)
+    q = {}
+    for kind in ("img", "text", "state"):
+        W = sum(params[f"projs_{kind}.{t}.MLP.0.weight"] for t in range(T))
+        b = sum(params[f"projs_{kind}.{t}.MLP.0.bias"] for t in range(T))
+        q[f"projs_{kind}.0.MLP.0.weight"] = W.to(torch.bfloat16).float()
+        q[f"projs_{kind}.0.MLP.0.bias"] = b
+    return q
+
+
+@pytest.mark.parametrize("T,B", [(1, 64), (10, 512)])
+def test_head_bf16_mode(T, B):
+    """bf16 mode (tcgen05 GEMMs, every GEMM operand rounded to bf16 once, fp32 accumulate, fp32 outputs).
+    Bars: classification logits <= 1e-3 against the oracle evaluated on identically quantised
+    operands (north_star), argmax exact where the fp64 margin exceeds the error bound; fused features
+    and gradients <= 1e-2 (norm-wise) against the UNquantised fp64 oracle (measured 3-6e-3: one bf16
+    rounding per GEMM stage)."""
+    from team_b200 import head
+    C = 2 * T
+    params = synth.make_params(T, seed=100 + T)
+    protos = synth.make_prototypes(C, seed=7)
+    batch = synth.make_batch(B, C, step=T)
+    cots = synth.make_cotangents(B, step=T)
+    outs, grads = run_head(params, batch, protos, cots, head.MODE_BF16)
+    q = _quantised_operand_params(params)
+    xq = batch["image"].to(torch.bfloat16).double()
+    tq = batch["text_cls"].to(torch.bfloat16).double()
+    lq = O.forward_for_classification({k: v.double() for k, v in q.items()}, xq, tq)
+    assert rel(outs[4], lq) < 1e-3, rel(outs[4], lq)
+    top2 = lq.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2e-3
+    assert torch.equal(outs[5].cpu()[safe], lq.argmax(1)[safe])
+    p64 = {k: v.double().requires_grad_(v.dim() > 0) for k, v in params.items()}
+    ref = O.forward_tri_modal(p64, batch["image"].double(), batch["text"].double(), batch["state"], protos.double())
+    for key, o, r in zip(("image", "text", "state", "proto"), outs[:4], ref[:4]):
+        assert rel(o, r) < 1e-2, (key, rel(o, r))
+    names = O.trainable_names(params)
+    gref = torch.autograd.grad(ref[:4], [p64[n] for n in names], grad_outputs=[c.double() for c in cots])
+    for n, gr in zip(names, gref):
+        assert rel(grads[n], gr) < 1.5e-2, (n, rel(grads[n], gr))
