@@ -239,32 +239,3 @@ class HeadStepRunner:
     def step(self, image, text, sid, text_cls, cots):
         self.forward(image, text, sid, text_cls)
         self.backward(image, text, sid, cots)
-
-
-def smoke_check():
-    """Tiny head fwd+bwd on cuda:0 against the CPU oracle (called by __graft_entry__.smoke)."""
-    from oracle import synth
-    from oracle import team_oracle as O
-    T, B = 2, 16
-    C_ = 2 * T
-    params = synth.make_params(T, seed=3)
-    protos = synth.make_prototypes(C_)
-    batch = synth.make_batch(B, C_, step=0)
-    cots = synth.make_cotangents(B)
-    dev = torch.device("cuda:0")
-    p = {k: v.to(dev).requires_grad_(v.dim() > 0) for k, v in params.items()}
-    pack = HeadParamPack.from_state_dict(p)
-    names = O.trainable_names(params)
-    pr = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in params.items()}
-    ref = O.forward_tri_modal(pr, batch["image"], batch["text"], batch["state"], protos)
-    gref = torch.autograd.grad(ref[:4], [pr[n] for n in names], grad_outputs=list(cots))
-    for mode, tol in ((MODE_F32, 2e-5), (MODE_BF16, 2e-2)):
-        outs = forward_tri_modal(pack, batch["image"].to(dev), batch["text"].to(dev), batch["state"].to(dev),
-                                 protos.to(dev), text_cls=batch["text_cls"].to(dev), mode=mode)
-        grads = torch.autograd.grad(outs[:4], [p[n] for n in names], grad_outputs=[c.to(dev) for c in cots])
-        worst = 0.0
-        for a, b in list(zip(outs[:4], ref[:4])) + list(zip(grads, gref)):
-            e = float((a.detach().cpu().double() - b.detach().double()).norm() / b.detach().double().norm())
-            worst = max(worst, e)
-        assert worst < tol, (mode, worst)
-        print(f"smoke: head fwd+bwd mode={'f32' if mode == MODE_F32 else 'bf16'} max rel err {worst:.2e} OK")
