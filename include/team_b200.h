@@ -165,6 +165,63 @@ int team_head_encode(const team_head_weights* w, int mode, int which, const void
                      int64_t n_rows, int normalize, float* out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ temporal GCN + state distances
+ * Replaces: TemporalStateGCN.forward / TemporalGCNBlock.forward   models/dynamic_modal_graph.py:239-337
+ *           (called under no_grad from InsectLifecycleModel.evolve_and_update, models/state_evolution.py:326-327).
+ * Edges arrive as a destination-sorted CSR (rowptr[N+1], src[E], edge_w[E]) that keeps the reference's
+ * edge order inside every destination (intra-class edges first, then inter-class, each by source index).
+ * out[N,512] = L2-normalised evolved node features. */
+typedef struct team_tgcn_block {
+    const float* msg_w;  const float* msg_b;  const float* msg_ln_g;  const float* msg_ln_b;   /* message_net: [320,640],[320],[320],[320] */
+    const float* upd_w;  const float* upd_b;  const float* upd_ln_g;  const float* upd_ln_b;   /* update_net */
+    const float* gate_w; const float* gate_b;                                                   /* temporal_gate: [1,320],[1] */
+} team_tgcn_block;
+typedef struct team_tgcn_weights {
+    const float* node_w; const float* node_b; const float* node_ln_g; const float* node_ln_b;  /* node_encoder: [256,512],[256],[256],[256] */
+    const float* time_w; const float* time_b; const float* time_ln_g; const float* time_ln_b;  /* time_encoder: [64,1],[64],[64],[64] */
+    team_tgcn_block blocks[8];
+    int32_t num_blocks;
+    int32_t reserved;
+    const float* out_w;  const float* out_b;                                                     /* output_proj: [512,320],[512] */
+} team_tgcn_weights;
+size_t team_tgcn_workspace_bytes(int64_t n_nodes);
+int team_tgcn_forward(const team_tgcn_weights* w, const float* node_feat, const float* time_steps,
+                      int64_t n_nodes, const int32_t* rowptr, const int32_t* src, const float* edge_w,
+                      float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* d_ij = 1 - cosine(u_i,u_j) for every ordered pair i != j, summed per (state_i,state_j) in double
+ * (models/state_evolution.py:345-364).  sums[100] double, counts[100] int64, row-major [state_i][state_j].
+ * workspace >= n_nodes*10*12 + 256 bytes. */
+int team_pairwise_state_dist(const float* node_feat, const int32_t* node_states, int64_t n_nodes,
+                             double* sums, int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+/* Proof_Net._sync_class_prototypes (utils/inc_net.py:600-617): nodes grouped by class (group_ptr CSR);
+ * img_prototypes[group_class[g]] = normalize(sum_i w_i p_i / sum w), w = 1.5 for state 4 else 1. */
+int team_sync_prototypes(const float* nodes, const int32_t* group_ptr, const int32_t* node_states,
+                         const int32_t* group_class, int64_t n_groups, float* img_prototypes, void* stream);
+int team_rows_normalize(float* x, int64_t n_rows, void* stream);
+/* out[g] = mean of nodes[member[i]] over i in [group_ptr[g], group_ptr[g+1]) (member NULL = identity):
+ * class embeddings / lifecycle features of evolve_and_update (models/state_evolution.py:256-258, :334-343). */
+int team_group_mean(const float* nodes, const int32_t* group_ptr, const int32_t* member, int64_t n_groups,
+                    float* out, void* stream);
+/* AdaptiveStateDistanceMatrix.get_distance_matrix (utils/state_distance.py:65-71) */
+int team_dist_matrix(const float* factors, int32_t n, float* out, void* stream);
+/* Learner.update_state_distance_matrix EMA (models/proof.py:666-675), sequential over (keys[e], vals[e]) */
+int team_dist_ema(float* factors, int32_t n, const int32_t* keys, const double* vals, int32_t m, double weight,
+                  void* stream);
+/* AdaptiveStateDistanceMatrix.forward update branch (utils/state_distance.py:96-134): per-state sums/counts
+ * (from team_segsum with key = state id) -> centres -> 2 - cosine -> sequential EMA into factors[10,10];
+ * pre_update_matrix (optional) receives get_distance_matrix() of the factors BEFORE the update. */
+int team_state_dist_forward(const float* state_sums, const int64_t* state_counts, float* factors, double decay,
+                            float* pre_update_matrix, void* stream);
+/* DynamicGCN.forward, eval mode (models/dynamic_modal_graph.py:131-163) */
+typedef struct team_dgcn_layer {
+    const float* w; const float* b; const float* ln_g; const float* ln_b;
+    int32_t in_dim; int32_t out_dim;
+} team_dgcn_layer;
+size_t team_dgcn_workspace_bytes(int64_t n_nodes, int32_t max_dim);
+int team_dgcn_forward(const team_dgcn_layer* layers, int32_t n_layers, const float* x, int64_t n_nodes,
+                      const int32_t* rowptr, const int32_t* src, const float* edge_w, float* out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ generic GEMM (tests/bench)
  * C[M,N] = alpha * op(A) op(B) + beta * C (+ bias[N]);  fp32 SIMT path.
  * ta: 0 -> A is [M,K] row-major (lda), 1 -> A is [K,M] row-major.

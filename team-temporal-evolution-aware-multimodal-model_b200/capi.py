@@ -46,6 +46,23 @@ class HeadGrads(C.Structure):
                  "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b")]
 
 
+class TgcnBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("msg_w", "msg_b", "msg_ln_g", "msg_ln_b", "upd_w", "upd_b", "upd_ln_g", "upd_ln_b", "gate_w", "gate_b")]
+
+
+class TgcnWeights(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in
+                 ("node_w", "node_b", "node_ln_g", "node_ln_b", "time_w", "time_b", "time_ln_g", "time_ln_b")] +
+                [("blocks", TgcnBlock * 8), ("num_blocks", C.c_int32), ("reserved", C.c_int32),
+                 ("out_w", C.c_void_p), ("out_b", C.c_void_p)])
+
+
+class DgcnLayer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p),
+                ("in_dim", C.c_int32), ("out_dim", C.c_int32)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -96,6 +113,32 @@ def _declare(lib):
         lib.team_head_encode.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, sz, vp]
 
 
+def _declare_graph(lib):
+    vp, i64, i32, sz, dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_double
+    lib.team_tgcn_workspace_bytes.restype = sz
+    lib.team_tgcn_workspace_bytes.argtypes = [i64]
+    lib.team_tgcn_forward.restype = i32
+    lib.team_tgcn_forward.argtypes = [C.POINTER(TgcnWeights), vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+    lib.team_pairwise_state_dist.restype = i32
+    lib.team_pairwise_state_dist.argtypes = [vp, vp, i64, vp, vp, vp, sz, vp]
+    lib.team_sync_prototypes.restype = i32
+    lib.team_sync_prototypes.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    lib.team_rows_normalize.restype = i32
+    lib.team_rows_normalize.argtypes = [vp, i64, vp]
+    lib.team_group_mean.restype = i32
+    lib.team_group_mean.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.team_dist_matrix.restype = i32
+    lib.team_dist_matrix.argtypes = [vp, C.c_int32, vp, vp]
+    lib.team_dist_ema.restype = i32
+    lib.team_dist_ema.argtypes = [vp, C.c_int32, vp, vp, C.c_int32, dbl, vp]
+    lib.team_state_dist_forward.restype = i32
+    lib.team_state_dist_forward.argtypes = [vp, vp, vp, dbl, vp, vp]
+    lib.team_dgcn_workspace_bytes.restype = sz
+    lib.team_dgcn_workspace_bytes.argtypes = [i64, C.c_int32]
+    lib.team_dgcn_forward.restype = i32
+    lib.team_dgcn_forward.argtypes = [C.POINTER(DgcnLayer), C.c_int32, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+
+
 def lib():
     """The loaded shared library; raises TeamB200Error if it has not been built."""
     global _lib
@@ -108,6 +151,7 @@ def lib():
                         "(there is no CPU/PyTorch fallback)")
                 handle = C.CDLL(LIB_PATH)
                 _declare(handle)
+                _declare_graph(handle)
                 _lib = handle
     return _lib
 
