@@ -237,6 +237,25 @@ int team_gemm_f32(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha,
 int team_gemm_bf16(int a_mn, int b_mn, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
                    const void* A_lo, int64_t lda, const void* B, int64_t ldb, float beta, float* C,
                    int64_t ldc, const float* bias, void* workspace, size_t workspace_bytes, void* stream);
+/* Grouped form: n independent problems in as few launches as possible (8 problems per launch), each
+ * C = alpha op(A) op(B) (+bias) (+beta C) written as fp32 (C) and/or bf16 (C_bf16); split-K is folded
+ * inside the kernel in a fixed order (deterministic).  workspace: >= 16 KiB + room for split-K partials
+ * (without it long-K problems simply run unsplit). */
+typedef struct team_gemm_desc {
+    int32_t a_mn, b_mn;
+    int64_t M, N, K;
+    float alpha, beta;
+    const void* A; int64_t lda;
+    const void* B; int64_t ldb;
+    float* C; int64_t ldc;
+    void* C_bf16; int64_t ldc_bf16;
+    const float* bias;
+} team_gemm_desc;
+int team_gemm_bf16_group(const team_gemm_desc* descs, int32_t n, void* workspace, size_t workspace_bytes, void* stream);
+/* programmatic dependent launch for the library's kernels (default: env TEAM_PDL, else off) */
+int team_set_pdl(int on);
+/* debugging aid: if buf != NULL every GEMM CTA writes 8 globaltimer stamps to buf[cta*8..] (tools/gemm_probe.py) */
+int team_gemm_debug_stamps(void* buf);
 /* fp32 [rows,cols] -> bf16 hi (and optional lo residual) */
 int team_f32_to_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, void* hi, void* lo,
                      int64_t ldd, void* stream);

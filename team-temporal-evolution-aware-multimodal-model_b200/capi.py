@@ -63,6 +63,13 @@ class DgcnLayer(C.Structure):
                 ("in_dim", C.c_int32), ("out_dim", C.c_int32)]
 
 
+class GemmDesc(C.Structure):
+    _fields_ = [("a_mn", C.c_int32), ("b_mn", C.c_int32), ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("alpha", C.c_float), ("beta", C.c_float), ("A", C.c_void_p), ("lda", C.c_int64),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("C_bf16", C.c_void_p), ("ldc_bf16", C.c_int64), ("bias", C.c_void_p)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -97,6 +104,11 @@ def _declare(lib):
                                        vp, i64, vp, vp, sz, vp]
         lib.team_f32_to_bf16.restype = i32
         lib.team_f32_to_bf16.argtypes = [vp, i64, i64, i64, vp, vp, i64, vp]
+    if hasattr(lib, "team_gemm_bf16_group"):
+        lib.team_gemm_bf16_group.restype = i32
+        lib.team_gemm_bf16_group.argtypes = [C.POINTER(GemmDesc), C.c_int32, vp, sz, vp]
+        lib.team_set_pdl.restype = i32
+        lib.team_set_pdl.argtypes = [i32]
     if hasattr(lib, "team_gemm_bf16_nt"):
         lib.team_gemm_bf16_nt.restype = i32
         lib.team_gemm_bf16_nt.argtypes = [i64, i64, i64, vp, i64, vp, i64, vp, i64, vp]

@@ -1,18 +1,28 @@
-// tcgen05 / TMA / TMEM bf16 GEMM for sm_100a (TEAM_MODE_BF16).
+// tcgen05 / TMA / TMEM bf16 grouped GEMM for sm_100a (TEAM_MODE_BF16).
 //
-//   C[M,N] (fp32) = alpha * op(A) op(B) (+ bias[N]) (+ beta * C)      fp32 accumulation in TMEM
+//   for every problem p of a group:  C_p[M,N] = alpha * op(A_p) op(B_p) (+ bias[N]) (+ beta * C_p)
+//   written as fp32 and/or bf16 (the bf16 copy is what the next GEMM of the head consumes, so no
+//   separate conversion pass exists); fp32 accumulation in tensor memory.
 //
-// Operands are bf16 in global memory and reach shared memory through TMA
-// (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a multi-stage mbarrier ring; ONE elected
-// thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1); the 128 x BN fp32
-// accumulator lives in tensor memory and is read back with tcgen05.ld by the 4 epilogue
-// warps (warp w owns TMEM lanes 32w..32w+31 = output rows).  Either operand may be K-major
-// (row-major [rows,K]) or MN-major (row-major [K,rows]) - selected by the UMMA instruction
-// descriptor major bits and the matching shared-memory descriptor - so the backward's
-// A^T B (weight gradients, reductions over the batch) and A B products need no transposed
-// copies.  Split-K (grid.z) writes fp32 partials that are folded in a fixed order.
-// An optional second A tensor ("lo" half of a 2-term bf16 split of an fp32 activation) is
-// accumulated into the same tile: C = (A_hi + A_lo) B, keeping 16 mantissa bits.
+// ONE launch runs up to TC_MAXP independent problems (the head's many small GEMMs have <= 64 output
+// tiles each and would leave most of the 148 SMs idle one at a time): the problem table - tensor
+// maps included - travels as a __grid_constant__ kernel parameter, so a captured CUDA graph holds it
+// by value.  CTA = one 128 x BN output tile of one problem (x one split of K).
+//
+//   operands : bf16 in global memory -> shared memory through TMA (cp.async.bulk.tensor.2d,
+//              SWIZZLE_128B) into a 3-stage mbarrier ring; either operand K-major (row-major
+//              [rows,K]) or MN-major (row-major [K,rows]) via the UMMA descriptor major bits, so
+//              A^T B / A B products of the backward need no transposed copies.
+//   math     : one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, cta_group::1), BN runtime
+//              (multiple of 16, <= 128); the accumulator lives in TMEM.
+//   epilogue : tcgen05.ld (warp w owns TMEM lanes 32w..32w+31) -> padded shared-memory tile ->
+//              row-contiguous 128-bit global stores (fp32) / 64-bit (bf16).
+//   split-K  : partial tiles go to a workspace; the LAST arriving CTA of a tile (atomic ticket) folds
+//              all partials in split order - deterministic - and runs the epilogue, so there is no
+//              second reduction kernel.  Tickets reset themselves.
+//   PDL      : griddepcontrol.launch_dependents / .wait bracket the prologue (barrier init, TMEM
+//              alloc, tensor-map prefetch) so it overlaps the previous kernel's tail when the launch
+//              carries the programmatic-stream-serialization attribute.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -25,6 +35,45 @@ constexpr int TC_BM = 128;           // UMMA_M
 constexpr int TC_BK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int TC_UMMA_K = 16;
 constexpr int TC_THREADS = 128;
+constexpr int TC_STAGES = 3;          // 2 CTAs / SM (multi-wave launches)
+constexpr int TC_MAX_STAGES = 6;      // 1 CTA / SM: single-wave launches keep twice the bytes in flight per CTA
+constexpr int TC_MAX_BN = 128;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
+constexpr int TC_B_BYTES = TC_MAX_BN * TC_BK * 2;      // 16 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }   // 3 stages: 97.25 KB -> 2 CTAs / SM
+constexpr uint32_t TC_TMEM_COLS = 128;
+constexpr int TC_MAXP = 8;           // problems per launch (kernel parameter space: 8 * 384 B)
+constexpr int TC_MAX_TICKETS = 4096; // split-K tickets at the head of the workspace
+constexpr int TC_TARGET_CTAS = 2 * NUM_SMS;
+
+static_assert(TC_BM * (TC_MAX_BN + 4) * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilogue staging must fit in the operand ring");
+
+struct alignas(64) TcProb {
+    CUtensorMap ma, mb;
+    float* C;
+    __nv_bfloat16* Cb;
+    const float* bias;
+    float* partial;
+    unsigned* ticket;
+    long long ldc, ldcb;
+    float alpha, beta;
+    int M, N, K;
+    int bn, tiles_n, cta_begin, splits, kb_per_split;
+    int a_mn, b_mn;
+};
+struct TcGroup {
+    TcProb p[TC_MAXP];
+    int n;
+    int stages;
+    unsigned long long* dbg;     // optional [cta][16] globaltimer stamps (tools/gemm_probe.py), else null
+};
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_STAMP(slot) do { if (g.dbg != nullptr) g.dbg[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +126,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
 // shared-memory matrix descriptors (SWIZZLE_128B, descriptor version 1)
 //   K-major : rows of 128 B (64 bf16 along K); 8-row groups SBO = 1024 B apart.
 //   MN-major: rows of 128 B (64 bf16 along M/N), one row per k; 8-k groups SBO = 1024 B apart;
@@ -86,177 +143,288 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor, kind::f16: D=f32, A=B=bf16, majors, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn) {
+__host__ __device__ inline uint32_t umma_idesc(int M, int N, int a_mn, int b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
-struct TcSmem {
-    static constexpr int A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
-    static constexpr int B_BYTES = BN * TC_BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 128) ? 3 : 4;      // 96 KB -> two CTAs per SM overlap epilogue and main loop
-    static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b);
+    return o;
+}
 
-// grid = (ceil(N/BN), ceil(M/128), splits); 128 threads.
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
-                         const __grid_constant__ CUtensorMap map_b, int M, int N, int K, int kb_per_split,
-                         int has_a2, float alpha, float beta, const float* __restrict__ bias,
-                         float* __restrict__ C, int64_t ldc, float* __restrict__ partial) {
-    using S = TcSmem<BN>;
+// grid = total CTAs of the group; 128 threads.
+__global__ void __launch_bounds__(TC_THREADS)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + S::STAGES;
-    uint64_t* tmem_full_bar = empty_bar + S::STAGES;
+    // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the shared address space -> LDS/STS
+    unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    const int nstages = g.stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * TC_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint32_t* last_flag = tmem_slot + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-    const int nkb = (K + TC_BK - 1) / TC_BK;                 // k-blocks of one pass over K
-    const int total_kb = has_a2 ? 2 * nkb : nkb;             // hi pass then lo pass
-    const int kb_begin = blockIdx.z * kb_per_split;
-    const int kb_end = min(total_kb, kb_begin + kb_per_split);
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    if (threadIdx.x == 0) TC_STAMP(0);
+
+    int pi = 0;
+    for (int i = 1; i < g.n; ++i)
+        if ((int)blockIdx.x >= g.p[i].cta_begin) pi = i;
+    const TcProb& P = g.p[pi];
+    const int local = (int)blockIdx.x - P.cta_begin;
+    const int split = local % P.splits, tile = local / P.splits;
+    const int m0 = (tile / P.tiles_n) * TC_BM, bn = P.bn, n0 = (tile % P.tiles_n) * bn;
+    const int nkb = (P.K + TC_BK - 1) / TC_BK;
+    const int kb_begin = split * P.kb_per_split;
+    const int kb_end = min(nkb, kb_begin + P.kb_per_split);
+    const int a_mn = P.a_mn, b_mn = P.b_mn;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.ma)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.mb)) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: let the next kernel start its own prologue; wait until everything before us has completed
+    if (threadIdx.x == 0) TC_STAMP(1);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) TC_STAMP(2);
 
-    if (kb_begin < kb_end) {
-        if (threadIdx.x == 0) {
-            // ===================== TMA producer =====================
-            int stage = 0; uint32_t phase = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                unsigned char* sa = smem + stage * S::STAGE_BYTES;
-                unsigned char* sb = sa + S::A_BYTES;
-                mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                const bool lo = kb >= nkb;
-                const CUtensorMap* ma = lo ? &map_a2 : &map_a;
-                const int k0 = (lo ? kb - nkb : kb) * TC_BK;
-                if (!A_MN) {
-                    tma_load_2d(sa, ma, &full_bar[stage], k0, m0);                    // box {64 k, 128 rows}
-                } else {
-#pragma unroll
-                    for (int c = 0; c < TC_BM / 64; ++c)                                // box {64 m, 64 k} per chunk
-                        tma_load_2d(sa + c * (TC_BK * 128), ma, &full_bar[stage], m0 + 64 * c, k0);
-                }
-                if (!B_MN) {
-                    tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);                // box {64 k, BN rows}
-                } else {
-#pragma unroll
-                    for (int c = 0; c < BN / 64; ++c)
-                        tma_load_2d(sb + c * (TC_BK * 128), &map_b, &full_bar[stage], n0 + 64 * c, k0);
-                }
-                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
-            }
-        } else if (threadIdx.x == 32) {
-            // ===================== MMA issuer (one thread) =====================
-            constexpr uint32_t idesc = umma_idesc(TC_BM, BN, A_MN, B_MN);
-            int stage = 0; uint32_t phase = 0;
-            for (int kb = kb_begin; kb < kb_end; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-                const uint32_t sb = sa + S::A_BYTES;
-#pragma unroll
-                for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-                    const uint64_t ad = A_MN ? umma_desc(sa + k * 2048, TC_BK * 128, 1024)
-                                             : umma_desc(sa + k * 32, 0, 1024);
-                    const uint64_t bd = B_MN ? umma_desc(sb + k * 2048, TC_BK * 128, 1024)
-                                             : umma_desc(sb + k * 32, 0, 1024);
-                    tcgen05_mma_f16(tmem_base, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
-                }
-                tcgen05_commit(&empty_bar[stage]);          // smem slot free once these MMAs retire
-                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
-            }
-            tcgen05_commit(tmem_full_bar);                  // accumulator complete
-        }
-        // ===================== epilogue: all 4 warps =====================
-        __syncwarp();
-        mbar_wait(tmem_full_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    const int row = m0 + warp * 32 + lane;
-    const bool have_acc = kb_begin < kb_end;
-    float* P = partial ? partial + (size_t)blockIdx.z * M * N : nullptr;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-        float v[16];
-        if (have_acc) {
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);   // warp-collective
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
-        const int col = n0 + c;
-        if (row < M && col < N) {
-            if (P != nullptr) {
-                float* dst = P + (size_t)row * N + col;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) if (col + i < N) dst[i] = v[i];
+    if (threadIdx.x == 0) {
+        // ===================== TMA producer =====================
+        const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + bn * TC_BK * 2);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char* sa = smem + stage * TC_STAGE_BYTES;
+            unsigned char* sb = sa + TC_A_BYTES;
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+            const int k0 = kb * TC_BK;
+            if (!a_mn) {
+                tma_load_2d(sa, &P.ma, &full_bar[stage], k0, m0);                      // box {64 k, 128 rows}
             } else {
-                float* dst = C + (int64_t)row * ldc + col;
-                const bool vec = (col + 15 < N) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x = alpha * v[i];
-                    if (bias != nullptr && col + i < N) x += __ldg(bias + col + i);
-                    v[i] = x;
-                }
-                if (vec) {
-                    if (beta != 0.f) {
+                for (int c = 0; c < TC_BM / 64; ++c)                                    // box {64 m, 64 k} per chunk
+                    tma_load_2d(sa + c * (TC_BK * 128), &P.ma, &full_bar[stage], m0 + 64 * c, k0);
+            }
+            if (!b_mn) {
+                tma_load_2d(sb, &P.mb, &full_bar[stage], k0, n0);                      // box {64 k, bn rows}
+            } else {
+                for (int c = 0; c < bn / 64; ++c)
+                    tma_load_2d(sb + c * (TC_BK * 128), &P.mb, &full_bar[stage], n0 + 64 * c, k0);
+            }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        TC_STAMP(3);
+    } else if (threadIdx.x == 32) {
+        // ===================== MMA issuer (one thread) =====================
+        const uint32_t idesc = umma_idesc(TC_BM, bn, a_mn, b_mn);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            if (kb == kb_begin) TC_STAMP(4);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+            const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 o = *reinterpret_cast<const float4*>(dst + i);
-                            v[i] += beta * o.x; v[i + 1] += beta * o.y; v[i + 2] += beta * o.z; v[i + 3] += beta * o.w;
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                const uint64_t ad = a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 0, 1024);
+                const uint64_t bd = b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 0, 1024);
+                tcgen05_mma_f16(tmem_base, ad, bd, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            }
+            tcgen05_commit(&empty_bar[stage]);          // smem slot free once these MMAs retire
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(tmem_full_bar);                  // accumulator complete (and every smem read retired)
+    }
+    // ===================== epilogue: all 4 warps =====================
+    __syncwarp();
+    mbar_wait(tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 64) TC_STAMP(5);
+
+    // TMEM -> padded smem tile (the operand ring is idle now); thread = one accumulator row
+    float* stg = reinterpret_cast<float*>(smem);
+    const int sld = bn + 4;
+    {
+        float* my = stg + (size_t)(warp * 32 + lane) * sld;
+        const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16);
+        int c = 0;
+        for (; c + 32 <= bn; c += 32) {              // two 16-column loads in flight per wait
+            uint32_t r[32];
+            tmem_ld16_nowait(tbase + (uint32_t)c, r);
+            tmem_ld16_nowait(tbase + (uint32_t)(c + 16), r + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(my + c + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+        if (c < bn) {
+            uint32_t r[16];
+            tmem_ld16_nowait(tbase + (uint32_t)c, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(my + c + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+        }
+    }
+    __syncwarp();
+    if (threadIdx.x == 64) TC_STAMP(8);
+    // each warp now streams out its own 32 rows, lanes along the columns: lane -> (row offset rr_off, float4 column cc)
+    const int lpr = bn >> 2;                                   // float4 columns per row (4..32)
+    const int rpp = 32 / lpr;                                  // rows per pass (1..8)
+    const int rr_off = lane / lpr, cc = lane - rr_off * lpr;   // the only divisions, hoisted out of the loops
+    const bool lane_on = rr_off < rpp;
+    const int splits = P.splits;
+    bool is_last = true;
+    if (splits > 1) {
+        float* mine = P.partial + ((size_t)tile * splits + split) * (size_t)(TC_BM * bn);
+        if (lane_on) {
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += rpp) {
+                const int row = warp * 32 + r0 + rr_off;
+                *reinterpret_cast<float4*>(mine + (size_t)row * bn + 4 * cc) = *reinterpret_cast<const float4*>(stg + (size_t)row * sld + 4 * cc);
+            }
+        }
+        if (threadIdx.x == 64) TC_STAMP(9);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 64) TC_STAMP(10);
+        if (threadIdx.x == 0) {
+            const unsigned old = atomicAdd(P.ticket + tile, 1u);
+            const bool last = old == (unsigned)(splits - 1);
+            if (last) P.ticket[tile] = 0;            // every split has taken its ticket: reset for the next launch
+            *last_flag = last ? 1u : 0u;
+        }
+        __syncthreads();
+        is_last = *last_flag != 0;
+        if (is_last) {
+            __threadfence();
+            // fold all partials in split order (deterministic) back into the smem tile, 8 rows of loads in flight
+            if (lane_on) {
+                const float* src = P.partial + (size_t)tile * splits * (size_t)(TC_BM * bn) + 4 * cc;
+                constexpr int FB = 16;                     // rows of loads in flight per lane
+                const int step = FB * rpp;
+                for (int r0 = 0; r0 < 32; r0 += step) {
+                    float4 acc[FB];
+#pragma unroll
+                    for (int j = 0; j < FB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int z = 0; z < splits; ++z) {
+                        float4 a[FB];
+#pragma unroll
+                        for (int j = 0; j < FB; ++j) {
+                            const int lr = r0 + j * rpp + rr_off;
+                            a[j] = lr < 32 ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * (TC_BM * bn) + (size_t)(warp * 32 + lr) * bn))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
+#pragma unroll
+                        for (int j = 0; j < FB; ++j) { acc[j].x += a[j].x; acc[j].y += a[j].y; acc[j].z += a[j].z; acc[j].w += a[j].w; }
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                } else {
+                    for (int j = 0; j < FB; ++j) {
+                        const int lr = r0 + j * rpp + rr_off;
+                        if (lr < 32) *reinterpret_cast<float4*>(stg + (size_t)(warp * 32 + lr) * sld + 4 * cc) = acc[j];
+                    }
+                }
+            }
+            __syncwarp();
+            if (threadIdx.x == 64) TC_STAMP(11);
+        }
+    }
+    if (threadIdx.x == 64) TC_STAMP(13);
+    if (is_last && lane_on) {
+        const int M = P.M, N = P.N;
+        float* const C = P.C;
+        __nv_bfloat16* const Cb = P.Cb;
+        const long long ldc = P.ldc, ldcb = P.ldcb;
+        const bool vec_ok = (N % 4 == 0) && (C == nullptr || ((ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0))) &&
+                            (Cb == nullptr || ((ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 7) == 0)));
+        const float alpha = P.alpha, beta = P.beta;
+        const int col = n0 + 4 * cc;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.bias != nullptr) {
+            if (col < N) bv.x = __ldg(P.bias + col);
+            if (col + 1 < N) bv.y = __ldg(P.bias + col + 1);
+            if (col + 2 < N) bv.z = __ldg(P.bias + col + 2);
+            if (col + 3 < N) bv.w = __ldg(P.bias + col + 3);
+        }
+        if (threadIdx.x == 64) TC_STAMP(12);
+        // rows this lane streams out: local rows lrow0, lrow0 + rpp, ... (nvalid of them inside M)
+        const int lrow0 = warp * 32 + rr_off;
+        int nvalid = 32 / rpp;
+        {
+            const int left = M - (m0 + lrow0);                 // rows of the matrix at or below this lane's first row
+            const int cap = left <= 0 ? 0 : (left + rpp - 1) / rpp;
+            if (cap < nvalid) nvalid = cap;
+        }
+        const float* sp = stg + (size_t)lrow0 * sld + 4 * cc;
+        const int sstep = rpp * sld;
+        if (col < N && vec_ok) {
+            float* cp = C != nullptr ? C + (long long)(m0 + lrow0) * ldc + col : nullptr;
+            __nv_bfloat16* bp = Cb != nullptr ? Cb + (long long)(m0 + lrow0) * ldcb + col : nullptr;
+            const long long cstep = (long long)rpp * ldc, bstep = (long long)rpp * ldcb;
+            const bool acc_c = beta != 0.f && cp != nullptr;
+            for (int q0 = 0; q0 < nvalid; q0 += 8) {           // 8 smem reads in flight, then 8 row-contiguous stores
+                float4 v[8], o[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (col + i < N) dst[i] = v[i] + (beta != 0.f ? beta * dst[i] : 0.f);
+                for (int j = 0; j < 8; ++j)
+                    if (q0 + j < nvalid) v[j] = *reinterpret_cast<const float4*>(sp + (size_t)(q0 + j) * sstep);
+                if (acc_c) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (q0 + j < nvalid) o[j] = *reinterpret_cast<const float4*>(cp + (q0 + j) * cstep);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (q0 + j >= nvalid) continue;
+                    float4 x = make_float4(fmaf(alpha, v[j].x, bv.x), fmaf(alpha, v[j].y, bv.y), fmaf(alpha, v[j].z, bv.z), fmaf(alpha, v[j].w, bv.w));
+                    if (acc_c) { x.x = fmaf(beta, o[j].x, x.x); x.y = fmaf(beta, o[j].y, x.y); x.z = fmaf(beta, o[j].z, x.z); x.w = fmaf(beta, o[j].w, x.w); }
+                    if (cp != nullptr) *reinterpret_cast<float4*>(cp + (q0 + j) * cstep) = x;
+                    if (bp != nullptr) *reinterpret_cast<uint2*>(bp + (q0 + j) * bstep) = pack_bf16x4(x);
+                }
+                if (threadIdx.x == 64 && q0 == 0) TC_STAMP(14);
+            }
+        } else if (col < N) {
+            // ragged N / unaligned outputs: element-wise with guards
+            for (int q = 0; q < nvalid; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)q * sstep);
+                const long long row = m0 + lrow0 + (long long)q * rpp;
+                const float xs[4] = {fmaf(alpha, v.x, bv.x), fmaf(alpha, v.y, bv.y), fmaf(alpha, v.z, bv.z), fmaf(alpha, v.w, bv.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (col + i >= N) continue;
+                    float y = xs[i];
+                    if (C != nullptr) {
+                        float* dst = C + row * ldc + col + i;
+                        if (beta != 0.f) y = fmaf(beta, *dst, y);
+                        *dst = y;
+                    }
+                    if (Cb != nullptr) Cb[row * ldcb + col + i] = __float2bfloat16_rn(y);
                 }
             }
         }
     }
+    if (threadIdx.x == 64) TC_STAMP(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) TC_STAMP(7);
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
     }
-}
-
-__global__ void __launch_bounds__(256)
-tc_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int M, int N, float alpha, float beta,
-                        float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)M * N) return;
-    const int m = (int)(idx / N), n = (int)(idx % N);
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[(size_t)z * M * N + idx];      // fixed order
-    float v = alpha * s;
-    if (bias != nullptr) v += bias[n];
-    if (beta != 0.f) v += beta * C[(int64_t)m * ldc + n];
-    C[(int64_t)m * ldc + n] = v;
 }
 
 // fp32 -> bf16 (hi) and optional residual (lo = bf16(x - hi)); rows x cols with leading dims
@@ -286,6 +454,11 @@ f32_to_bf16_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int
 // ------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
+static bool g_pdl = false;
+static unsigned long long* g_dbg = nullptr;
+
+void tc_set_pdl(bool on) { g_pdl = on; }
+bool tc_pdl() { return g_pdl; }
 
 static int get_encode() {
     std::call_once(g_encode_once, [] {
@@ -294,6 +467,8 @@ static int get_encode() {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        const char* e = getenv("TEAM_PDL");
+        if (e != nullptr) g_pdl = e[0] != '0';
     });
     if (g_encode == nullptr) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -319,75 +494,142 @@ static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t o
     return TEAM_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int tc_launch(cudaStream_t st, const TcGemm& g, int splits, int kbps, float* partial) {
-    using S = TcSmem<BN>;
-    CUtensorMap ma, ma2, mb;
-    int rc;
-    // K-major operand [rows,K]: inner = K, box {64, tile rows};  MN-major operand [K,rows]: inner = rows, box {64, 64}
-    if (!A_MN) rc = make_map(&ma, g.A, g.K, g.M, g.lda, TC_BK, TC_BM); else rc = make_map(&ma, g.A, g.M, g.K, g.lda, 64, TC_BK);
-    if (rc) return rc;
-    if (g.A2 != nullptr) {
-        if (!A_MN) rc = make_map(&ma2, g.A2, g.K, g.M, g.lda, TC_BK, TC_BM); else rc = make_map(&ma2, g.A2, g.M, g.K, g.lda, 64, TC_BK);
-        if (rc) return rc;
-    } else {
-        ma2 = ma;
-    }
-    if (!B_MN) rc = make_map(&mb, g.B, g.K, g.N, g.ldb, TC_BK, BN); else rc = make_map(&mb, g.B, g.N, g.K, g.ldb, 64, TC_BK);
-    if (rc) return rc;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
-    static bool attr_set = false;          // per template instantiation
+size_t tc_workspace_bytes(size_t partial_bytes) { return (size_t)TC_MAX_TICKETS * sizeof(unsigned) + partial_bytes; }
+
+int tc_workspace_init(cudaStream_t st, void* ws, size_t ws_bytes) {
+    if (ws == nullptr || ws_bytes < (size_t)TC_MAX_TICKETS * sizeof(unsigned)) return TEAM_OK;
+    TEAM_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)TC_MAX_TICKETS * sizeof(unsigned), st));
+    return TEAM_OK;
+}
+
+static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double flops, double bytes) {
+    static bool attr_set = false;
     if (!attr_set) {
-        TEAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(TC_MAX_STAGES)));
         attr_set = true;
     }
-    dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + TC_BM - 1) / TC_BM), (unsigned)splits);
-    const int pslot = prof_enabled() ? prof_begin(st, 1, 2.0 * g.M * g.N * g.K * (g.A2 ? 2 : 1),
-                                                  2.0 * (g.M * g.K * (g.A2 ? 2 : 1) + g.N * g.K) + 4.0 * g.M * g.N) : -1;
-    kern<<<grid, TC_THREADS, S::BYTES, st>>>(ma, ma2, mb, (int)g.M, (int)g.N, (int)g.K, kbps, g.A2 != nullptr ? 1 : 0,
-                                             g.alpha, g.beta, g.bias, g.C, g.ldc, partial);
+    const int pslot = prof_enabled() ? prof_begin(st, 1, flops, bytes) : -1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)total_ctas, 1, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = tc_smem_bytes(grp.stages);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel, grp);
     if (pslot >= 0) prof_end(st, pslot);
-    TEAM_LAUNCH_CHECK("gemm_bf16_tcgen05_kernel");
-    if (splits > 1) {
-        const int64_t tot = g.M * g.N;
-        tc_splitk_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(partial, splits, (int)g.M, (int)g.N, g.alpha, g.beta, g.C, g.ldc, g.bias);
-        TEAM_LAUNCH_CHECK("tc_splitk_reduce_kernel");
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16_tcgen05_kernel");
+    return TEAM_OK;
+}
+
+// Plans tiles / splits for ops[0..n) and launches them in chunks of TC_MAXP problems.
+int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t ws_bytes) {
+    int rc = get_encode();
+    if (rc) return rc;
+    unsigned* tickets = reinterpret_cast<unsigned*>(ws);
+    char* part_base = ws ? reinterpret_cast<char*>(ws) + (size_t)TC_MAX_TICKETS * sizeof(unsigned) : nullptr;
+    const size_t part_cap = (ws && ws_bytes > (size_t)TC_MAX_TICKETS * sizeof(unsigned)) ? ws_bytes - (size_t)TC_MAX_TICKETS * sizeof(unsigned) : 0;
+    for (int base = 0; base < n; base += TC_MAXP) {
+        const int cnt = n - base < TC_MAXP ? n - base : TC_MAXP;
+        TcGroup grp;
+        memset(&grp, 0, sizeof(grp));
+        int np = 0;
+        int tiles[TC_MAXP], nkbs[TC_MAXP];
+        for (int i = 0; i < cnt; ++i) {
+            const TcGemm& g = ops[base + i];
+            if (g.M <= 0 || g.N <= 0) continue;
+            TEAM_REQUIRE(g.K > 0 && g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm_bf16: K=%lld lda=%lld ldb=%lld (leading dims must be multiples of 8)", (long long)g.K, (long long)g.lda, (long long)g.ldb);
+            TEAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0, "gemm_bf16: operands must be 16-byte aligned");
+            TEAM_REQUIRE(g.C != nullptr || g.Cb != nullptr, "gemm_bf16: no output");
+            TcProb& p = grp.p[np];
+            const int tiles_m = (int)((g.M + TC_BM - 1) / TC_BM);
+            // N tile: up to 128 wide; halve it while the problem alone would leave most SMs without a tile
+            int bn;
+            const int nt128 = (int)((g.N + TC_MAX_BN - 1) / TC_MAX_BN);
+            const bool narrow = tiles_m * nt128 * 2 <= NUM_SMS && g.N > 64;
+            if (g.b_mn) {
+                bn = (g.N > 64 && !narrow) ? 128 : 64;
+            } else {
+                const int nt = narrow ? (int)((g.N + 63) / 64) : nt128;
+                bn = (int)(((g.N + nt - 1) / nt + 15) / 16 * 16);
+            }
+            p.bn = bn;
+            p.tiles_n = (int)((g.N + bn - 1) / bn);
+            p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
+            p.a_mn = g.a_mn ? 1 : 0; p.b_mn = g.b_mn ? 1 : 0;
+            p.alpha = g.alpha; p.beta = g.beta;
+            p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias;
+            // K-major operand [rows,K]: inner = K, box {64, tile rows};  MN-major operand [K,rows]: inner = rows, box {64, 64}
+            if (!g.a_mn) rc = make_map(&p.ma, g.A, g.K, g.M, g.lda, TC_BK, TC_BM); else rc = make_map(&p.ma, g.A, g.M, g.K, g.lda, 64, TC_BK);
+            if (rc) return rc;
+            if (!g.b_mn) rc = make_map(&p.mb, g.B, g.K, g.N, g.ldb, TC_BK, bn); else rc = make_map(&p.mb, g.B, g.N, g.K, g.ldb, 64, TC_BK);
+            if (rc) return rc;
+            tiles[np] = tiles_m * p.tiles_n;
+            nkbs[np] = (int)((g.K + TC_BK - 1) / TC_BK);
+            p.splits = 1;
+            ++np;
+        }
+        if (np == 0) continue;
+        // split-K: long-K problems get ~12 k-blocks per CTA while the launch stays within two CTAs per SM
+        int total = 0;
+        for (int i = 0; i < np; ++i) total += tiles[i];
+        if (part_base != nullptr) {
+            for (;;) {
+                int best = -1, best_kb = 12;
+                for (int i = 0; i < np; ++i) {
+                    const int per = (nkbs[i] + grp.p[i].splits - 1) / grp.p[i].splits;
+                    if (per > best_kb && grp.p[i].splits < 16 && total + tiles[i] <= TC_TARGET_CTAS) { best = i; best_kb = per; }
+                }
+                if (best < 0) break;
+                grp.p[best].splits += 1;
+                total += tiles[best];
+            }
+        }
+        size_t part_off = 0;
+        int ticket_off = 0, cta = 0;
+        double flops = 0, bytes = 0;
+        for (int i = 0; i < np; ++i) {
+            TcProb& p = grp.p[i];
+            int kbps = (nkbs[i] + p.splits - 1) / p.splits;
+            p.splits = (nkbs[i] + kbps - 1) / kbps;
+            if (p.splits > 1) {
+                const size_t need = (size_t)tiles[i] * p.splits * TC_BM * p.bn * sizeof(float);
+                if (part_off + need > part_cap || ticket_off + tiles[i] > TC_MAX_TICKETS) { p.splits = 1; kbps = nkbs[i]; }
+                else {
+                    p.partial = reinterpret_cast<float*>(part_base + part_off);
+                    p.ticket = tickets + ticket_off;
+                    part_off += need; ticket_off += tiles[i];
+                }
+            }
+            p.kb_per_split = kbps;
+            p.cta_begin = cta;
+            cta += tiles[i] * p.splits;
+            flops += 2.0 * p.M * p.N * p.K;
+            bytes += 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + (p.C ? 4.0 : 0.0) * p.M * p.N + (p.Cb ? 2.0 : 0.0) * p.M * p.N;
+        }
+        grp.n = np;
+        grp.stages = cta <= NUM_SMS ? TC_MAX_STAGES : TC_STAGES;
+        grp.dbg = g_dbg;
+        if ((rc = tc_launch(st, grp, cta, flops, bytes))) return rc;
     }
     return TEAM_OK;
 }
 
 int gemm_bf16_tc(cudaStream_t st, const TcGemm& g, void* ws, size_t ws_bytes) {
-    int rc = get_encode();
+    if (g.A2 == nullptr) return gemm_bf16_group(st, &g, 1, ws, ws_bytes);
+    // two-term split of A: C = alpha (A_hi + A_lo) B + ... as two accumulating passes
+    TcGemm a = g, b = g;
+    a.A2 = nullptr;
+    int rc = gemm_bf16_group(st, &a, 1, ws, ws_bytes);
     if (rc) return rc;
-    if (g.M <= 0 || g.N <= 0) return TEAM_OK;
-    TEAM_REQUIRE(g.K > 0 && g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm_bf16_tc: K=%lld lda=%lld ldb=%lld (leading dims must be multiples of 8)", (long long)g.K, (long long)g.lda, (long long)g.ldb);
-    TEAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0, "gemm_bf16_tc: operands must be 16-byte aligned");
-    // tile width: the widest BN that still fills the machine
-    const int64_t mt = (g.M + TC_BM - 1) / TC_BM;
-    int BN = 128;
-    if (g.N <= 64 || mt * ((g.N + 127) / 128) < NUM_SMS) BN = 64;
-    const int64_t tiles = mt * ((g.N + BN - 1) / BN);
-    const int nkb = (int)((g.K + TC_BK - 1) / TC_BK);
-    const int total_kb = g.A2 ? 2 * nkb : nkb;
-    int splits = 1;
-    if (tiles * 2 <= NUM_SMS && total_kb >= 8 && ws != nullptr) {
-        int64_t s = NUM_SMS / tiles;
-        if (s > total_kb / 4) s = total_kb / 4;
-        if (s >= 2 && (size_t)s * g.M * g.N * sizeof(float) <= ws_bytes) splits = (int)s;
-    }
-    int kbps = (total_kb + splits - 1) / splits;
-    splits = (total_kb + kbps - 1) / kbps;
-    float* partial = splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
-#define TC_DISPATCH(BN_)                                                                       \
-    do {                                                                                       \
-        if (!g.a_mn && !g.b_mn) return tc_launch<BN_, false, false>(st, g, splits, kbps, partial); \
-        if (!g.a_mn && g.b_mn) return tc_launch<BN_, false, true>(st, g, splits, kbps, partial);   \
-        if (g.a_mn && !g.b_mn) return tc_launch<BN_, true, false>(st, g, splits, kbps, partial);   \
-        return tc_launch<BN_, true, true>(st, g, splits, kbps, partial);                        \
-    } while (0)
-    if (BN == 128) TC_DISPATCH(128);
-    TC_DISPATCH(64);
-#undef TC_DISPATCH
+    b.A = g.A2; b.A2 = nullptr; b.beta = 1.f; b.bias = nullptr;
+    TEAM_REQUIRE(g.C != nullptr && g.Cb == nullptr, "gemm_bf16: the two-term A split needs an fp32 output");
+    return gemm_bf16_group(st, &b, 1, ws, ws_bytes);
 }
 
 int to_bf16(cudaStream_t st, const float* src, int64_t lds, int64_t rows, int cols, void* hi, void* lo, int64_t ldd) {
@@ -399,14 +641,6 @@ int to_bf16(cudaStream_t st, const float* src, int64_t lds, int64_t rows, int co
     return TEAM_OK;
 }
 
-size_t tc_operand_bytes(const HeadDims& d) {
-    // generous bound on the bf16 copies one fwd or bwd call makes (see BfCache in head.cu)
-    const size_t B2 = d.B2, Nsp = d.Nsp;
-    const size_t elems = B2 * (20 * (size_t)D + 8 * Nsp) + Nsp * (16 * (size_t)D + 6 * Nsp) + 16 * (size_t)D * D +
-                         (size_t)(d.Rt + d.C + 64 + (d.Tc > 0 ? d.Tc : 0)) * 4 * D;
-    return align_up(elems * 2 + 96 * 256, 256);
-}
-
 }  // namespace team
 
 using namespace team;
@@ -415,9 +649,29 @@ extern "C" int team_gemm_bf16(int a_mn, int b_mn, int64_t M, int64_t N, int64_t 
                               const void* A_lo, int64_t lda, const void* B, int64_t ldb, float beta, float* C,
                               int64_t ldc, const float* bias, void* workspace, size_t workspace_bytes, void* stream) {
     TcGemm g;
+    memset(&g, 0, sizeof(g));
     g.a_mn = a_mn != 0; g.b_mn = b_mn != 0; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
     g.A = A; g.A2 = A_lo; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
+    int rc = tc_workspace_init((cudaStream_t)stream, workspace, workspace_bytes);
+    if (rc) return rc;
     return gemm_bf16_tc((cudaStream_t)stream, g, workspace, workspace_bytes);
+}
+
+extern "C" int team_gemm_bf16_group(const team_gemm_desc* descs, int32_t n, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+    TEAM_REQUIRE(descs != nullptr && n >= 1 && n <= 64, "team_gemm_bf16_group: bad args");
+    TcGemm ops[64];
+    for (int i = 0; i < n; ++i) {
+        const team_gemm_desc& d = descs[i];
+        TcGemm& g = ops[i];
+        memset(&g, 0, sizeof(g));
+        g.a_mn = d.a_mn != 0; g.b_mn = d.b_mn != 0; g.M = d.M; g.N = d.N; g.K = d.K; g.alpha = d.alpha; g.beta = d.beta;
+        g.A = d.A; g.lda = d.lda; g.B = d.B; g.ldb = d.ldb; g.C = d.C; g.ldc = d.ldc; g.Cb = d.C_bf16; g.ldcb = d.ldc_bf16;
+        g.bias = d.bias;
+    }
+    int rc = tc_workspace_init((cudaStream_t)stream, workspace, workspace_bytes);
+    if (rc) return rc;
+    return gemm_bf16_group((cudaStream_t)stream, ops, n, workspace, workspace_bytes);
 }
 
 extern "C" int team_gemm_bf16_nt(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
@@ -428,4 +682,14 @@ extern "C" int team_gemm_bf16_nt(int64_t M, int64_t N, int64_t K, const void* A,
 extern "C" int team_f32_to_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, void* hi, void* lo,
                                 int64_t ldd, void* stream) {
     return to_bf16((cudaStream_t)stream, src, lds, rows, (int)cols, hi, lo, ldd);
+}
+
+extern "C" int team_gemm_debug_stamps(void* buf) {
+    g_dbg = reinterpret_cast<unsigned long long*>(buf);
+    return TEAM_OK;
+}
+
+extern "C" int team_set_pdl(int on) {
+    tc_set_pdl(on != 0);
+    return TEAM_OK;
 }

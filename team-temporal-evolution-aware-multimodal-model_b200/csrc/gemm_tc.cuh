@@ -1,6 +1,6 @@
-// tcgen05 / TMA / TMEM bf16 GEMM (mode BF16) - declarations.
+// tcgen05 / TMA / TMEM bf16 grouped GEMM (mode BF16) - declarations.
 #pragma once
-#include "head.cuh"
+#include "common.cuh"
 
 namespace team {
 
@@ -9,19 +9,25 @@ struct TcGemm {
     int64_t M, N, K;
     float alpha, beta;
     const void* A;            // bf16
-    const void* A2;           // optional bf16 "lo" half of A (same layout), may be null
+    const void* A2;           // optional bf16 "lo" half of A (same layout), single-problem entry only
     int64_t lda;
     const void* B;            // bf16
     int64_t ldb;
-    float* C;                 // fp32 [M,N]
+    float* C;                 // fp32 [M,N] output (and beta input), may be null if Cb is set
     int64_t ldc;
+    void* Cb;                 // bf16 [M,N] copy of the output, may be null
+    int64_t ldcb;
     const float* bias;        // fp32 [N] or null
 };
 
+// one launch per TC_MAXP problems; ws = [tickets | split-K partials] (tc_workspace_init zeroes the tickets)
+int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t ws_bytes);
 int gemm_bf16_tc(cudaStream_t st, const TcGemm& g, void* ws, size_t ws_bytes);
+size_t tc_workspace_bytes(size_t partial_bytes);
+int tc_workspace_init(cudaStream_t st, void* ws, size_t ws_bytes);
+void tc_set_pdl(bool on);
+bool tc_pdl();
 // fp32 [rows,cols] (lds) -> bf16 hi (+ optional lo = bf16(x - hi)) with leading dimension ldd
 int to_bf16(cudaStream_t st, const float* src, int64_t lds, int64_t rows, int cols, void* hi, void* lo, int64_t ldd);
-// bytes of bf16 operand staging the BF16 mode needs inside the head workspace
-size_t tc_operand_bytes(const HeadDims& d);
 
 }  // namespace team

@@ -13,6 +13,14 @@ HeadDims head_dims(int64_t B, int C, int P, int Tc) {
     return d;
 }
 
+static size_t tc_operand_bytes(const HeadDims& d) {
+    // generous bound on the bf16 copies one fwd or bwd call makes (see BfCache below)
+    const size_t B2 = d.B2, Nsp = d.Nsp;
+    const size_t elems = B2 * (20 * (size_t)D + 8 * Nsp) + Nsp * (16 * (size_t)D + 6 * Nsp) + 16 * (size_t)D * D +
+                         (size_t)(d.Rt + d.C + 64 + (d.Tc > 0 ? d.Tc : 0)) * 4 * D;
+    return align_up(elems * 2 + 96 * 256, 256);
+}
+
 void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     size_t off = 0;
     auto take = [&](size_t n_floats) -> float* {
@@ -115,7 +123,7 @@ static int hgemm(HeadCtx& cx, bool ta, bool tb, int64_t M, int64_t N, int64_t K,
     if (!tc_ok) return gemm_f32(cx.st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
     TcGemm g;
     g.a_mn = ta; g.b_mn = !tb; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
-    g.A2 = nullptr; g.lda = lda; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
+    g.A2 = nullptr; g.Cb = nullptr; g.ldcb = 0; g.lda = lda; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
     int rc = bf16_view(cx, A, ta ? K : M, ta ? M : K, lda, &g.A);
     if (rc) return rc;
     if ((rc = bf16_view(cx, B, tb ? N : K, tb ? K : N, ldb, &g.B))) return rc;
@@ -207,6 +215,7 @@ static int setup(HeadCtx& cx, const team_head_weights* hw, int mode, int64_t bat
     cx.bc.n = 0; cx.bc.used = 0;
     cx.bc.area = reinterpret_cast<char*>(cx.w.bf16_area);
     cx.bc.cap = cx.w.bf16_bytes;
+    if (mode == TEAM_MODE_BF16) return tc_workspace_init(cx.st, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
     return TEAM_OK;
 }
 

@@ -86,3 +86,59 @@ def test_gemm_bf16_epilogue_and_split():
     # two-term split recovers the fp32 operand to ~2^-17
     ref32 = 0.25 * (Af.double() @ Bq.double().t()) + bias.double() - 1.5 * C0.double()
     assert rel(Cm, ref32) < 3e-5
+
+
+@pytest.mark.parametrize("with_ws", [True, False])
+def test_gemm_bf16_group(with_ws):
+    """Grouped launch: 11 problems (two launches) with mixed operand majors, ragged shapes, long K (in-kernel
+    split-K with fixed-order fold), fp32 / bf16 / dual outputs, alpha/beta/bias - each against fp64."""
+    from team_b200 import capi
+    capi.require_device()
+    g = torch.Generator().manual_seed(11)
+    pad = lambda n: (n + 7) // 8 * 8
+    specs = [  # a_mn, b_mn, M, N, K, alpha, beta, bias, out ("f", "b", "fb")
+        (0, 0, 2048, 144, 512, 0.5, 0.0, False, "f"), (0, 0, 2048, 144, 512, 1.0, 0.0, False, "fb"),
+        (1, 1, 512, 512, 2192, 1.0, 0.0, False, "fb"), (1, 1, 144, 512, 2192, 1.0, 1.0, False, "f"),
+        (0, 1, 2048, 512, 144, 1.0, 1.0, False, "fb"), (0, 0, 20, 512, 512, 1.0, 0.0, True, "f"),
+        (0, 0, 10, 512, 512, 1.0, 0.0, True, "fb"), (0, 1, 512, 512, 512, 1.0, 0.0, False, "b"),
+        (0, 0, 300, 72, 200, 2.0, -1.0, True, "f"), (1, 0, 130, 70, 136, 1.0, 0.0, False, "f"),
+        (0, 1, 2048, 512, 1536, 1.0, 1.0, False, "f")]
+    descs = (capi.GemmDesc * len(specs))()
+    keep, checks = [], []
+    for i, (a_mn, b_mn, M, N, K, alpha, beta, use_bias, out) in enumerate(specs):
+        A = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), generator=g).to(torch.bfloat16).cuda()
+        B = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), generator=g).to(torch.bfloat16).cuda()
+        Av = A[:, :M] if a_mn else A[:, :K]
+        Bv = B[:, :N] if b_mn else B[:, :K]
+        C0 = torch.randn((M, N), generator=g).cuda()
+        bias = torch.randn((N,), generator=g).cuda() if use_bias else None
+        ref = alpha * ((Av.double().t() if a_mn else Av.double()) @ (Bv.double() if b_mn else Bv.double().t()))
+        if use_bias:
+            ref = ref + bias.double()
+        if beta != 0.0:
+            ref = ref + beta * C0.double()
+        Cf = C0.clone() if "f" in out or beta != 0.0 else None
+        Cb = torch.zeros((M, pad(N)), dtype=torch.bfloat16, device="cuda") if "b" in out else None
+        d = descs[i]
+        d.a_mn, d.b_mn, d.M, d.N, d.K, d.alpha, d.beta = a_mn, b_mn, M, N, K, alpha, beta
+        d.A, d.lda, d.B, d.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+        d.C, d.ldc = (Cf.data_ptr(), N) if Cf is not None else (None, 0)
+        d.C_bf16, d.ldc_bf16 = (Cb.data_ptr(), Cb.stride(0)) if Cb is not None else (None, 0)
+        d.bias = bias.data_ptr() if use_bias else None
+        keep += [A, B, C0, bias]
+        checks.append((Cf, Cb, ref, N))
+    ws = torch.empty(64 << 20 if with_ws else 1, dtype=torch.uint8, device="cuda")
+    for rep in range(2):          # second round: the split-K tickets must have reset themselves
+        if rep == 1:
+            for i, (a_mn, b_mn, M, N, K, alpha, beta, use_bias, out) in enumerate(specs):
+                if checks[i][0] is not None:
+                    checks[i][0].copy_(keep[4 * i + 2])
+        capi.check(capi.lib().team_gemm_bf16_group(descs, len(specs), ws.data_ptr() if with_ws else None,
+                                                   ws.numel() if with_ws else 0, _st()), "team_gemm_bf16_group")
+        torch.cuda.synchronize()
+        for i, (Cf, Cb, ref, N) in enumerate(checks):
+            if Cf is not None:
+                assert rel(Cf, ref) < 3e-6, (rep, i, rel(Cf, ref))
+            if Cb is not None:
+                assert rel(Cb[:, :N].float(), ref) < 4e-3, (rep, i)
+                assert torch.equal(Cb[:, :N], (Cf if Cf is not None else ref.float()).to(torch.bfloat16)) or Cf is None
