@@ -250,6 +250,12 @@ typedef struct team_gemm_desc {
     float* C; int64_t ldc;
     void* C_bf16; int64_t ldc_bf16;
     const float* bias;
+    /* optional second K-segment accumulated into the same output tile: C = alpha (op(A) op(B) + op(A2) op(B2)) ...
+     * (K2 = 0: none).  Lets dW = dQo^T Xo + dQs^T S run as one problem. */
+    int32_t a_mn2, b_mn2;
+    int64_t K2;
+    const void* A2; int64_t lda2;
+    const void* B2; int64_t ldb2;
 } team_gemm_desc;
 int team_gemm_bf16_group(const team_gemm_desc* descs, int32_t n, void* workspace, size_t workspace_bytes, void* stream);
 /* programmatic dependent launch for the library's kernels (default: env TEAM_PDL, else off) */

@@ -67,7 +67,9 @@ class GemmDesc(C.Structure):
     _fields_ = [("a_mn", C.c_int32), ("b_mn", C.c_int32), ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
                 ("alpha", C.c_float), ("beta", C.c_float), ("A", C.c_void_p), ("lda", C.c_int64),
                 ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
-                ("C_bf16", C.c_void_p), ("ldc_bf16", C.c_int64), ("bias", C.c_void_p)]
+                ("C_bf16", C.c_void_p), ("ldc_bf16", C.c_int64), ("bias", C.c_void_p),
+                ("a_mn2", C.c_int32), ("b_mn2", C.c_int32), ("K2", C.c_int64),
+                ("A2", C.c_void_p), ("lda2", C.c_int64), ("B2", C.c_void_p), ("ldb2", C.c_int64)]
 
 
 _lib = None

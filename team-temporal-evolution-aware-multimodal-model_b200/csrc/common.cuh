@@ -63,6 +63,14 @@ __device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a);
+    o.y = *reinterpret_cast<const uint32_t*>(&b);
+    return o;
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace team

@@ -43,14 +43,18 @@ constexpr int TC_B_BYTES = TC_MAX_BN * TC_BK * 2;      // 16 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }   // 3 stages: 97.25 KB -> 2 CTAs / SM
 constexpr uint32_t TC_TMEM_COLS = 128;
-constexpr int TC_MAXP = 8;           // problems per launch (kernel parameter space: 8 * 384 B)
+constexpr int TC_MAXP = 8;           // problems per launch (kernel parameter space: 8 * 768 B; CUDA >= 12.1 allows 32 KB)
 constexpr int TC_MAX_TICKETS = 4096; // split-K tickets at the head of the workspace
 constexpr int TC_TARGET_CTAS = 2 * NUM_SMS;
 
 static_assert(TC_BM * (TC_MAX_BN + 4) * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilogue staging must fit in the operand ring");
 
-struct alignas(64) TcProb {
+struct alignas(64) TcSegDev {
     CUtensorMap ma, mb;
+    int K, nkb, a_mn, b_mn;
+};
+struct alignas(64) TcProb {
+    TcSegDev s[2];            // K-segments accumulated into the same TMEM tile (s[1].nkb == 0: single segment)
     float* C;
     __nv_bfloat16* Cb;
     const float* bias;
@@ -58,9 +62,8 @@ struct alignas(64) TcProb {
     unsigned* ticket;
     long long ldc, ldcb;
     float alpha, beta;
-    int M, N, K;
+    int M, N;
     int bn, tiles_n, cta_begin, splits, kb_per_split;
-    int a_mn, b_mn;
 };
 struct TcGroup {
     TcProb p[TC_MAXP];
@@ -148,14 +151,6 @@ __host__ __device__ inline uint32_t umma_idesc(int M, int N, int a_mn, int b_mn)
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
-    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 o;
-    o.x = *reinterpret_cast<const uint32_t*>(&a);
-    o.y = *reinterpret_cast<const uint32_t*>(&b);
-    return o;
-}
-
 // grid = total CTAs of the group; 128 threads.
 __global__ void __launch_bounds__(TC_THREADS)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
@@ -178,17 +173,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     const int local = (int)blockIdx.x - P.cta_begin;
     const int split = local % P.splits, tile = local / P.splits;
     const int m0 = (tile / P.tiles_n) * TC_BM, bn = P.bn, n0 = (tile % P.tiles_n) * bn;
-    const int nkb = (P.K + TC_BK - 1) / TC_BK;
+    const int nkb0 = P.s[0].nkb;
+    const int nkb = nkb0 + P.s[1].nkb;
     const int kb_begin = split * P.kb_per_split;
     const int kb_end = min(nkb, kb_begin + P.kb_per_split);
-    const int a_mn = P.a_mn, b_mn = P.b_mn;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.ma)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.mb)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.s[0].ma)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.s[0].mb)) : "memory");
+        if (P.s[1].nkb > 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.s[1].ma)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.s[1].mb)) : "memory");
+        }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -213,28 +212,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
             unsigned char* sa = smem + stage * TC_STAGE_BYTES;
             unsigned char* sb = sa + TC_A_BYTES;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
-            const int k0 = kb * TC_BK;
-            if (!a_mn) {
-                tma_load_2d(sa, &P.ma, &full_bar[stage], k0, m0);                      // box {64 k, 128 rows}
+            const TcSegDev& sg = P.s[kb >= nkb0 ? 1 : 0];
+            const int k0 = (kb >= nkb0 ? kb - nkb0 : kb) * TC_BK;
+            if (!sg.a_mn) {
+                tma_load_2d(sa, &sg.ma, &full_bar[stage], k0, m0);                     // box {64 k, 128 rows}
             } else {
 #pragma unroll
                 for (int c = 0; c < TC_BM / 64; ++c)                                    // box {64 m, 64 k} per chunk
-                    tma_load_2d(sa + c * (TC_BK * 128), &P.ma, &full_bar[stage], m0 + 64 * c, k0);
+                    tma_load_2d(sa + c * (TC_BK * 128), &sg.ma, &full_bar[stage], m0 + 64 * c, k0);
             }
-            if (!b_mn) {
-                tma_load_2d(sb, &P.mb, &full_bar[stage], k0, n0);                      // box {64 k, bn rows}
+            if (!sg.b_mn) {
+                tma_load_2d(sb, &sg.mb, &full_bar[stage], k0, n0);                     // box {64 k, bn rows}
             } else {
                 for (int c = 0; c < bn / 64; ++c)
-                    tma_load_2d(sb + c * (TC_BK * 128), &P.mb, &full_bar[stage], n0 + 64 * c, k0);
+                    tma_load_2d(sb + c * (TC_BK * 128), &sg.mb, &full_bar[stage], n0 + 64 * c, k0);
             }
             if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         TC_STAMP(3);
     } else if (threadIdx.x == 32) {
         // ===================== MMA issuer (one thread) =====================
-        const uint32_t idesc = umma_idesc(TC_BM, bn, a_mn, b_mn);
+        const uint32_t idesc0 = umma_idesc(TC_BM, bn, P.s[0].a_mn, P.s[0].b_mn);
+        const uint32_t idesc1 = umma_idesc(TC_BM, bn, P.s[1].a_mn, P.s[1].b_mn);
         int stage = 0; uint32_t phase = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
+            const int si = kb >= nkb0 ? 1 : 0;
+            const int a_mn = P.s[si].a_mn, b_mn = P.s[si].b_mn;
+            const uint32_t idesc = si ? idesc1 : idesc0;
             mbar_wait(&full_bar[stage], phase);
             if (kb == kb_begin) TC_STAMP(4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -540,19 +544,26 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
         memset(&grp, 0, sizeof(grp));
         int np = 0;
         int tiles[TC_MAXP], nkbs[TC_MAXP];
+        double kflops[TC_MAXP];
         for (int i = 0; i < cnt; ++i) {
             const TcGemm& g = ops[base + i];
             if (g.M <= 0 || g.N <= 0) continue;
-            TEAM_REQUIRE(g.K > 0 && g.lda % 8 == 0 && g.ldb % 8 == 0, "gemm_bf16: K=%lld lda=%lld ldb=%lld (leading dims must be multiples of 8)", (long long)g.K, (long long)g.lda, (long long)g.ldb);
-            TEAM_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0, "gemm_bf16: operands must be 16-byte aligned");
+            TEAM_REQUIRE(g.nseg == 1 || g.nseg == 2, "gemm_bf16: nseg %d", g.nseg);
             TEAM_REQUIRE(g.C != nullptr || g.Cb != nullptr, "gemm_bf16: no output");
+            bool any_b_mn = false;
+            for (int q = 0; q < g.nseg; ++q) {
+                const TcSeg& sg = g.s[q];
+                TEAM_REQUIRE(sg.K > 0 && sg.lda % 8 == 0 && sg.ldb % 8 == 0, "gemm_bf16: K=%lld lda=%lld ldb=%lld (leading dims must be multiples of 8)", (long long)sg.K, (long long)sg.lda, (long long)sg.ldb);
+                TEAM_REQUIRE((reinterpret_cast<uintptr_t>(sg.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(sg.B) & 15) == 0, "gemm_bf16: operands must be 16-byte aligned");
+                any_b_mn = any_b_mn || sg.b_mn;
+            }
             TcProb& p = grp.p[np];
             const int tiles_m = (int)((g.M + TC_BM - 1) / TC_BM);
             // N tile: up to 128 wide; halve it while the problem alone would leave most SMs without a tile
             int bn;
             const int nt128 = (int)((g.N + TC_MAX_BN - 1) / TC_MAX_BN);
             const bool narrow = tiles_m * nt128 * 2 <= NUM_SMS && g.N > 64;
-            if (g.b_mn) {
+            if (any_b_mn) {
                 bn = (g.N > 64 && !narrow) ? 128 : 64;
             } else {
                 const int nt = narrow ? (int)((g.N + 63) / 64) : nt128;
@@ -560,17 +571,25 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
             }
             p.bn = bn;
             p.tiles_n = (int)((g.N + bn - 1) / bn);
-            p.M = (int)g.M; p.N = (int)g.N; p.K = (int)g.K;
-            p.a_mn = g.a_mn ? 1 : 0; p.b_mn = g.b_mn ? 1 : 0;
+            p.M = (int)g.M; p.N = (int)g.N;
             p.alpha = g.alpha; p.beta = g.beta;
             p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias;
-            // K-major operand [rows,K]: inner = K, box {64, tile rows};  MN-major operand [K,rows]: inner = rows, box {64, 64}
-            if (!g.a_mn) rc = make_map(&p.ma, g.A, g.K, g.M, g.lda, TC_BK, TC_BM); else rc = make_map(&p.ma, g.A, g.M, g.K, g.lda, 64, TC_BK);
-            if (rc) return rc;
-            if (!g.b_mn) rc = make_map(&p.mb, g.B, g.K, g.N, g.ldb, TC_BK, bn); else rc = make_map(&p.mb, g.B, g.N, g.K, g.ldb, 64, TC_BK);
-            if (rc) return rc;
+            nkbs[np] = 0;
+            kflops[np] = 0;
+            for (int q = 0; q < g.nseg; ++q) {
+                const TcSeg& sg = g.s[q];
+                TcSegDev& sd = p.s[q];
+                sd.K = (int)sg.K; sd.a_mn = sg.a_mn ? 1 : 0; sd.b_mn = sg.b_mn ? 1 : 0;
+                sd.nkb = (int)((sg.K + TC_BK - 1) / TC_BK);
+                // K-major operand [rows,K]: inner = K, box {64, tile rows};  MN-major operand [K,rows]: inner = rows, box {64, 64}
+                if (!sg.a_mn) rc = make_map(&sd.ma, sg.A, sg.K, g.M, sg.lda, TC_BK, TC_BM); else rc = make_map(&sd.ma, sg.A, g.M, sg.K, sg.lda, 64, TC_BK);
+                if (rc) return rc;
+                if (!sg.b_mn) rc = make_map(&sd.mb, sg.B, sg.K, g.N, sg.ldb, TC_BK, bn); else rc = make_map(&sd.mb, sg.B, g.N, sg.K, sg.ldb, 64, TC_BK);
+                if (rc) return rc;
+                nkbs[np] += sd.nkb;
+                kflops[np] += (double)sg.K;
+            }
             tiles[np] = tiles_m * p.tiles_n;
-            nkbs[np] = (int)((g.K + TC_BK - 1) / TC_BK);
             p.splits = 1;
             ++np;
         }
@@ -609,8 +628,8 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
             p.kb_per_split = kbps;
             p.cta_begin = cta;
             cta += tiles[i] * p.splits;
-            flops += 2.0 * p.M * p.N * p.K;
-            bytes += 2.0 * ((double)p.M * p.K + (double)p.N * p.K) + (p.C ? 4.0 : 0.0) * p.M * p.N + (p.Cb ? 2.0 : 0.0) * p.M * p.N;
+            flops += 2.0 * p.M * p.N * kflops[i];
+            bytes += 2.0 * ((double)p.M + (double)p.N) * kflops[i] + (p.C ? 4.0 : 0.0) * p.M * p.N + (p.Cb ? 2.0 : 0.0) * p.M * p.N;
         }
         grp.n = np;
         grp.stages = cta <= NUM_SMS ? TC_MAX_STAGES : TC_STAGES;
@@ -622,12 +641,13 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
 
 int gemm_bf16_tc(cudaStream_t st, const TcGemm& g, void* ws, size_t ws_bytes) {
     if (g.A2 == nullptr) return gemm_bf16_group(st, &g, 1, ws, ws_bytes);
+    TEAM_REQUIRE(g.nseg == 1, "gemm_bf16: the two-term A split takes a single K-segment");
     // two-term split of A: C = alpha (A_hi + A_lo) B + ... as two accumulating passes
     TcGemm a = g, b = g;
     a.A2 = nullptr;
     int rc = gemm_bf16_group(st, &a, 1, ws, ws_bytes);
     if (rc) return rc;
-    b.A = g.A2; b.A2 = nullptr; b.beta = 1.f; b.bias = nullptr;
+    b.s[0].A = g.A2; b.A2 = nullptr; b.beta = 1.f; b.bias = nullptr;
     TEAM_REQUIRE(g.C != nullptr && g.Cb == nullptr, "gemm_bf16: the two-term A split needs an fp32 output");
     return gemm_bf16_group(st, &b, 1, ws, ws_bytes);
 }
@@ -650,8 +670,9 @@ extern "C" int team_gemm_bf16(int a_mn, int b_mn, int64_t M, int64_t N, int64_t 
                               int64_t ldc, const float* bias, void* workspace, size_t workspace_bytes, void* stream) {
     TcGemm g;
     memset(&g, 0, sizeof(g));
-    g.a_mn = a_mn != 0; g.b_mn = b_mn != 0; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
-    g.A = A; g.A2 = A_lo; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
+    g.M = M; g.N = N; g.nseg = 1; g.alpha = alpha; g.beta = beta;
+    g.s[0].a_mn = a_mn != 0; g.s[0].b_mn = b_mn != 0; g.s[0].K = K;
+    g.s[0].A = A; g.A2 = A_lo; g.s[0].lda = lda; g.s[0].B = B; g.s[0].ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
     int rc = tc_workspace_init((cudaStream_t)stream, workspace, workspace_bytes);
     if (rc) return rc;
     return gemm_bf16_tc((cudaStream_t)stream, g, workspace, workspace_bytes);
@@ -665,8 +686,13 @@ extern "C" int team_gemm_bf16_group(const team_gemm_desc* descs, int32_t n, void
         const team_gemm_desc& d = descs[i];
         TcGemm& g = ops[i];
         memset(&g, 0, sizeof(g));
-        g.a_mn = d.a_mn != 0; g.b_mn = d.b_mn != 0; g.M = d.M; g.N = d.N; g.K = d.K; g.alpha = d.alpha; g.beta = d.beta;
-        g.A = d.A; g.lda = d.lda; g.B = d.B; g.ldb = d.ldb; g.C = d.C; g.ldc = d.ldc; g.Cb = d.C_bf16; g.ldcb = d.ldc_bf16;
+        g.M = d.M; g.N = d.N; g.alpha = d.alpha; g.beta = d.beta;
+        g.nseg = d.K2 > 0 ? 2 : 1;
+        g.s[0].a_mn = d.a_mn != 0; g.s[0].b_mn = d.b_mn != 0; g.s[0].K = d.K;
+        g.s[0].A = d.A; g.s[0].lda = d.lda; g.s[0].B = d.B; g.s[0].ldb = d.ldb;
+        g.s[1].a_mn = d.a_mn2 != 0; g.s[1].b_mn = d.b_mn2 != 0; g.s[1].K = d.K2;
+        g.s[1].A = d.A2; g.s[1].lda = d.lda2; g.s[1].B = d.B2; g.s[1].ldb = d.ldb2;
+        g.C = d.C; g.ldc = d.ldc; g.Cb = d.C_bf16; g.ldcb = d.ldc_bf16;
         g.bias = d.bias;
     }
     int rc = tc_workspace_init((cudaStream_t)stream, workspace, workspace_bytes);

@@ -4,15 +4,24 @@
 
 namespace team {
 
-struct TcGemm {
+// one K-segment of a problem: op(A)[M,K] op(B)[K,N]
+struct TcSeg {
     bool a_mn, b_mn;          // false: operand stored [rows,K] (K-major); true: stored [K,rows] (MN-major)
-    int64_t M, N, K;
-    float alpha, beta;
+    int64_t K;
     const void* A;            // bf16
-    const void* A2;           // optional bf16 "lo" half of A (same layout), single-problem entry only
     int64_t lda;
     const void* B;            // bf16
     int64_t ldb;
+};
+
+// C[M,N] = alpha * sum_s op(A_s) op(B_s) (+ bias[N]) (+ beta * C): up to two K-segments accumulate into the
+// same tensor-memory tile (dW = dQo^T Xo + dQs^T S and friends need no second pass and no ordering).
+struct TcGemm {
+    int64_t M, N;
+    int nseg;                 // 1 or 2
+    TcSeg s[2];
+    float alpha, beta;
+    const void* A2;           // optional bf16 "lo" half of s[0].A (same layout), single-problem entry only
     float* C;                 // fp32 [M,N] output (and beta input), may be null if Cb is set
     int64_t ldc;
     void* Cb;                 // bf16 [M,N] copy of the output, may be null

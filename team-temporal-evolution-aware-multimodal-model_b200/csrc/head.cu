@@ -13,121 +13,139 @@ HeadDims head_dims(int64_t B, int C, int P, int Tc) {
     return d;
 }
 
-static size_t tc_operand_bytes(const HeadDims& d) {
-    // generous bound on the bf16 copies one fwd or bwd call makes (see BfCache below)
-    const size_t B2 = d.B2, Nsp = d.Nsp;
-    const size_t elems = B2 * (20 * (size_t)D + 8 * Nsp) + Nsp * (16 * (size_t)D + 6 * Nsp) + 16 * (size_t)D * D +
-                         (size_t)(d.Rt + d.C + 64 + (d.Tc > 0 ? d.Tc : 0)) * 4 * D;
-    return align_up(elems * 2 + 96 * 256, 256);
-}
-
 void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     size_t off = 0;
-    auto take = [&](size_t n_floats) -> float* {
-        float* p = base ? reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off) : nullptr;
-        off += align_up(n_floats * sizeof(float), 256);
+    const bool bf = mode == TEAM_MODE_BF16;
+    auto take_bytes = [&](size_t bytes) -> char* {
+        char* p = base ? reinterpret_cast<char*>(base) + off : nullptr;
+        off += align_up(bytes, 256);
         return p;
     };
-    const size_t B2 = d.B2, Nsp = d.Nsp, Rt = d.Rt;
-    for (int i = 0; i < 3; ++i) { w->Wsum[i] = take((size_t)D * D); w->bsum[i] = take(D); }
+    auto take = [&](size_t n_floats) -> float* { return reinterpret_cast<float*>(take_bytes(n_floats * sizeof(float))); };
+    // fp32 matrix [rows, cols] and, in BF16 mode, its bf16 shadow
+    auto mat = [&](size_t rows, size_t cols, bool want_f = true) -> Mat {
+        Mat m;
+        m.f = want_f ? take(rows * cols) : nullptr;
+        m.h = bf ? reinterpret_cast<__nv_bfloat16*>(take_bytes(rows * cols * 2)) : nullptr;
+        m.ld = (int64_t)cols;
+        return m;
+    };
+    const size_t B2 = d.B2, Nsp = d.Nsp, Rt = d.Rt, Bn = d.B;
+    for (int i = 0; i < 3; ++i) { w->Wsum[i] = mat(D, D); w->bsum[i] = take(D); }
+    w->Wqkv = mat(3 * D, D);
+    w->Wfc = mat(D, D, false);
+    w->protos = mat(d.C, D, false); w->E = mat(10, D, false);
+    w->img = mat(Bn, D, false); w->txt = mat(Bn, D, false);
     w->Ztab = take(Rt * D);
-    w->S = take(Nsp * D); w->invS = take(Nsp);
-    w->QKVs = take(Nsp * 3 * D); w->VFs = take(Nsp * D);
-    w->TT = take(Nsp * Nsp); w->mt = take(Nsp); w->Zt = take(Nsp); w->Pt = take(Nsp * Nsp); w->NFt = take(Nsp * D);
-    w->Xo = take(B2 * D); w->invo = take(B2);
-    w->QKVo = take(B2 * 3 * D); w->VFo = take(B2 * D);
-    w->SQ = take(B2 * Nsp); w->SK = take(B2 * Nsp);
-    w->Aext = take(B2 * Nsp); w->aown = take(B2 * 2);
-    w->Ybo = take(B2 * D); w->lnstat = take(B2 * 2);
-    w->dYo = take(B2 * D); w->rowdot = take(B2); w->dsown = take(B2 * 2);
-    w->dSK = take(B2 * Nsp); w->dVFo = take(B2 * D);
-    w->dQKVo = take(B2 * 3 * D); w->dXo = take(B2 * D);
-    w->Rfull = take(Nsp * D); w->Gfull = take(Nsp * D); w->hfull = take(Nsp);
-    w->dTT = take(Nsp * Nsp); w->tmpNN = take(Nsp * Nsp); w->dVFs = take(Nsp * D);
-    w->dQKVs = take(Nsp * 3 * D); w->dZtab = take(Rt * D);
+    w->S = mat(Nsp, D); w->invS = take(Nsp);
+    w->QKVs = mat(Nsp, 3 * D); w->VFs = mat(Nsp, D);
+    w->TT = take(Nsp * Nsp); w->mt = take(Nsp); w->Zt = take(Nsp); w->Pt = mat(Nsp, Nsp); w->NFt = take(Nsp * D);
+    w->Xo = mat(B2, D); w->invo = take(B2);
+    w->QKVo = mat(B2, 3 * D); w->VFo = take(B2 * D);
+    w->SQ = mat(B2, Nsp); w->SK = take(B2 * Nsp);
+    w->Aext = mat(B2, Nsp); w->aown = take(B2 * 2);
+    w->Ybo = take(B2 * D);
+    w->dYo = mat(B2, D); w->rowdot = take(B2); w->dsown = take(B2 * 2);
+    w->dSK = mat(B2, Nsp); w->dVFo = mat(B2, D);
+    w->dQKVo = mat(B2, 3 * D); w->dXo = mat(B2, D);
+    w->Rfull = take(Nsp * D); w->Gfull = mat(Nsp, D); w->hfull = take(Nsp);
+    w->dTT = mat(Nsp, Nsp); w->tmpNN = take(Nsp * Nsp); w->dVFs = mat(Nsp, D);
+    w->dQKVs = mat(Nsp, 3 * D); w->dZtab = mat(Rt, D);
     const TabOff to = tab_offsets(d);
     w->tab_partials = take((size_t)d.nctas * to.len); w->tab_reduced = take(to.len);
     w->own_partials = take((size_t)d.nctas * OWN_PARTIAL_LEN); w->own_reduced = take(OWN_PARTIAL_LEN);
-    w->colsum_partials = take((size_t)64 * D);
+    w->nrm_partials = take((size_t)4 * NRM_MAX_PARTIALS * D);
     // split-K scratch: largest user is a [512,512] weight gradient reduced over 2B rows
     size_t g = gemm_f32_workspace_bytes(D, D, B2);
     const size_t g2 = gemm_f32_workspace_bytes(Nsp, D, B2);
     if (g2 > g) g = g2;
-    if (g < (size_t)64 * D * D * sizeof(float)) g = (size_t)64 * D * D * sizeof(float);
+    if (g < (size_t)96 * D * D * sizeof(float)) g = (size_t)96 * D * D * sizeof(float);
     w->gemm_ws_bytes = g;
     w->gemm_ws = take(g / sizeof(float));
-    w->bf16_bytes = (mode == TEAM_MODE_BF16) ? tc_operand_bytes(d) : 0;
-    w->bf16_area = w->bf16_bytes ? (void*)take(w->bf16_bytes / sizeof(float)) : nullptr;
     // last, so that the layout of everything above does not depend on the number of text-class rows
+    w->tcls = mat((size_t)(d.Tc > 0 ? d.Tc : 1), D, false);
     w->Zc = take((size_t)(d.Tc > 0 ? d.Tc : 1) * D);
     w->total_bytes = off;
 }
-
-// bf16 shadow copies of GEMM operands (mode BF16), valid for the duration of one fwd or bwd call.
-// An operand is converted the first time a GEMM asks for it; sub-views of an already converted
-// parent (same leading dimension) are served from the parent.  The orchestration below only asks
-// for an operand after its final write, so no invalidation is needed.
-struct BfCache {
-    struct Ent { const float* base; int64_t rows, cols, ld; char* bf; };
-    Ent e[96];
-    int n = 0;
-    char* area = nullptr;
-    size_t cap = 0, used = 0;
-};
 
 struct HeadCtx {
     cudaStream_t st;
     int mode;
     HeadDims d;
     HeadWS w;
-    BfCache bc;
 };
 
-static int bf16_view(HeadCtx& cx, const float* p, int64_t rows, int64_t cols, int64_t ld, const void** out) {
-    BfCache& c = cx.bc;
-    for (int i = 0; i < c.n; ++i) {
-        const BfCache::Ent& e = c.e[i];
-        if (e.ld != ld || p < e.base) continue;
-        const int64_t off = p - e.base;
-        const int64_t r0 = off / ld, c0 = off % ld;
-        if (r0 + rows <= e.rows && c0 + cols <= e.cols) { *out = e.bf + off * 2; return TEAM_OK; }
+// ---------------------------------------------------------------------------------------------------------
+// GEMM waves.  The head is a short chain of WAVES; every wave is a set of independent products
+//   C[M,N] = alpha * sum_{s<nseg} op(A_s) op(B_s) (+ bias) (+ beta C)
+// BF16 mode: the whole wave is ONE launch of the grouped tcgen05 kernel (bf16 shadows of the operands,
+// fp32 accumulation in tensor memory, fp32 output + optional bf16 shadow written by the epilogue).
+// F32 mode: one fp32 FFMA GEMM per segment (parity mode, not the fast path).
+struct GSeg {
+    bool a_mn, b_mn;          // false: operand stored [rows,K] (K-major); true: stored [K,rows]
+    int64_t K;
+    Mat A, B;
+};
+struct GOp {
+    int64_t M, N;
+    int nseg;
+    GSeg s[2];
+    float alpha, beta;
+    Mat C;                    // C.h (if any) receives the bf16 shadow of the result
+    const float* bias;
+};
+
+struct Wave {
+    GOp op[8];
+    int n = 0;
+    GOp& add(int64_t M, int64_t N, float beta, const Mat& C, const float* bias = nullptr) {
+        GOp& o = op[n++];
+        o.M = M; o.N = N; o.nseg = 0; o.alpha = 1.f; o.beta = beta; o.C = C; o.bias = bias;
+        return o;
     }
-    const size_t bytes = align_up((size_t)((rows - 1) * ld + cols) * 2, 256);
-    if (c.n >= 96 || c.used + bytes > c.cap) {
-        set_error("head: bf16 operand staging exhausted (%zu + %zu > %zu, %d entries)", c.used, bytes, c.cap, c.n);
-        return TEAM_EWORKSPACE;
+};
+// A [M,K] K-major / A stored [K,M] (a_mn) times B stored [N,K] (K-major) / B stored [K,N] (b_mn)
+static GOp& seg(GOp& o, bool a_mn, const Mat& A, bool b_mn, const Mat& B, int64_t K) {
+    GSeg& g = o.s[o.nseg++];
+    g.a_mn = a_mn; g.b_mn = b_mn; g.K = K; g.A = A; g.B = B;
+    return o;
+}
+
+static int run_wave(HeadCtx& cx, Wave& wv) {
+    if (wv.n == 0) return TEAM_OK;
+    int rc;
+    if (cx.mode == TEAM_MODE_BF16) {
+        TcGemm t[8];
+        int nt = 0;
+        for (int i = 0; i < wv.n; ++i) {
+            const GOp& o = wv.op[i];
+            if (o.M <= 0 || o.N <= 0) continue;
+            TcGemm& g = t[nt++];
+            memset(&g, 0, sizeof(g));
+            g.M = o.M; g.N = o.N; g.nseg = o.nseg; g.alpha = o.alpha; g.beta = o.beta;
+            for (int q = 0; q < o.nseg; ++q) {
+                TEAM_REQUIRE(o.s[q].A.h != nullptr && o.s[q].B.h != nullptr, "head: GEMM operand without bf16 shadow (wave op %d)", i);
+                g.s[q].a_mn = o.s[q].a_mn; g.s[q].b_mn = o.s[q].b_mn; g.s[q].K = o.s[q].K;
+                g.s[q].A = o.s[q].A.h; g.s[q].lda = o.s[q].A.ld; g.s[q].B = o.s[q].B.h; g.s[q].ldb = o.s[q].B.ld;
+            }
+            g.C = o.C.f; g.ldc = o.C.ld; g.Cb = o.C.h; g.ldcb = o.C.ld; g.bias = o.bias;
+        }
+        rc = gemm_bf16_group(cx.st, t, nt, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
+        wv.n = 0;
+        return rc;
     }
-    char* dst = c.area + c.used;
-    c.used += bytes;
-    int rc = to_bf16(cx.st, p, ld, rows, (int)cols, dst, nullptr, ld);
-    if (rc) return rc;
-    c.e[c.n++] = BfCache::Ent{p, rows, cols, ld, dst};
-    *out = dst;
+    for (int i = 0; i < wv.n; ++i) {
+        const GOp& o = wv.op[i];
+        if (o.M <= 0 || o.N <= 0) continue;
+        for (int q = 0; q < o.nseg; ++q) {
+            const GSeg& g = o.s[q];
+            rc = gemm_f32(cx.st, g.a_mn, !g.b_mn, o.M, o.N, g.K, o.alpha, g.A.f, g.A.ld, g.B.f, g.B.ld, q == 0 ? o.beta : 1.f,
+                          o.C.f, o.C.ld, q == 0 ? o.bias : nullptr, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
+            if (rc) return rc;
+        }
+    }
+    wv.n = 0;
     return TEAM_OK;
-}
-
-// convert a whole parent buffer now (its column sub-views are then served from it)
-static int bf16_parent(HeadCtx& cx, const float* p, int64_t rows, int64_t cols) {
-    if (cx.mode != TEAM_MODE_BF16) return TEAM_OK;
-    const void* unused;
-    return bf16_view(cx, p, rows, cols, cols, &unused);
-}
-
-// C[M,N] = alpha op(A) op(B) + beta C (+bias).  ta: A stored [K,M]; tb: B stored [N,K].
-// F32 mode: fp32 FFMA GEMM.  BF16 mode: operands rounded to bf16 once, tcgen05 GEMM, fp32 accumulate.
-static int hgemm(HeadCtx& cx, bool ta, bool tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A,
-                 int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias) {
-    const bool tc_ok = cx.mode == TEAM_MODE_BF16 && (lda % 8 == 0) && (ldb % 8 == 0) && K >= 1 &&
-                       ((reinterpret_cast<uintptr_t>(A) & 31) == 0) && ((reinterpret_cast<uintptr_t>(B) & 31) == 0) &&
-                       ((ta ? M : K) % 4 == 0) && ((tb ? K : N) % 4 == 0);
-    if (!tc_ok) return gemm_f32(cx.st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
-    TcGemm g;
-    g.a_mn = ta; g.b_mn = !tb; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
-    g.A2 = nullptr; g.Cb = nullptr; g.ldcb = 0; g.lda = lda; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
-    int rc = bf16_view(cx, A, ta ? K : M, ta ? M : K, lda, &g.A);
-    if (rc) return rc;
-    if ((rc = bf16_view(cx, B, tb ? N : K, tb ? K : N, ldb, &g.B))) return rc;
-    return gemm_bf16_tc(cx.st, g, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
 }
 
 static int validate(const team_head_weights* hw, int mode, int64_t batch) {
@@ -148,55 +166,54 @@ static PtrList plist(const float* const* p, int n) {
     return l;
 }
 
-#define HG(...)                                       \
-    do {                                              \
-        int _rc = hgemm(cx, __VA_ARGS__);             \
-        if (_rc != TEAM_OK) return _rc;               \
-    } while (0)
+static void conv_add(ConvList& cl, int& blocks, const float* src, float* dstf, __nv_bfloat16* dsth, int64_t n_floats) {
+    if (n_floats <= 0 || (dstf == nullptr && dsth == nullptr)) return;
+    ConvSeg& s = cl.s[cl.n++];
+    s.src = src; s.dstf = dstf; s.dsth = dsth; s.n4 = n_floats / 4; s.blk0 = blocks;
+    blocks += (int)((s.n4 + 255) / 256);
+}
 
-static int sum_projections(HeadCtx& cx, const team_head_weights* hw) {
+// step prologue (one launch): summed projections, packed {Wq;Wk;Wv}, bf16 shadows of weights and inputs
+static int prologue(HeadCtx& cx, const team_head_weights* hw, int nsum, const float* image, const float* text,
+                    const float* text_cls, int64_t batch) {
+    HeadWS& w = cx.w;
+    const HeadDims& d = cx.d;
     const int T = hw->num_tasks;
+    PrepSum ps;
+    memset(&ps, 0, sizeof(ps));
     const float* const* Ws[3] = {hw->w_img, hw->w_text, hw->w_state};
     const float* const* Bs[3] = {hw->b_img, hw->b_text, hw->b_state};
     for (int k = 0; k < 3; ++k) {
-        sum_weights_kernel<<<D * D / 4 / 256, 256, 0, cx.st>>>(plist(Ws[k], T), plist(Bs[k], T), cx.w.Wsum[k], cx.w.bsum[k]);
-        TEAM_LAUNCH_CHECK("sum_weights_kernel");
+        ps.W[k] = plist(Ws[k], T); ps.Bv[k] = plist(Bs[k], T);
+        ps.Wout[k] = w.Wsum[k].f; ps.Wh[k] = w.Wsum[k].h; ps.bout[k] = w.bsum[k];
     }
+    ps.n = nsum;
+    ConvList cl;
+    memset(&cl, 0, sizeof(cl));
+    cl.sum_blocks = nsum * PREP_SUM_BLOCKS_PER_W;
+    int blocks = 0;
+    if (hw->w_q) conv_add(cl, blocks, hw->w_q, w.Wqkv.f, w.Wqkv.h, (int64_t)D * D);
+    if (hw->w_k) conv_add(cl, blocks, hw->w_k, w.Wqkv.f + (size_t)D * D, w.Wqkv.h ? w.Wqkv.h + (size_t)D * D : nullptr, (int64_t)D * D);
+    if (hw->w_v) conv_add(cl, blocks, hw->w_v, w.Wqkv.f + (size_t)2 * D * D, w.Wqkv.h ? w.Wqkv.h + (size_t)2 * D * D : nullptr, (int64_t)D * D);
+    if (hw->w_fc) conv_add(cl, blocks, hw->w_fc, nullptr, w.Wfc.h, (int64_t)D * D);
+    if (hw->prototypes) conv_add(cl, blocks, hw->prototypes, nullptr, w.protos.h, (int64_t)d.C * D);
+    if (hw->state_emb) conv_add(cl, blocks, hw->state_emb, nullptr, w.E.h, (int64_t)10 * D);
+    if (image) conv_add(cl, blocks, image, nullptr, w.img.h, batch * D);
+    if (text) conv_add(cl, blocks, text, nullptr, w.txt.h, batch * D);
+    if (text_cls && d.Tc > 0) conv_add(cl, blocks, text_cls, nullptr, w.tcls.h, (int64_t)d.Tc * D);
+    prep_kernel<<<cl.sum_blocks + blocks, 256, 0, cx.st>>>(ps, cl);
+    TEAM_LAUNCH_CHECK("prep_kernel");
     return TEAM_OK;
 }
 
-// X[M,D] @ {Wq,Wk,Wv}^T -> out[M,3D]
-static int qkv_forward(HeadCtx& cx, const team_head_weights* hw, const float* X, int64_t rows, float* out) {
-    HG(false, true, rows, D, D, 1.f, X, D, hw->w_q, D, 0.f, out, 3 * D, nullptr);
-    HG(false, true, rows, D, D, 1.f, X, D, hw->w_k, D, 0.f, out + D, 3 * D, nullptr);
-    HG(false, true, rows, D, D, 1.f, X, D, hw->w_v, D, 0.f, out + 2 * D, 3 * D, nullptr);
-    return TEAM_OK;
-}
-
-static int step_rows_forward(HeadCtx& cx, const team_head_weights* hw) {
-    const HeadDims& d = cx.d;
+static void bind_inputs(HeadCtx& cx, const team_head_weights* hw, const float* image, const float* text, const float* text_cls) {
     HeadWS& w = cx.w;
-    // prototype rows and state-table rows: project, normalise, place into S
-    HG(false, true, d.C, D, D, 1.f, hw->prototypes, D, w.Wsum[0], D, 0.f, w.Ztab, D, w.bsum[0]);
-    HG(false, true, 10, D, D, 1.f, hw->state_emb, D, w.Wsum[2], D, 0.f, w.Ztab + (size_t)d.C * D, D, w.bsum[2]);
-    rows_normalize_kernel<<<(d.C + 7) / 8, 256, 0, cx.st>>>(w.Ztab, d.C, w.S, w.invS, 1);
-    TEAM_LAUNCH_CHECK("rows_normalize_kernel");
-    rows_normalize_kernel<<<2, 256, 0, cx.st>>>(w.Ztab + (size_t)d.C * D, 10, w.S + (size_t)d.M * D, w.invS + d.M, 1);
-    TEAM_LAUNCH_CHECK("rows_normalize_kernel");
-    const int fill_rows = d.P + (d.Nsp - d.Ns);
-    if (fill_rows > 0) {
-        fill_prompt_rows_kernel<<<fill_rows, 128, 0, cx.st>>>(plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S);
-        TEAM_LAUNCH_CHECK("fill_prompt_rows_kernel");
-    }
-    int rc = qkv_forward(cx, hw, w.S, d.Nsp, w.QKVs);
-    if (rc) return rc;
-    if ((rc = bf16_parent(cx, w.QKVs, d.Nsp, 3 * D))) return rc;
-    HG(false, true, d.Nsp, D, D, 1.f, w.QKVs + 2 * D, 3 * D, hw->w_fc, D, 0.f, w.VFs, D, nullptr);
-    HG(false, true, d.Nsp, d.Nsp, D, 1.f, w.QKVs, 3 * D, w.QKVs + D, 3 * D, 0.f, w.TT, d.Nsp, nullptr);
-    table_prep_kernel<<<(d.Nsp + 7) / 8, 256, 0, cx.st>>>(w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt);
-    TEAM_LAUNCH_CHECK("table_prep_kernel");
-    HG(false, false, d.Nsp, D, d.Nsp, 1.f, w.Pt, d.Nsp, w.VFs, D, 0.f, w.NFt, D, nullptr);
-    return TEAM_OK;
+    w.Wfc.f = const_cast<float*>(hw->w_fc);
+    w.protos.f = const_cast<float*>(hw->prototypes);
+    w.E.f = const_cast<float*>(hw->state_emb);
+    w.img.f = const_cast<float*>(image);
+    w.txt.f = const_cast<float*>(text);
+    w.tcls.f = const_cast<float*>(text_cls);
 }
 
 static int setup(HeadCtx& cx, const team_head_weights* hw, int mode, int64_t batch, int Tc, void* workspace,
@@ -212,11 +229,14 @@ static int setup(HeadCtx& cx, const team_head_weights* hw, int mode, int64_t bat
         return TEAM_EWORKSPACE;
     }
     TEAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "head: workspace must be 256-byte aligned");
-    cx.bc.n = 0; cx.bc.used = 0;
-    cx.bc.area = reinterpret_cast<char*>(cx.w.bf16_area);
-    cx.bc.cap = cx.w.bf16_bytes;
-    if (mode == TEAM_MODE_BF16) return tc_workspace_init(cx.st, cx.w.gemm_ws, cx.w.gemm_ws_bytes);
     return TEAM_OK;
+}
+
+static void norm_add(NormList& nl, int& blocks, const float* Z, float* X, __nv_bfloat16* Xh, float* inv, int64_t rows) {
+    if (rows <= 0) return;
+    NormSeg& s = nl.s[nl.n++];
+    s.Z = Z; s.X = X; s.Xh = Xh; s.inv = inv; s.rows = rows; s.blk0 = blocks;
+    blocks += (int)((rows + 7) / 8);
 }
 
 }  // namespace team
@@ -231,6 +251,13 @@ extern "C" size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, 
     return w.total_bytes;
 }
 
+#define RUN(wave)                                     \
+    do {                                              \
+        int _rc = run_wave(cx, wave);                 \
+        if (_rc != TEAM_OK) return _rc;               \
+    } while (0)
+
+// Forward: 12 launches (prologue, prompt rows, 4 GEMM waves, 6 row kernels) - see DESIGN.md section 4.
 extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t batch, const float* image_feat,
                                  const float* text_feat, const int64_t* state_ids, const float* text_cls,
                                  int64_t num_text_cls, float* out_image, float* out_text, float* out_state,
@@ -240,48 +267,73 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     int rc = setup(cx, hw, mode, batch, (int)(text_cls ? num_text_cls : 0), workspace, workspace_bytes, stream);
     if (rc) return rc;
     TEAM_REQUIRE(image_feat && text_feat && state_ids && out_image && out_text && out_state && out_proto, "head fwd: null pointer");
+    TEAM_REQUIRE(hw->w_q && hw->w_k && hw->w_v && hw->w_fc && hw->b_fc && hw->ln_g && hw->ln_b && hw->state_emb && hw->prototypes, "head fwd: null weight");
     const HeadDims& d = cx.d;
     HeadWS& w = cx.w;
-    if ((rc = sum_projections(cx, hw))) return rc;
-    if ((rc = step_rows_forward(cx, hw))) return rc;
-    // own rows: image rows [0,B), text rows [B,2B)
-    HG(false, true, d.B, D, D, 1.f, image_feat, D, w.Wsum[0], D, 0.f, w.Xo, D, w.bsum[0]);
-    HG(false, true, d.B, D, D, 1.f, text_feat, D, w.Wsum[1], D, 0.f, w.Xo + (size_t)d.B * D, D, w.bsum[1]);
-    rows_normalize_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(w.Xo, d.B2, w.Xo, w.invo, 1);
-    TEAM_LAUNCH_CHECK("rows_normalize_kernel");
-    if ((rc = qkv_forward(cx, hw, w.Xo, d.B2, w.QKVo))) return rc;
-    if ((rc = bf16_parent(cx, w.QKVo, d.B2, 3 * D))) return rc;
-    HG(false, true, d.B2, D, D, 1.f, w.QKVo + 2 * D, 3 * D, hw->w_fc, D, 0.f, w.VFo, D, nullptr);
-    HG(false, true, d.B2, d.Nsp, D, 1.f, w.QKVo, 3 * D, w.QKVs + D, 3 * D, 0.f, w.SQ, d.Nsp, nullptr);
-    HG(false, true, d.B2, d.Nsp, D, 1.f, w.QKVo + D, 3 * D, w.QKVs, 3 * D, 0.f, w.SK, d.Nsp, nullptr);
-    attn_own_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.SQ, w.QKVo, state_ids, w.Aext, w.aown);
+    const bool want_cls = d.Tc > 0 && (cls_logits != nullptr || cls_argmax != nullptr);
+    bind_inputs(cx, hw, image_feat, text_feat, text_cls);
+    if ((rc = prologue(cx, hw, 3, image_feat, text_feat, want_cls ? text_cls : nullptr, batch))) return rc;
+    const int fill_rows = d.P + (d.Nsp - d.Ns);
+    if (fill_rows > 0) {
+        fill_prompt_rows_kernel<<<fill_rows, 128, 0, cx.st>>>(plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S.f, w.S.h);
+        TEAM_LAUNCH_CHECK("fill_prompt_rows_kernel");
+    }
+    Wave wv;
+    const Mat none{nullptr, nullptr, 0};
+    auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
+    // ---- wave 1: every projection of the step (prototype rows, state table, image rows, text rows, class text)
+    seg(wv.add(d.C, D, 0.f, fonly(w.Ztab, D), w.bsum[0]), false, w.protos, false, w.Wsum[0], D);
+    seg(wv.add(10, D, 0.f, fonly(w.Ztab + (size_t)d.C * D, D), w.bsum[2]), false, w.E, false, w.Wsum[2], D);
+    seg(wv.add(d.B, D, 0.f, fonly(w.Xo.f, D), w.bsum[0]), false, w.img, false, w.Wsum[0], D);
+    seg(wv.add(d.B, D, 0.f, fonly(w.Xo.f + (size_t)d.B * D, D), w.bsum[1]), false, w.txt, false, w.Wsum[1], D);
+    if (want_cls) seg(wv.add(d.Tc, D, 0.f, fonly(w.Zc, D), w.bsum[1]), false, w.tcls, false, w.Wsum[1], D);
+    RUN(wv);
+    {   // L2-normalise: prototype rows -> S[0,C), state table -> S[M,M+10), own rows in place
+        NormList nl;
+        memset(&nl, 0, sizeof(nl));
+        nl.do_normalize = 1;
+        int blocks = 0;
+        norm_add(nl, blocks, w.Ztab, w.S.f, w.S.h, w.invS, d.C);
+        norm_add(nl, blocks, w.Ztab + (size_t)d.C * D, w.S.f + (size_t)d.M * D, w.S.h ? w.S.h + (size_t)d.M * D : nullptr, w.invS + d.M, 10);
+        norm_add(nl, blocks, w.Xo.f, w.Xo.f, w.Xo.h, w.invo, d.B2);
+        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
+        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
+    }
+    // ---- wave 2: q/k/v of the step rows and of the own rows against the packed [3D, D] weight
+    seg(wv.add(d.Nsp, 3 * D, 0.f, w.QKVs), false, w.S, false, w.Wqkv, D);
+    seg(wv.add(d.B2, 3 * D, 0.f, w.QKVo), false, w.Xo, false, w.Wqkv, D);
+    RUN(wv);
+    // ---- wave 3: fc folded into V, and every score matrix
+    const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
+    const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
+    seg(wv.add(d.Nsp, D, 0.f, w.VFs), false, Vs, false, w.Wfc, D);
+    seg(wv.add(d.B2, D, 0.f, fonly(w.VFo, D)), false, Vo, false, w.Wfc, D);
+    seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.TT, d.Nsp)), false, Qs, false, Ks, D);
+    seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
+    seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
+    RUN(wv);
+    table_prep_kernel<<<(d.Nsp + 7) / 8, 256, 0, cx.st>>>(w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+    TEAM_LAUNCH_CHECK("table_prep_kernel");
+    attn_own_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.SQ.f, w.QKVo.f, state_ids, w.Aext.f, w.Aext.h, w.aown);
     TEAM_LAUNCH_CHECK("attn_own_kernel");
-    HG(false, false, d.B2, D, d.Nsp, 1.f, w.Aext, d.Nsp, w.VFs, D, 0.f, w.Ybo, D, nullptr);
-    ln_own_fwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.Ybo, w.aown, w.VFo, w.Xo, hw->b_fc, hw->ln_g, hw->ln_b, w.lnstat, out_image, out_text);
+    // ---- wave 4: probabilities x (fc-space) values
+    seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
+    seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
+    RUN(wv);
+    ln_own_fwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.Ybo, w.aown, w.VFo, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
     TEAM_LAUNCH_CHECK("ln_own_fwd_kernel");
     const int tgrid = d.B < 2 * NUM_SMS ? d.B : 2 * NUM_SMS;
-    table_rows_fwd_kernel<<<tgrid, TR_WARPS * 32, 0, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs, w.S, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
+    table_rows_fwd_kernel<<<tgrid, TR_WARPS * 32, 0, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
     TEAM_LAUNCH_CHECK("table_rows_fwd_kernel");
-    if (text_cls != nullptr && num_text_cls > 0 && (cls_logits != nullptr || cls_argmax != nullptr)) {
+    if (want_cls) {
         // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
-        HG(false, true, num_text_cls, D, D, 1.f, text_cls, D, w.Wsum[1], D, 0.f, w.Zc, D, w.bsum[1]);
-        if ((rc = cosine_logits_launch(cx.st, w.Xo, d.B, w.Zc, num_text_cls, nullptr, cls_logits, cls_argmax))) return rc;
+        if ((rc = cosine_logits_launch(cx.st, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
     }
+    (void)none;
     return TEAM_OK;
 }
 
-static int colsum(HeadCtx& cx, const float* X, int64_t rows, float* out, int accumulate) {
-    int chunks = (int)((rows + 31) / 32);
-    if (chunks > 64) chunks = 64;
-    if (chunks < 1) chunks = 1;
-    const int64_t rpc = (rows + chunks - 1) / chunks;
-    colsum_partial_kernel<<<chunks, 128, 0, cx.st>>>(X, rows, rpc, cx.w.colsum_partials);
-    TEAM_LAUNCH_CHECK("colsum_partial_kernel");
-    colsum_final_kernel<<<1, 128, 0, cx.st>>>(cx.w.colsum_partials, chunks, out, accumulate);
-    TEAM_LAUNCH_CHECK("colsum");
-    return TEAM_OK;
-}
-
+// Backward: 15 launches (5 GEMM waves, 10 row kernels); needs the workspace of the matching forward call.
 extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t batch, const float* image_feat,
                                  const float* text_feat, const int64_t* state_ids, const float* g_image,
                                  const float* g_text, const float* g_state, const float* g_proto,
@@ -294,119 +346,157 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
                  gr->w_q && gr->w_k && gr->w_v && gr->w_fc && gr->b_fc && gr->ln_g && gr->ln_b, "head bwd: null gradient buffer");
     const HeadDims& d = cx.d;
     HeadWS& w = cx.w;
+    bind_inputs(cx, hw, image_feat, text_feat, nullptr);
     const TabOff to = tab_offsets(d);
-    if ((rc = bf16_parent(cx, w.QKVo, d.B2, 3 * D))) return rc;
-    if ((rc = bf16_parent(cx, w.QKVs, d.Nsp, 3 * D))) return rc;
+    auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
     // ---- table-query rows (prototype / state outputs)
     const int tgrid = d.B < d.nctas ? d.B : d.nctas;
     const size_t tsm = (size_t)(3 * TR_WARPS * D + 10 * D + 3 * D + d.Rt * 11) * sizeof(float);
     TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    table_rows_bwd_kernel<<<tgrid, TR_WARPS * 32, tsm, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs, w.S, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, g_proto, g_state, w.dSK, w.dVFo, w.tab_partials);
+    table_rows_bwd_kernel<<<tgrid, TR_WARPS * 32, tsm, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.tab_partials);
     TEAM_LAUNCH_CHECK("table_rows_bwd_kernel");
-    reduce_partials_kernel<<<(unsigned)((to.len / 4 + 63) / 64), 256, 0, cx.st>>>(w.tab_partials, tgrid, to.len / 4, w.tab_reduced);
-    TEAM_LAUNCH_CHECK("reduce_partials_kernel");
-    expand_table_kernel<<<d.Nsp, 128, 0, cx.st>>>(d, w.tab_reduced, w.Rfull, w.Gfull, w.hfull, w.dTT, w.dVFs);
-    TEAM_LAUNCH_CHECK("expand_table_kernel");
     // ---- own query rows
     int ogrid = (d.B + 7) / 8;
     if (ogrid > d.nctas) ogrid = d.nctas;
-    ln_own_bwd_kernel<<<ogrid, 256, 0, cx.st>>>(d, w.Ybo, w.Xo, w.VFo, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo, w.dXo, w.rowdot, w.dsown, w.dVFo, w.own_partials);
+    ln_own_bwd_kernel<<<ogrid, 256, 0, cx.st>>>(d, w.Ybo, w.Xo.f, w.VFo, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo.f, w.dVFo.h, w.own_partials);
     TEAM_LAUNCH_CHECK("ln_own_bwd_kernel");
-    reduce_partials_kernel<<<(OWN_PARTIAL_LEN / 4 + 63) / 64, 256, 0, cx.st>>>(w.own_partials, ogrid, OWN_PARTIAL_LEN / 4, w.own_reduced);
-    TEAM_LAUNCH_CHECK("reduce_partials_kernel");
-    finalize_ln_grads_kernel<<<1, 128, 0, cx.st>>>(d, w.tab_reduced, w.own_reduced, gr->ln_g, gr->ln_b, gr->b_fc);
-    TEAM_LAUNCH_CHECK("ln_own_bwd");
-    // dA = dYo VFs^T  (into the SQ buffer), dVFs += Aext^T dYo, dS = Aext.*(dA - rowdot)/tau
-    HG(false, true, d.B2, d.Nsp, D, 1.f, w.dYo, D, w.VFs, D, 0.f, w.SQ, d.Nsp, nullptr);
-    HG(true, false, d.Nsp, D, d.B2, 1.f, w.Aext, d.Nsp, w.dYo, D, 1.f, w.dVFs, D, nullptr);
     {
-        const int64_t n = (int64_t)d.B2 * d.Nsp;
-        ds_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx.st>>>(n, d.Nsp, w.Aext, w.rowdot, w.SQ);
+        ReduceJobs rj;
+        rj.j[0] = ReduceJob{w.tab_partials, w.tab_reduced, to.len / 4, tgrid};
+        rj.j[1] = ReduceJob{w.own_partials, w.own_reduced, OWN_PARTIAL_LEN / 4, ogrid};
+        rj.blocks0 = (int)((to.len / 4 + 63) / 64);
+        reduce_partials_kernel<<<rj.blocks0 + (OWN_PARTIAL_LEN / 4 + 63) / 64, 256, 0, cx.st>>>(rj);
+        TEAM_LAUNCH_CHECK("reduce_partials_kernel");
+    }
+    expand_table_kernel<<<d.Nsp + 1, 128, 0, cx.st>>>(d, w.tab_reduced, w.own_reduced, w.Rfull, w.Gfull.f, w.Gfull.h, w.hfull, w.dTT.f, w.dVFs.f, gr->ln_g, gr->ln_b, gr->b_fc);
+    TEAM_LAUNCH_CHECK("expand_table_kernel");
+    const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
+    const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
+    const Mat dQo = sub(w.dQKVo, 0, 0), dKo = sub(w.dQKVo, 0, D), dVo = sub(w.dQKVo, 0, 2 * D);
+    const Mat dQs = sub(w.dQKVs, 0, 0), dKs = sub(w.dQKVs, 0, D), dVs = sub(w.dQKVs, 0, 2 * D);
+    Wave wv;
+    // ---- wave 5: dA = dYo VFs^T (into SQ), G VFs^T, dKo = dSK Qs, dVFs += Aext^T dYo + Pt^T G
+    seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, w.dYo, false, w.VFs, D);
+    seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.tmpNN, d.Nsp)), false, w.Gfull, false, w.VFs, D);
+    seg(wv.add(d.B2, D, 0.f, dKo), false, w.dSK, true, Qs, d.Nsp);
+    seg(seg(wv.add(d.Nsp, D, 1.f, w.dVFs), true, w.Aext, true, w.dYo, d.B2), true, w.Pt, true, w.Gfull, d.Nsp);
+    RUN(wv);
+    {   // dS = Aext .* (dA - rowdot) / tau (in place);  dTT += Pt .* (G VFs^T - h) / tau
+        const int64_t n4 = (int64_t)d.B2 * d.Nsp / 4;
+        ds_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, cx.st>>>(n4, d.Nsp / 4, w.Aext.f, w.rowdot, w.SQ.f, w.SQ.h);
         TEAM_LAUNCH_CHECK("ds_kernel");
+        dtt_kernel<<<(d.Nsp * d.Nsp + 255) / 256, 256, 0, cx.st>>>(d.Nsp, d.M, w.Pt.f, w.tmpNN, w.hfull, w.dTT.f, w.dTT.h);
+        TEAM_LAUNCH_CHECK("dtt_kernel");
     }
-    float* dS = w.SQ;
-    float *dQo = w.dQKVo, *dKo = w.dQKVo + D, *dVo = w.dQKVo + 2 * D;
-    float *dQs = w.dQKVs, *dKs = w.dQKVs + D, *dVs = w.dQKVs + 2 * D;
-    const float *Qo = w.QKVo, *Ko = w.QKVo + D, *Vo = w.QKVo + 2 * D;
-    const float *Qs = w.QKVs, *Ks = w.QKVs + D, *Vs = w.QKVs + 2 * D;
-    HG(false, false, d.B2, D, d.Nsp, 1.f, dS, d.Nsp, Ks, 3 * D, 0.f, dQo, 3 * D, nullptr);          // dQo = dS Ks
-    HG(true, false, d.Nsp, D, d.B2, 1.f, dS, d.Nsp, Qo, 3 * D, 0.f, dKs, 3 * D, nullptr);           // dKs = dS^T Qo
-    HG(false, false, d.B2, D, d.Nsp, 1.f, w.dSK, d.Nsp, Qs, 3 * D, 0.f, dKo, 3 * D, nullptr);       // dKo = dSK Qs
-    HG(true, false, d.Nsp, D, d.B2, 1.f, w.dSK, d.Nsp, Ko, 3 * D, 0.f, dQs, 3 * D, nullptr);        // dQs = dSK^T Ko
-    own_own_bwd_kernel<<<(d.B + 7) / 8, 256, 0, cx.st>>>(d, w.QKVo, w.dsown, w.dQKVo);
+    const Mat& dS = w.SQ;
+    // ---- wave 6: score gradients -> dQ/dK, fc folded into V, dWfc
+    seg(wv.add(d.B2, D, 0.f, dQo), false, dS, true, Ks, d.Nsp);                                                    // dQo = dS Ks
+    seg(seg(wv.add(d.Nsp, D, 0.f, dKs), true, dS, true, Qo, d.B2), true, w.dTT, true, Qs, d.Nsp);                  // dKs = dS^T Qo + dTT^T Qs
+    seg(seg(wv.add(d.Nsp, D, 0.f, dQs), true, w.dSK, true, Ko, d.B2), false, w.dTT, true, Ks, d.Nsp);              // dQs = dSK^T Ko + dTT Ks
+    seg(wv.add(d.B2, D, 0.f, dVo), false, w.dVFo, true, w.Wfc, D);                                                 // dVo = dVFo Wfc
+    seg(wv.add(d.Nsp, D, 0.f, dVs), false, w.dVFs, true, w.Wfc, D);
+    seg(seg(wv.add(D, D, 0.f, fonly(gr->w_fc, D)), true, w.dVFo, true, Vo, d.B2), true, w.dVFs, true, Vs, d.Nsp);  // dWfc = dVFo^T Vo + dVFs^T Vs
+    RUN(wv);
+    own_own_bwd_kernel<<<(d.B + 7) / 8, 256, 0, cx.st>>>(d, w.QKVo.f, w.dsown, w.dQKVo.f, w.dQKVo.h);
     TEAM_LAUNCH_CHECK("own_own_bwd_kernel");
-    // ---- per-step part of the table queries
-    HG(false, true, d.Nsp, d.Nsp, D, 1.f, w.Gfull, D, w.VFs, D, 0.f, w.tmpNN, d.Nsp, nullptr);     // G VFs^T
-    dtt_kernel<<<(d.Nsp * d.Nsp + 255) / 256, 256, 0, cx.st>>>(d.Nsp, d.M, w.Pt, w.tmpNN, w.hfull, w.dTT);
-    TEAM_LAUNCH_CHECK("dtt_kernel");
-    HG(true, false, d.Nsp, D, d.Nsp, 1.f, w.Pt, d.Nsp, w.Gfull, D, 1.f, w.dVFs, D, nullptr);        // dVFs += P^T G
-    HG(false, false, d.Nsp, D, d.Nsp, 1.f, w.dTT, d.Nsp, Ks, 3 * D, 1.f, dQs, 3 * D, nullptr);      // dQs += dTT Ks
-    HG(true, false, d.Nsp, D, d.Nsp, 1.f, w.dTT, d.Nsp, Qs, 3 * D, 1.f, dKs, 3 * D, nullptr);       // dKs += dTT^T Qs
-    // ---- fc folded into V
-    HG(false, false, d.B2, D, D, 1.f, w.dVFo, D, hw->w_fc, D, 0.f, dVo, 3 * D, nullptr);            // dVo = dVFo Wfc
-    HG(false, false, d.Nsp, D, D, 1.f, w.dVFs, D, hw->w_fc, D, 0.f, dVs, 3 * D, nullptr);
-    HG(true, false, D, D, d.B2, 1.f, w.dVFo, D, Vo, 3 * D, 0.f, gr->w_fc, D, nullptr);              // dWfc = dVFo^T Vo
-    HG(true, false, D, D, d.Nsp, 1.f, w.dVFs, D, Vs, 3 * D, 1.f, gr->w_fc, D, nullptr);             //      + dVFs^T Vs
-    // ---- q/k/v projections
-    if ((rc = bf16_parent(cx, w.dQKVo, d.B2, 3 * D))) return rc;
-    if ((rc = bf16_parent(cx, w.dQKVs, d.Nsp, 3 * D))) return rc;
-    const float* Wqkv[3] = {hw->w_q, hw->w_k, hw->w_v};
-    float* dWqkv[3] = {gr->w_q, gr->w_k, gr->w_v};
-    for (int i = 0; i < 3; ++i) {
-        HG(false, false, d.B2, D, D, 1.f, w.dQKVo + i * D, 3 * D, Wqkv[i], D, 1.f, w.dXo, D, nullptr);      // dXo += dQ Wq ...
-        HG(false, false, d.Nsp, D, D, 1.f, w.dQKVs + i * D, 3 * D, Wqkv[i], D, 1.f, w.Rfull, D, nullptr);   // dS_rows (in Rfull)
-        HG(true, false, D, D, d.B2, 1.f, w.dQKVo + i * D, 3 * D, w.Xo, D, 0.f, dWqkv[i], D, nullptr);
-        HG(true, false, D, D, d.Nsp, 1.f, w.dQKVs + i * D, 3 * D, w.S, D, 1.f, dWqkv[i], D, nullptr);
+    // ---- wave 7: through the packed q/k/v projection
+    seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
+    seg(wv.add(d.Nsp, D, 1.f, fonly(w.Rfull, D)), false, w.dQKVs, true, w.Wqkv, 3 * D);                            // dS_rows (in Rfull)
+    {
+        float* dW[3] = {gr->w_q, gr->w_k, gr->w_v};
+        for (int i = 0; i < 3; ++i)
+            seg(seg(wv.add(D, D, 0.f, fonly(dW[i], D)), true, sub(w.dQKVo, 0, i * D), true, w.Xo, d.B2), true, sub(w.dQKVs, 0, i * D), true, w.S, d.Nsp);
     }
-    // ---- normalisations and the newest projections
-    nrm_bwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(w.dXo, d.B2, w.Xo, w.invo, nullptr, d.B2, 0);
-    TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
-    // proto rows [0,C) and state rows [M,M+10) of dS_rows -> compact dZtab [C+10]
-    nrm_bwd_kernel<<<(d.Rt + 7) / 8, 256, 0, cx.st>>>(w.dZtab, d.Rt, w.S, w.invS, w.Rfull, d.C, d.P);
-    TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
-    const float* dz0 = w.dXo;
-    const float* dz1 = w.dXo + (size_t)d.B * D;
-    const float* dzp = w.dZtab;
-    const float* dzs = w.dZtab + (size_t)d.C * D;
-    HG(true, false, D, D, d.B, 1.f, dz0, D, image_feat, D, 0.f, gr->w_img, D, nullptr);              // dWi = dz0^T x
-    HG(true, false, D, D, d.C, 1.f, dzp, D, hw->prototypes, D, 1.f, gr->w_img, D, nullptr);          //     + dzp^T protos
-    HG(true, false, D, D, d.B, 1.f, dz1, D, text_feat, D, 0.f, gr->w_text, D, nullptr);
-    HG(true, false, D, D, 10, 1.f, dzs, D, hw->state_emb, D, 0.f, gr->w_state, D, nullptr);
-    HG(false, false, 10, D, D, 1.f, dzs, D, w.Wsum[2], D, 0.f, gr->state_emb, D, nullptr);           // dE = dzs Ws
-    if ((rc = colsum(cx, dz0, d.B, gr->b_img, 0))) return rc;
-    if ((rc = colsum(cx, dzp, d.C, gr->b_img, 1))) return rc;
-    if ((rc = colsum(cx, dz1, d.B, gr->b_text, 0))) return rc;
-    if ((rc = colsum(cx, dzs, 10, gr->b_state, 0))) return rc;
-    if (gr->prompts != nullptr && d.P > 0) {   // gradient of every prompt row (callers keep the newest task's slice)
-        TEAM_CUDA_CHECK(cudaMemcpyAsync(gr->prompts, w.Rfull + (size_t)d.C * D, (size_t)d.P * D * sizeof(float), cudaMemcpyDeviceToDevice, cx.st));
+    RUN(wv);
+    // ---- normalisation backward of own rows, prototype rows and state-table rows (+ bias-gradient partials)
+    NrmList nl;
+    memset(&nl, 0, sizeof(nl));
+    int nblk[4];
+    {
+        int blocks = 0;
+        auto add = [&](const float* src, const float* X, const float* inv, float* dZ, __nv_bfloat16* dZh, int64_t rows, int64_t src_off) {
+            NrmSeg& s = nl.s[nl.n];
+            int rpb = (int)((rows + NRM_MAX_PARTIALS - 1) / NRM_MAX_PARTIALS);
+            rpb = (rpb + 7) / 8 * 8;
+            if (rpb < 8) rpb = 8;
+            s.dXsrc = src; s.X = X; s.inv = inv; s.dZ = dZ; s.dZh = dZh; s.rows = rows; s.src_off = src_off;
+            s.rows_per_block = rpb; s.blk0 = blocks;
+            s.partial = w.nrm_partials + (size_t)nl.n * NRM_MAX_PARTIALS * D;
+            nblk[nl.n] = (int)((rows + rpb - 1) / rpb);
+            blocks += nblk[nl.n];
+            ++nl.n;
+        };
+        add(w.dXo.f, w.Xo.f, w.invo, w.dXo.f, w.dXo.h, d.B, 0);                                                    // dz0 (in place)
+        add(w.dXo.f, w.Xo.f, w.invo, w.dXo.f + (size_t)d.B * D, w.dXo.h ? w.dXo.h + (size_t)d.B * D : nullptr, d.B, d.B);   // dz1
+        add(w.Rfull, w.S.f, w.invS, w.dZtab.f, w.dZtab.h, d.C, 0);                                                 // dzp
+        add(w.Rfull, w.S.f, w.invS, w.dZtab.f + (size_t)d.C * D, w.dZtab.h ? w.dZtab.h + (size_t)d.C * D : nullptr, 10, d.M);   // dzs
+        nrm_bwd_kernel<<<blocks, 256, 0, cx.st>>>(nl);
+        TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
+    }
+    // ---- wave 8: gradients of the newest projections and of the state embedding
+    const Mat dz0 = sub(w.dXo, 0, 0), dz1 = sub(w.dXo, d.B, 0), dzp = sub(w.dZtab, 0, 0), dzs = sub(w.dZtab, d.C, 0);
+    seg(seg(wv.add(D, D, 0.f, fonly(gr->w_img, D)), true, dz0, true, w.img, d.B), true, dzp, true, w.protos, d.C);  // dWi = dz0^T x + dzp^T protos
+    seg(wv.add(D, D, 0.f, fonly(gr->w_text, D)), true, dz1, true, w.txt, d.B);
+    seg(wv.add(D, D, 0.f, fonly(gr->w_state, D)), true, dzs, true, w.E, 10);
+    seg(wv.add(10, D, 0.f, fonly(gr->state_emb, D)), false, dzs, true, w.Wsum[2], D);                              // dE = dzs Ws
+    RUN(wv);
+    {
+        FinishArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        for (int i = 0; i < 4; ++i) { fa.part[i] = nl.s[i].partial; fa.nblk[i] = nblk[i]; }
+        fa.b_img = gr->b_img; fa.b_text = gr->b_text; fa.b_state = gr->b_state;
+        fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
+        finish_bwd_kernel<<<3 + (fa.prompts ? d.P : 0), 128, 0, cx.st>>>(fa);
+        TEAM_LAUNCH_CHECK("finish_bwd_kernel");
     }
     return TEAM_OK;
 }
 
+// workspace: team_head_workspace_bytes(which <= 1 ? n_rows : 1, C, P, 0, mode)
 extern "C" int team_head_encode(const team_head_weights* hw, int mode, int which, const void* x, int64_t n_rows,
                                 int normalize, float* out, void* workspace, size_t workspace_bytes, void* stream) {
     HeadCtx cx;
-    int rc = setup(cx, hw, mode, 1, 0, workspace, workspace_bytes, stream);
+    TEAM_REQUIRE(which >= 0 && which <= 3 && out != nullptr && n_rows >= 0, "head encode: bad args");
+    if (which == 3 && hw != nullptr) n_rows = hw->num_classes;
+    if (n_rows == 0) return TEAM_OK;
+    int rc = setup(cx, hw, mode, which <= 1 ? n_rows : 1, 0, workspace, workspace_bytes, stream);
     if (rc) return rc;
-    TEAM_REQUIRE(which >= 0 && which <= 3 && out != nullptr, "head encode: bad args");
-    if ((rc = sum_projections(cx, hw))) return rc;
+    HeadWS& w = cx.w;
+    const float* xf = which <= 1 ? reinterpret_cast<const float*>(x) : nullptr;
+    TEAM_REQUIRE(which > 1 || xf != nullptr, "head encode: null input");
+    TEAM_REQUIRE(which != 2 || (x != nullptr && hw->state_emb != nullptr), "head encode: null state ids / embedding");
+    TEAM_REQUIRE(which != 3 || hw->prototypes != nullptr, "head encode: null prototypes");
+    bind_inputs(cx, hw, xf, nullptr, nullptr);
+    {
+        team_head_weights tmp = *hw;            // only the projections (and the rows being encoded) are staged
+        tmp.w_q = tmp.w_k = tmp.w_v = tmp.w_fc = nullptr;
+        if (which != 3) tmp.prototypes = nullptr;
+        if (which != 2) tmp.state_emb = nullptr;
+        if ((rc = prologue(cx, &tmp, 3, xf, nullptr, nullptr, which <= 1 ? n_rows : 0))) return rc;
+    }
+    auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
     const int k = which == 3 ? 0 : which;
-    const float* src = reinterpret_cast<const float*>(x);
-    if (which == 3) { src = hw->prototypes; n_rows = hw->num_classes; }
+    Wave wv;
+    NormList nl;
+    memset(&nl, 0, sizeof(nl));
+    nl.do_normalize = normalize;
+    int blocks = 0;
     if (which == 2) {
         // 10-row table first, then gather by state id
-        TEAM_REQUIRE(x != nullptr, "head encode: null state ids");
-        HG(false, true, 10, D, D, 1.f, hw->state_emb, D, cx.w.Wsum[2], D, 0.f, cx.w.Ztab, D, cx.w.bsum[2]);
-        rows_normalize_kernel<<<2, 256, 0, cx.st>>>(cx.w.Ztab, 10, cx.w.Ztab, nullptr, normalize);
+        seg(wv.add(10, D, 0.f, fonly(w.Ztab, D), w.bsum[2]), false, w.E, false, w.Wsum[2], D);
+        RUN(wv);
+        norm_add(nl, blocks, w.Ztab, w.Ztab, nullptr, nullptr, 10);
+        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
         TEAM_LAUNCH_CHECK("rows_normalize_kernel");
-        gather_rows_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, cx.st>>>(cx.w.Ztab, reinterpret_cast<const int64_t*>(x), n_rows, out);
+        gather_rows_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, cx.st>>>(w.Ztab, reinterpret_cast<const int64_t*>(x), n_rows, out);
         TEAM_LAUNCH_CHECK("gather_rows_kernel");
         return TEAM_OK;
     }
-    TEAM_REQUIRE(src != nullptr, "head encode: null input");
-    HG(false, true, n_rows, D, D, 1.f, src, D, cx.w.Wsum[k], D, 0.f, out, D, cx.w.bsum[k]);
+    seg(wv.add(n_rows, D, 0.f, fonly(out, D), w.bsum[k]), false, which == 3 ? w.protos : w.img, false, w.Wsum[k], D);
+    RUN(wv);
     if (normalize) {
-        rows_normalize_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, cx.st>>>(out, n_rows, out, nullptr, 1);
+        norm_add(nl, blocks, out, out, nullptr, nullptr, n_rows);
+        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
         TEAM_LAUNCH_CHECK("rows_normalize_kernel");
     }
     return TEAM_OK;

@@ -28,55 +28,75 @@ __host__ __device__ inline size_t table_partial_len(const HeadDims& d) {
            + (size_t)2 * D;          // dgamma, dbeta
 }
 constexpr int OWN_PARTIAL_LEN = 3 * D;   // dgamma, dbeta, dbfc of the own rows
+constexpr int NRM_MAX_PARTIALS = 64;     // per-segment column-sum partials of nrm_bwd (bias gradients)
+
+// fp32 matrix + (mode BF16) its bf16 shadow with the same leading dimension.  Every GEMM operand of the
+// head is a Mat: the fp32 side feeds the CUDA-core kernels and the F32 mode, the bf16 side feeds tcgen05.
+// The shadow is written by whoever produces the fp32 values (GEMM epilogue or row kernel) - there is no
+// separate conversion pass except for the caller's inputs and weights (prep_kernel).
+struct Mat {
+    float* f;
+    __nv_bfloat16* h;
+    int64_t ld;
+};
+inline Mat sub(const Mat& m, int64_t r0, int64_t c0) {
+    Mat o;
+    o.f = m.f ? m.f + r0 * m.ld + c0 : nullptr;
+    o.h = m.h ? m.h + r0 * m.ld + c0 : nullptr;
+    o.ld = m.ld;
+    return o;
+}
 
 struct HeadWS {
     // ---- step level
-    float *Wsum[3], *bsum[3];         // summed projections img/text/state
+    Mat Wsum[3];                      // [D][D] summed projections img/text/state
+    float* bsum[3];
+    Mat Wqkv;                         // [3D][D] packed {Wq;Wk;Wv}
+    Mat Wfc;                          // f = caller's w_fc
+    Mat protos, E, img, txt, tcls;    // caller's inputs (f) + bf16 shadows
     float* Zc;                        // [Tc][D] encode_text(text_cls), pre-normalisation
     float* Ztab;                      // [Rt][D] pre-normalisation proto/state rows
-    float* S;                         // [Nsp][D] step rows
+    Mat S;                            // [Nsp][D] step rows
     float* invS;                      // [Nsp] inverse norms (proto + state rows)
-    float* QKVs;                      // [Nsp][3D]
-    float* VFs;                       // [Nsp][D]
+    Mat QKVs;                         // [Nsp][3D]
+    Mat VFs;                          // [Nsp][D]
     float* TT;                        // [Nsp][Nsp]
     float *mt, *Zt;                   // [Nsp]
-    float* Pt;                        // [Nsp][Nsp]
+    Mat Pt;                           // [Nsp][Nsp]
     float* NFt;                       // [Nsp][D]
     // ---- per sample
-    float* Xo;                        // [B2][D]
+    Mat Xo;                           // [B2][D]
     float* invo;                      // [B2]
-    float* QKVo;                      // [B2][3D]
+    Mat QKVo;                         // [B2][3D]
     float* VFo;                       // [B2][D]
-    float *SQ, *SK;                   // [B2][Nsp]
-    float* Aext;                      // [B2][Nsp]
+    Mat SQ;                           // [B2][Nsp]  scores of own queries; backward: dA then dS in place
+    float* SK;                        // [B2][Nsp]
+    Mat Aext;                         // [B2][Nsp]
     float* aown;                      // [B2][2]
     float* Ybo;                       // [B2][D]
-    float* lnstat;                    // [B2][2]
     // ---- backward scratch
-    float* dYo;                       // [B2][D]
+    Mat dYo;                          // [B2][D]
     float* rowdot;                    // [B2]
     float* dsown;                     // [B2][2]
-    float* dSK;                       // [B2][Nsp]
-    float* dVFo;                      // [B2][D]
-    float* dQKVo;                     // [B2][3D]
-    float* dXo;                       // [B2][D]
-    float *Rfull, *Gfull;             // [Nsp][D]
+    Mat dSK;                          // [B2][Nsp]
+    Mat dVFo;                         // [B2][D]
+    Mat dQKVo;                        // [B2][3D]
+    Mat dXo;                          // [B2][D]   du_o, then + dQKV Wqkv, then dz in place
+    float* Rfull;                     // [Nsp][D]  residual gradient of the step rows, then + dQKVs Wqkv
+    Mat Gfull;                        // [Nsp][D]
     float* hfull;                     // [Nsp]
-    float* dTT;                       // [Nsp][Nsp]
+    Mat dTT;                          // [Nsp][Nsp]
     float* tmpNN;                     // [Nsp][Nsp]
-    float* dVFs;                      // [Nsp][D]
-    float* dQKVs;                     // [Nsp][3D]
-    float* dZtab;                     // [Rt][D]
+    Mat dVFs;                         // [Nsp][D]
+    Mat dQKVs;                        // [Nsp][3D]
+    Mat dZtab;                        // [Rt][D]
     float* tab_partials;              // [nctas][table_partial_len]
     float* tab_reduced;               // [table_partial_len]
     float* own_partials;              // [nctas][OWN_PARTIAL_LEN]
     float* own_reduced;               // [OWN_PARTIAL_LEN]
-    float* colsum_partials;           // [64][D]
+    float* nrm_partials;              // [4][NRM_MAX_PARTIALS][D]
     void* gemm_ws;                    // split-K scratch
     size_t gemm_ws_bytes;
-    // ---- bf16 operands for the tcgen05 path (mode BF16 only)
-    void* bf16_area;
-    size_t bf16_bytes;
     size_t total_bytes;
 };
 

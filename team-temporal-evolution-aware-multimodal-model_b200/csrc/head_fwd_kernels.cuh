@@ -11,47 +11,104 @@
 
 namespace team {
 
-// ------------------------------------------------------------------ sum_t W_t, sum_t b_t
+// ------------------------------------------------------------------ step prologue: sum_t W_t, sum_t b_t, operand staging
+// ONE launch: blocks [0, sum_blocks) sum the per-task projection weights/biases (fp32 + bf16 shadow); the
+// remaining blocks copy/convert the listed fp32 matrices (caller inputs, attention weights) into the
+// workspace (optional fp32 copy, optional bf16 shadow).  Both lists travel by value (graph-capturable).
+struct PrepSum {
+    PtrList W[3], Bv[3];
+    float* Wout[3];
+    __nv_bfloat16* Wh[3];
+    float* bout[3];
+    int n;                     // how many of the 3 projections to sum
+};
+struct ConvSeg {
+    const float* src;
+    float* dstf;               // optional fp32 copy
+    __nv_bfloat16* dsth;       // optional bf16 shadow
+    int64_t n4;                // float4 count (rows * cols / 4; both sides contiguous)
+    int blk0;                  // first conversion block of this segment
+};
+constexpr int PREP_MAX_SEGS = 12;
+struct ConvList {
+    ConvSeg s[PREP_MAX_SEGS];
+    int n;
+    int sum_blocks;
+};
+constexpr int PREP_SUM_BLOCKS_PER_W = D * D / 4 / 256;      // 256
+
 __global__ void __launch_bounds__(256)
-sum_weights_kernel(PtrList W, PtrList Bv, float* __restrict__ Wout, float* __restrict__ bout) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // float4 index
-    if (i < D * D / 4) {
-        float4 s = reinterpret_cast<const float4*>(W.p[0])[i];
+prep_kernel(const __grid_constant__ PrepSum ps, const __grid_constant__ ConvList cl) {
+    if ((int)blockIdx.x < cl.sum_blocks) {
+        const int k = blockIdx.x / PREP_SUM_BLOCKS_PER_W;
+        const int i = (blockIdx.x % PREP_SUM_BLOCKS_PER_W) * 256 + threadIdx.x;        // float4 index
+        const PtrList& W = ps.W[k];
+        float4 s = __ldg(reinterpret_cast<const float4*>(W.p[0]) + i);
         for (int t = 1; t < W.n; ++t) {
-            const float4 a = reinterpret_cast<const float4*>(W.p[t])[i];
+            const float4 a = __ldg(reinterpret_cast<const float4*>(W.p[t]) + i);
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
-        reinterpret_cast<float4*>(Wout)[i] = s;
-    }
-    if (i < D / 4) {
-        float4 s = reinterpret_cast<const float4*>(Bv.p[0])[i];
-        for (int t = 1; t < Bv.n; ++t) {
-            const float4 a = reinterpret_cast<const float4*>(Bv.p[t])[i];
-            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        reinterpret_cast<float4*>(ps.Wout[k])[i] = s;
+        if (ps.Wh[k] != nullptr) reinterpret_cast<uint2*>(ps.Wh[k])[i] = pack_bf16x4(s);
+        if (i < D / 4) {
+            const PtrList& Bv = ps.Bv[k];
+            float4 b = __ldg(reinterpret_cast<const float4*>(Bv.p[0]) + i);
+            for (int t = 1; t < Bv.n; ++t) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(Bv.p[t]) + i);
+                b.x += a.x; b.y += a.y; b.z += a.z; b.w += a.w;
+            }
+            reinterpret_cast<float4*>(ps.bout[k])[i] = b;
         }
-        reinterpret_cast<float4*>(bout)[i] = s;
+        return;
     }
+    const int cb = (int)blockIdx.x - cl.sum_blocks;
+    int si = 0;
+    for (int q = 1; q < cl.n; ++q)
+        if (cb >= cl.s[q].blk0) si = q;
+    const ConvSeg& sg = cl.s[si];
+    const int64_t i = (int64_t)(cb - sg.blk0) * 256 + threadIdx.x;
+    if (i >= sg.n4) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sg.src) + i);
+    if (sg.dstf != nullptr) reinterpret_cast<float4*>(sg.dstf)[i] = v;
+    if (sg.dsth != nullptr) reinterpret_cast<uint2*>(sg.dsth)[i] = pack_bf16x4(v);
 }
 
 // ------------------------------------------------------------------ row L2-normalise (F.normalize)
-// X[r] = Z[r] / max(|Z[r]|, 1e-12); inv[r] = 1/max(|Z[r]|,eps).  warp per row.  If gather != null the
-// source row is Z[gather[r]] (embedding lookup).  dst_map: row r is written to X[dst_off + r].
+// For every segment: X[r] = Z[r] / max(|Z[r]|, 1e-12) (fp32 + bf16 shadow); inv[r] = 1/max(|Z[r]|,eps).
+// warp per row, 8 rows per block, one launch for all row sets of a step.
+struct NormSeg {
+    const float* Z;
+    float* X;
+    __nv_bfloat16* Xh;
+    float* inv;
+    int64_t rows;
+    int blk0;
+};
+struct NormList {
+    NormSeg s[4];
+    int n;
+    int do_normalize;
+};
 __global__ void __launch_bounds__(256)
-rows_normalize_kernel(const float* __restrict__ Z, int64_t n_rows, float* __restrict__ X, float* __restrict__ inv,
-                      int do_normalize) {
+rows_normalize_kernel(const __grid_constant__ NormList nl) {
+    int si = 0;
+    for (int q = 1; q < nl.n; ++q)
+        if ((int)blockIdx.x >= nl.s[q].blk0) si = q;
+    const NormSeg& sg = nl.s[si];
     const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= n_rows) return;
+    const int64_t r = (int64_t)((int)blockIdx.x - sg.blk0) * 8 + (threadIdx.x >> 5);
+    if (r >= sg.rows) return;
     float4 v[4];
-    ld_row(Z + r * D, lane, v);
+    ld_row(sg.Z + r * D, lane, v);
     float s = 1.0f;
-    if (do_normalize) {
+    if (nl.do_normalize) {
         const float ss = warp_sum(dot_part(v, v));
         s = 1.0f / fmaxf(sqrtf(ss), NORM_EPS);
         scale_row(v, s);
     }
-    st_row(X + r * D, lane, v);
-    if (inv != nullptr && lane == 0) inv[r] = s;
+    st_row(sg.X + r * D, lane, v);
+    st_row_h(sg.Xh != nullptr ? sg.Xh + r * D : nullptr, lane, v);
+    if (sg.inv != nullptr && lane == 0) sg.inv[r] = s;
 }
 
 // out[r] = table[clamp(ids[r])]  (state-embedding style gather of 512-wide rows)
@@ -67,7 +124,8 @@ gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
 
 // prompts of all tasks -> S rows [C, C+P); zero rows [Ns, Nsp)
 __global__ void __launch_bounds__(128)
-fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float* __restrict__ S) {
+fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float* __restrict__ S,
+                        __nv_bfloat16* __restrict__ Sh) {
     const int r = blockIdx.x;                    // 0 .. P + (Nsp-Ns) - 1
     const int P = prompts.n * ppt;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -79,13 +137,14 @@ fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float*
         dst = Ns + (r - P);
     }
     reinterpret_cast<float4*>(S + (size_t)dst * D)[threadIdx.x] = v;
+    if (Sh != nullptr) reinterpret_cast<uint2*>(Sh + (size_t)dst * D)[threadIdx.x] = pack_bf16x4(v);
 }
 
 // ------------------------------------------------------------------ per-step softmax partials of step-row queries
 // For every step row r: m_r = max_j<M TT[r][j]/tau, P[r][j] = exp(TT[r][j]/tau - m_r) (0 for j>=M), Z_r = sum_j P.
 __global__ void __launch_bounds__(256)
 table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restrict__ mt, float* __restrict__ Zt,
-                  float* __restrict__ Pt) {
+                  float* __restrict__ Pt, __nv_bfloat16* __restrict__ Pth) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= Nsp) return;
@@ -97,6 +156,7 @@ table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restric
         float p = 0.f;
         if (j < M) { p = expf(TT[(size_t)r * Nsp + j] * INV_TAU - mx); z += p; }
         Pt[(size_t)r * Nsp + j] = p;
+        if (Pth != nullptr) Pth[(size_t)r * Nsp + j] = __float2bfloat16_rn(p);
     }
     z = warp_sum(z);
     if (lane == 0) { mt[r] = mx; Zt[r] = z; }
@@ -106,7 +166,8 @@ table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restric
 // keys: M shared step rows, the sample's state-table row (column M+sid), own image key, own text key.
 __global__ void __launch_bounds__(256)
 attn_own_kernel(HeadDims d, const float* __restrict__ SQ, const float* __restrict__ QKVo,
-                const int64_t* __restrict__ state_ids, float* __restrict__ Aext, float* __restrict__ aown) {
+                const int64_t* __restrict__ state_ids, float* __restrict__ Aext, __nv_bfloat16* __restrict__ Aexth,
+                float* __restrict__ aown) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= d.B2) return;
@@ -131,7 +192,11 @@ attn_own_kernel(HeadDims d, const float* __restrict__ SQ, const float* __restric
     const float p_img = expf(s_img - mx), p_txt = expf(s_txt - mx);
     z = warp_sum(z) + p_img + p_txt;
     const float iz = 1.0f / z;
-    for (int j = lane; j < d.Nsp; j += 32) Aext[(size_t)row * d.Nsp + j] *= iz;
+    for (int j = lane; j < d.Nsp; j += 32) {
+        const float a = Aext[(size_t)row * d.Nsp + j] * iz;
+        Aext[(size_t)row * d.Nsp + j] = a;
+        if (Aexth != nullptr) Aexth[(size_t)row * d.Nsp + j] = __float2bfloat16_rn(a);
+    }
     if (lane == 0) { aown[2 * row] = p_img * iz; aown[2 * row + 1] = p_txt * iz; }
 }
 
@@ -139,7 +204,7 @@ attn_own_kernel(HeadDims d, const float* __restrict__ SQ, const float* __restric
 __global__ void __launch_bounds__(256)
 ln_own_fwd_kernel(HeadDims d, float* __restrict__ Ybo, const float* __restrict__ aown,
                   const float* __restrict__ VFo, const float* __restrict__ Xo, const float* __restrict__ bfc,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ lnstat,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
                   float* __restrict__ out_image, float* __restrict__ out_text) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -158,7 +223,6 @@ ln_own_fwd_kernel(HeadDims d, float* __restrict__ Ybo, const float* __restrict__
     float rstd;
     ln_forward(y, g, be, xh, rstd, o);
     st_row((row < d.B ? out_image : out_text) + (size_t)b * D, lane, o);
-    (void)lnstat;
 }
 
 // ------------------------------------------------------------------ table-query rows (prototype + state outputs)

@@ -22,6 +22,12 @@ __device__ __forceinline__ void st_row(float* p, int lane, const float4 (&v)[4])
 #pragma unroll
     for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[lane + 32 * i] = v[i];
 }
+// bf16 shadow of a 512-wide row (same lane -> column mapping); p may be null (F32 mode)
+__device__ __forceinline__ void st_row_h(__nv_bfloat16* p, int lane, const float4 (&v)[4]) {
+    if (p == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<uint2*>(p)[lane + 32 * i] = pack_bf16x4(v[i]);
+}
 __device__ __forceinline__ float dot_part(const float4 (&a)[4], const float4 (&b)[4]) {
     float s = 0.f;
 #pragma unroll

@@ -174,7 +174,7 @@ def encode(pack: HeadParamPack, which: str, x: Optional[torch.Tensor], img_proto
     else:
         x = _f32c(x, dev); n, xp = x.shape[0], x.data_ptr()
     L = capi.lib()
-    nbytes = L.team_head_workspace_bytes(1, hw.num_classes, pack.T * pack.ppt, 0, mode)
+    nbytes = L.team_head_workspace_bytes(n if idx <= 1 else 1, hw.num_classes, pack.T * pack.ppt, 0, mode)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     out = torch.empty((n, capi.D), dtype=torch.float32, device=dev)
     capi.check(L.team_head_encode(C.byref(hw), mode, idx, xp, n, int(normalize), out.data_ptr(),

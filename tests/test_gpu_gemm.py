@@ -142,3 +142,39 @@ def test_gemm_bf16_group(with_ws):
             if Cb is not None:
                 assert rel(Cb[:, :N].float(), ref) < 4e-3, (rep, i)
                 assert torch.equal(Cb[:, :N], (Cf if Cf is not None else ref.float()).to(torch.bfloat16)) or Cf is None
+
+
+@pytest.mark.parametrize("maj", [((1, 1), (1, 1)), ((1, 1), (0, 1)), ((0, 0), (1, 0)), ((0, 1), (0, 1))])
+def test_gemm_bf16_two_segments(maj):
+    """C = A1 B1 + A2 B2 accumulated in one TMEM tile (segments may differ in operand majors and in K)."""
+    from team_b200 import capi
+    capi.require_device()
+    g = torch.Generator().manual_seed(5)
+    pad = lambda n: (n + 7) // 8 * 8
+    cases = [(144, 512, 2048, 144), (512, 512, 2048, 20), (512, 512, 10, 1000), (2048, 512, 1536, 72)]
+    descs = (capi.GemmDesc * len(cases))()
+    keep, refs, outs = [], [], []
+    for i, (M, N, K1, K2) in enumerate(cases):
+        ref = torch.zeros((M, N), dtype=torch.float64)
+        ptrs = []
+        for (a_mn, b_mn), K in zip(maj, (K1, K2)):
+            A = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), generator=g).to(torch.bfloat16).cuda()
+            B = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), generator=g).to(torch.bfloat16).cuda()
+            Av = (A[:, :M] if a_mn else A[:, :K]).double().cpu()
+            Bv = (B[:, :N] if b_mn else B[:, :K]).double().cpu()
+            ref += (Av.t() if a_mn else Av) @ (Bv if b_mn else Bv.t())
+            ptrs.append((A, B))
+            keep += [A, B]
+        out = torch.full((M, N), float("nan"), device="cuda")
+        d = descs[i]
+        (d.a_mn, d.b_mn), (d.a_mn2, d.b_mn2) = maj
+        d.M, d.N, d.K, d.K2, d.alpha, d.beta = M, N, K1, K2, 1.0, 0.0
+        d.A, d.lda, d.B, d.ldb = ptrs[0][0].data_ptr(), ptrs[0][0].stride(0), ptrs[0][1].data_ptr(), ptrs[0][1].stride(0)
+        d.A2, d.lda2, d.B2, d.ldb2 = ptrs[1][0].data_ptr(), ptrs[1][0].stride(0), ptrs[1][1].data_ptr(), ptrs[1][1].stride(0)
+        d.C, d.ldc = out.data_ptr(), N
+        refs.append(ref); outs.append(out)
+    ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    capi.check(capi.lib().team_gemm_bf16_group(descs, len(cases), ws.data_ptr(), ws.numel(), _st()), "team_gemm_bf16_group")
+    torch.cuda.synchronize()
+    for i in range(len(cases)):
+        assert rel(outs[i], refs[i]) < 3e-6, (i, rel(outs[i], refs[i]))
