@@ -165,6 +165,15 @@ int team_head_encode(const team_head_weights* w, int mode, int which, const void
                      int64_t n_rows, int normalize, float* out,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradient of encode_image / encode_text (which = 0 | 1) w.r.t. the newest projection of that modality:
+ * y = [normalize](x Wsum^T + bsum); g_w[512,512] = dz^T x, g_b[512] = colsum(dz) with dz = g_out or its
+ * normalise-backward.  This is the autograd path of the ClipLoss branch (models/proof.py:428-431).
+ * workspace: team_head_workspace_bytes(n_rows, C, P, 0, mode); team_head_encode takes the same size
+ * (which <= 1) or the batch-1 size (which >= 2). */
+int team_head_encode_bwd(const team_head_weights* w, int mode, int which, const float* x, int64_t n_rows,
+                         int normalize, const float* g_out, float* g_w, float* g_b,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ temporal GCN + state distances
  * Replaces: TemporalStateGCN.forward / TemporalGCNBlock.forward   models/dynamic_modal_graph.py:239-337
  *           (called under no_grad from InsectLifecycleModel.evolve_and_update, models/state_evolution.py:326-327).

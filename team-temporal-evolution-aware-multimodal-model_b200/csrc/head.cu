@@ -446,7 +446,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         for (int i = 0; i < 4; ++i) { fa.part[i] = nl.s[i].partial; fa.nblk[i] = nblk[i]; }
         fa.b_img = gr->b_img; fa.b_text = gr->b_text; fa.b_state = gr->b_state;
         fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
-        finish_bwd_kernel<<<3 + (fa.prompts ? d.P : 0), 128, 0, cx.st>>>(fa);
+        finish_bwd_kernel<<<3 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st>>>(fa);
         TEAM_LAUNCH_CHECK("finish_bwd_kernel");
     }
     return TEAM_OK;
@@ -499,5 +499,62 @@ extern "C" int team_head_encode(const team_head_weights* hw, int mode, int which
         rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
         TEAM_LAUNCH_CHECK("rows_normalize_kernel");
     }
+    return TEAM_OK;
+}
+
+// Gradient of encode_image / encode_text (which = 0 | 1) with respect to the newest projection of that
+// modality (older ones are frozen and share the same gradient, utils/inc_net.py:494-507):
+//   y = [normalize](x Wsum^T + bsum);  g_w = dz^T x,  g_b = colsum(dz),  dz = g_out or its normalise-backward.
+// The forward is recomputed (one GEMM + one row kernel) instead of being kept alive by the caller.
+// workspace: team_head_workspace_bytes(n_rows, C, P, 0, mode)
+extern "C" int team_head_encode_bwd(const team_head_weights* hw, int mode, int which, const float* x, int64_t n_rows,
+                                    int normalize, const float* g_out, float* g_w, float* g_b, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    HeadCtx cx;
+    TEAM_REQUIRE((which == 0 || which == 1) && x != nullptr && g_out != nullptr && g_w != nullptr && g_b != nullptr && n_rows >= 1,
+                 "head encode bwd: bad args");
+    int rc = setup(cx, hw, mode, n_rows, 0, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    HeadWS& w = cx.w;
+    bind_inputs(cx, hw, x, nullptr, nullptr);
+    {
+        team_head_weights tmp = *hw;
+        tmp.w_q = tmp.w_k = tmp.w_v = tmp.w_fc = nullptr;
+        tmp.prototypes = nullptr; tmp.state_emb = nullptr;
+        if ((rc = prologue(cx, &tmp, 3, x, nullptr, nullptr, n_rows))) return rc;
+    }
+    auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
+    Wave wv;
+    if (normalize) {
+        seg(wv.add(n_rows, D, 0.f, fonly(w.Xo.f, D), w.bsum[which]), false, w.img, false, w.Wsum[which], D);
+        RUN(wv);
+        NormList nl;
+        memset(&nl, 0, sizeof(nl));
+        nl.do_normalize = 1;
+        int blocks = 0;
+        norm_add(nl, blocks, w.Xo.f, w.Xo.f, nullptr, w.invo, n_rows);
+        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
+        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
+    }
+    NrmList nl;
+    memset(&nl, 0, sizeof(nl));
+    nl.identity = normalize ? 0 : 1;
+    int rpb = (int)((n_rows + NRM_MAX_PARTIALS - 1) / NRM_MAX_PARTIALS);
+    rpb = (rpb + 7) / 8 * 8;
+    NrmSeg& sg = nl.s[0];
+    sg.dXsrc = g_out; sg.X = w.Xo.f; sg.inv = w.invo; sg.dZ = w.dXo.f; sg.dZh = w.dXo.h; sg.rows = n_rows; sg.src_off = 0;
+    sg.rows_per_block = rpb; sg.blk0 = 0; sg.partial = w.nrm_partials;
+    nl.n = 1;
+    const int nblk = (int)((n_rows + rpb - 1) / rpb);
+    nrm_bwd_kernel<<<nblk, 256, 0, cx.st>>>(nl);
+    TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
+    seg(wv.add(D, D, 0.f, fonly(g_w, D)), true, sub(w.dXo, 0, 0), true, w.img, n_rows);
+    RUN(wv);
+    FinishArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.part[0] = w.nrm_partials; fa.nblk[0] = nblk;
+    fa.b_img = g_b;
+    finish_bwd_kernel<<<1, 512, 0, cx.st>>>(fa);
+    TEAM_LAUNCH_CHECK("finish_bwd_kernel");
     return TEAM_OK;
 }

@@ -378,6 +378,7 @@ struct NrmSeg {
 struct NrmList {
     NrmSeg s[4];
     int n;
+    int identity;              // 1: dz = dx (no normalisation in the forward)
 };
 __global__ void __launch_bounds__(256)
 nrm_bwd_kernel(const __grid_constant__ NrmList nl) {
@@ -395,14 +396,16 @@ nrm_bwd_kernel(const __grid_constant__ NrmList nl) {
     for (int64_t r = r_begin + warp; r < r_end; r += 8) {
         const int64_t xr = r + sg.src_off;
         float4 x[4], dx[4];
-        ld_row(sg.X + xr * D, lane, x);
+        if (!nl.identity) ld_row(sg.X + xr * D, lane, x);
         ld_row(sg.dXsrc + xr * D, lane, dx);
-        const float dt = warp_sum(dot_part(x, dx));
-        const float s = sg.inv[xr];
+        if (!nl.identity) {
+            const float dt = warp_sum(dot_part(x, dx));
+            const float s = sg.inv[xr];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            dx[i].x = s * (dx[i].x - x[i].x * dt); dx[i].y = s * (dx[i].y - x[i].y * dt);
-            dx[i].z = s * (dx[i].z - x[i].z * dt); dx[i].w = s * (dx[i].w - x[i].w * dt);
+            for (int i = 0; i < 4; ++i) {
+                dx[i].x = s * (dx[i].x - x[i].x * dt); dx[i].y = s * (dx[i].y - x[i].y * dt);
+                dx[i].z = s * (dx[i].z - x[i].z * dt); dx[i].w = s * (dx[i].w - x[i].w * dt);
+            }
         }
         st_row(sg.dZ + r * D, lane, dx);
         st_row_h(sg.dZh != nullptr ? sg.dZh + r * D : nullptr, lane, dx);
@@ -430,26 +433,37 @@ struct FinishArgs {
     float* prompts;            // may be null
     int C, P;
 };
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 finish_bwd_kernel(const __grid_constant__ FinishArgs fa) {
-    const int t = threadIdx.x;
+    __shared__ float4 fold[4][128];
+    const int t = threadIdx.x & 127, g = threadIdx.x >> 7;     // 4 groups of 128 threads, each a quarter of the partials
     if (blockIdx.x < 3) {
         const int k = blockIdx.x;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         const int segs[2] = {k == 0 ? 0 : (k == 1 ? 1 : 3), k == 0 ? 2 : -1};
         for (int q = 0; q < 2; ++q) {
-            if (segs[q] < 0) continue;
+            if (segs[q] < 0 || fa.part[segs[q]] == nullptr) continue;
             const float* p = fa.part[segs[q]];
-            for (int b = 0; b < fa.nblk[segs[q]]; ++b) {
+            const int n = fa.nblk[segs[q]];
+            const int per = (n + 3) / 4, b0 = g * per, b1 = min(n, b0 + per);
+            for (int b = b0; b < b1; ++b) {
                 const float4 a = reinterpret_cast<const float4*>(p + (size_t)b * D)[t];
                 s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
             }
         }
-        float* out = k == 0 ? fa.b_img : (k == 1 ? fa.b_text : fa.b_state);
-        reinterpret_cast<float4*>(out)[t] = s;
+        fold[g][t] = s;
+        __syncthreads();
+        if (g == 0) {
+            float4 r = fold[0][t];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) { r.x += fold[q][t].x; r.y += fold[q][t].y; r.z += fold[q][t].z; r.w += fold[q][t].w; }
+            float* out = k == 0 ? fa.b_img : (k == 1 ? fa.b_text : fa.b_state);
+            if (out != nullptr) reinterpret_cast<float4*>(out)[t] = r;
+        }
         return;
     }
-    const int r = blockIdx.x - 3;
+    // prompt rows: 4 rows per block
+    const int r = (blockIdx.x - 3) * 4 + g;
     if (fa.prompts != nullptr && r < fa.P)
         reinterpret_cast<float4*>(fa.prompts + (size_t)r * D)[t] = reinterpret_cast<const float4*>(fa.Rfull + (size_t)(fa.C + r) * D)[t];
 }

@@ -153,6 +153,24 @@ def build_evolution_graph(by_state: Dict[int, Dict[int, torch.Tensor]],
     return EvolutionGraph(cls, st, tm, rowptr, src.astype(np.int32), w.astype(np.float32), order)
 
 
+def graph_from_edge_list(n_nodes: int, edge_index, edge_weights, time_steps) -> EvolutionGraph:
+    """EvolutionGraph from the reference's COO inputs of TemporalStateGCN.forward
+    (edge_index [2,E] src/dst, edge_weights [E], time_steps [N,1]): destination-sorted, stable, so the
+    per-destination accumulation order equals the reference's edge-loop order."""
+    ei = np.asarray(edge_index.detach().cpu().numpy() if torch.is_tensor(edge_index) else edge_index, dtype=np.int64).reshape(2, -1)
+    w = np.asarray(edge_weights.detach().cpu().numpy() if torch.is_tensor(edge_weights) else edge_weights, dtype=np.float32).reshape(-1)
+    t = np.asarray(time_steps.detach().cpu().numpy() if torch.is_tensor(time_steps) else time_steps, dtype=np.float64).reshape(-1)
+    if t.shape[0] != n_nodes or w.shape[0] != ei.shape[1]:
+        raise ValueError("time_steps must have one entry per node and edge_weights one per edge")
+    if ei.size and (ei.min() < 0 or ei.max() >= n_nodes):
+        raise ValueError("edge_index out of range")
+    o = np.argsort(ei[1], kind="stable")
+    rowptr = np.zeros(n_nodes + 1, dtype=np.int32)
+    np.cumsum(np.bincount(ei[1], minlength=n_nodes), out=rowptr[1:])
+    z = np.zeros(n_nodes, dtype=np.int64)
+    return EvolutionGraph(z, z.copy(), t, rowptr, ei[0][o].astype(np.int32), w[o], [])
+
+
 # --------------------------------------------------------------------------- temporal GCN
 def _tgcn_weights(p: Dict[str, torch.Tensor], prefix: str, dev):
     """ctypes view of the TemporalStateGCN parameters (state_dict names)."""

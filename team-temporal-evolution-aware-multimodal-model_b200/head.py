@@ -182,6 +182,87 @@ def encode(pack: HeadParamPack, which: str, x: Optional[torch.Tensor], img_proto
     return out
 
 
+class _EncodeFn(torch.autograd.Function):
+    """encode_image / encode_text with autograd to the projections (the ClipLoss branch of the training
+    step, models/proof.py:428-431).  No gradient flows into the (frozen-backbone) features."""
+
+    @staticmethod
+    def forward(ctx, x, idx, normalize, mode, T, ppt, *params):
+        capi.require_device()
+        if not x.is_cuda:
+            raise capi.TeamB200Error("encode needs CUDA tensors (no CPU fallback)")
+        dev = x.device
+        x = _f32c(x, dev)
+        flat = [_f32c(p, dev) for p in params]
+        hw = _fill_weights(T, ppt, flat, torch.zeros((1, capi.D), device=dev))
+        n = x.shape[0]
+        L = capi.lib()
+        nbytes = L.team_head_workspace_bytes(max(n, 1), 1, T * ppt, 0, mode)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        out = torch.empty((n, capi.D), dtype=torch.float32, device=dev)
+        capi.check(L.team_head_encode(C.byref(hw), mode, idx, x.data_ptr(), n, int(normalize), out.data_ptr(),
+                                      ws.data_ptr(), nbytes, _stream_ptr()), "team_head_encode")
+        ctx.hold = (x, flat)
+        ctx.meta = (idx, int(normalize), mode, T, ppt, n, nbytes)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, flat = ctx.hold
+        idx, normalize, mode, T, ppt, n, nbytes = ctx.meta
+        dev = x.device
+        hw = _fill_weights(T, ppt, flat, torch.zeros((1, capi.D), device=dev))
+        gw = torch.empty((capi.D, capi.D), dtype=torch.float32, device=dev)
+        gb = torch.empty((capi.D,), dtype=torch.float32, device=dev)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        g = _f32c(g_out, dev)
+        capi.check(capi.lib().team_head_encode_bwd(C.byref(hw), mode, idx, x.data_ptr(), n, normalize, g.data_ptr(),
+                                                   gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()),
+                   "team_head_encode_bwd")
+        need = ctx.needs_input_grad[6:]
+        out: List[Optional[torch.Tensor]] = [None] * len(need)
+        for t in range(T):                       # W = sum_t W_t  =>  dW_t = dW for every unfrozen t
+            if need[2 * idx * T + t]:
+                out[2 * idx * T + t] = gw
+            if need[(2 * idx + 1) * T + t]:
+                out[(2 * idx + 1) * T + t] = gb
+        return (None,) * 6 + tuple(out)
+
+
+def encode_grad(pack: HeadParamPack, which: str, x: torch.Tensor, normalize: bool = False, mode: int = MODE_F32):
+    """Differentiable encode_image / encode_text (utils/inc_net.py:401-415)."""
+    idx = {"image": 0, "text": 1}[which]
+    if x.shape[0] == 0:
+        return torch.empty((0, capi.D), dtype=torch.float32, device=x.device)
+    return _EncodeFn.apply(x, idx, normalize, mode, pack.T, pack.ppt, *pack.flat)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Proj_Pure_MLP.forward (convs/projections.py:7-18) on its own: x W^T + b for [*,512] inputs (no autograd)."""
+    capi.require_device()
+    if not x.is_cuda:
+        raise capi.TeamB200Error("linear needs CUDA tensors (no CPU fallback)")
+    dev = x.device
+    shape = x.shape
+    x2 = _f32c(x.reshape(-1, capi.D), dev)
+    w, b = _f32c(weight, dev), _f32c(bias, dev)
+    hw = capi.HeadWeights()
+    hw.num_tasks, hw.prompts_per_task, hw.num_classes = 1, 0, 1
+    hw.w_img[0], hw.b_img[0] = w.data_ptr(), b.data_ptr()
+    hw.w_text[0], hw.b_text[0] = w.data_ptr(), b.data_ptr()
+    hw.w_state[0], hw.b_state[0] = w.data_ptr(), b.data_ptr()
+    n = x2.shape[0]
+    out = torch.empty((n, capi.D), dtype=torch.float32, device=dev)
+    if n == 0:
+        return out.reshape(shape)
+    L = capi.lib()
+    nbytes = L.team_head_workspace_bytes(n, 1, 0, 0, MODE_F32)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    capi.check(L.team_head_encode(C.byref(hw), MODE_F32, 0, x2.data_ptr(), n, 0, out.data_ptr(), ws.data_ptr(), nbytes,
+                                  _stream_ptr()), "team_head_encode")
+    return out.reshape(shape)
+
+
 GRAD_LAYOUT = (("w_img", capi.D * capi.D), ("b_img", capi.D), ("w_text", capi.D * capi.D), ("b_text", capi.D),
                ("w_state", capi.D * capi.D), ("b_state", capi.D), ("state_emb", capi.NUM_STATES * capi.D),
                ("w_q", capi.D * capi.D), ("w_k", capi.D * capi.D), ("w_v", capi.D * capi.D),
