@@ -9,7 +9,7 @@ namespace team {
 HeadDims head_dims(int64_t B, int C, int P, int Tc) {
     HeadDims d;
     d.B = (int)B; d.B2 = 2 * (int)B; d.C = C; d.P = P; d.M = C + P; d.Ns = d.M + 10;
-    d.Nsp = (d.Ns + 15) / 16 * 16; d.Rt = C + 10; d.Tc = Tc; d.nctas = NUM_SMS;
+    d.Nsp = (d.Ns + 15) / 16 * 16; d.Rt = C + 10; d.Tc = Tc; d.nctas = 3 * NUM_SMS;
     return d;
 }
 
@@ -41,7 +41,7 @@ void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     w->QKVs = mat(Nsp, 3 * D); w->VFs = mat(Nsp, D);
     w->TT = take(Nsp * Nsp); w->mt = take(Nsp); w->Zt = take(Nsp); w->Pt = mat(Nsp, Nsp); w->NFt = take(Nsp * D);
     w->Xo = mat(B2, D); w->invo = take(B2);
-    w->QKVo = mat(B2, 3 * D); w->VFo = take(B2 * D);
+    w->QKVo = mat(B2, 3 * D); w->VFo = mat(B2, D);
     w->SQ = mat(B2, Nsp); w->SK = take(B2 * Nsp);
     w->Aext = mat(B2, Nsp); w->aown = take(B2 * 2);
     w->Ybo = take(B2 * D);
@@ -51,6 +51,10 @@ void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     w->Rfull = take(Nsp * D); w->Gfull = mat(Nsp, D); w->hfull = take(Nsp);
     w->dTT = mat(Nsp, Nsp); w->tmpNN = take(Nsp * Nsp); w->dVFs = mat(Nsp, D);
     w->dQKVs = mat(Nsp, 3 * D); w->dZtab = mat(Rt, D);
+    w->ldA = 2 * ((d.Rt + 63) / 64 * 64);
+    w->GG = mat(B2, D); w->A1 = mat(B2, w->ldA); w->A23 = mat(B2, w->ldA);
+    w->RG = take((size_t)w->ldA * D);
+    w->dVFs_a = take(Nsp * D); w->dbfc_parts = take((size_t)EXP_SUM_BLOCKS * D);
     const TabOff to = tab_offsets(d);
     w->tab_partials = take((size_t)d.nctas * to.len); w->tab_reduced = take(to.len);
     w->own_partials = take((size_t)d.nctas * OWN_PARTIAL_LEN); w->own_reduced = take(OWN_PARTIAL_LEN);
@@ -307,7 +311,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
     const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
     seg(wv.add(d.Nsp, D, 0.f, w.VFs), false, Vs, false, w.Wfc, D);
-    seg(wv.add(d.B2, D, 0.f, fonly(w.VFo, D)), false, Vo, false, w.Wfc, D);
+    seg(wv.add(d.B2, D, 0.f, w.VFo), false, Vo, false, w.Wfc, D);
     seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.TT, d.Nsp)), false, Qs, false, Ks, D);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
@@ -320,10 +324,10 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
     seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
     RUN(wv);
-    ln_own_fwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.Ybo, w.aown, w.VFo, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
+    ln_own_fwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
     TEAM_LAUNCH_CHECK("ln_own_fwd_kernel");
-    const int tgrid = d.B < 2 * NUM_SMS ? d.B : 2 * NUM_SMS;
-    table_rows_fwd_kernel<<<tgrid, TR_WARPS * 32, 0, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
+    const int tgrid = d.B < 6 * NUM_SMS ? d.B : 6 * NUM_SMS;
+    table_rows_fwd_kernel<<<tgrid, TQ_WARPS * 32, 0, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
     TEAM_LAUNCH_CHECK("table_rows_fwd_kernel");
     if (want_cls) {
         // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
@@ -351,35 +355,40 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
     // ---- table-query rows (prototype / state outputs)
     const int tgrid = d.B < d.nctas ? d.B : d.nctas;
-    const size_t tsm = (size_t)(3 * TR_WARPS * D + 10 * D + 3 * D + d.Rt * 11) * sizeof(float);
+    const size_t tsm = table_bwd_smem_floats(d) * sizeof(float);
+    TEAM_REQUIRE(tsm <= 200 * 1024, "head bwd: too many classes for the table-row kernel (%d)", d.C);
     TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    table_rows_bwd_kernel<<<tgrid, TR_WARPS * 32, tsm, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.tab_partials);
+    table_rows_bwd_kernel<<<tgrid, TQ_WARPS * 32, tsm, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
     TEAM_LAUNCH_CHECK("table_rows_bwd_kernel");
     // ---- own query rows
     int ogrid = (d.B + 7) / 8;
-    if (ogrid > d.nctas) ogrid = d.nctas;
-    ln_own_bwd_kernel<<<ogrid, 256, 0, cx.st>>>(d, w.Ybo, w.Xo.f, w.VFo, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo.f, w.dVFo.h, w.own_partials);
+    if (ogrid > NUM_SMS) ogrid = NUM_SMS;
+    ln_own_bwd_kernel<<<ogrid, 256, 0, cx.st>>>(d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo.f, w.dVFo.h, w.own_partials);
     TEAM_LAUNCH_CHECK("ln_own_bwd_kernel");
     {
         ReduceJobs rj;
         rj.j[0] = ReduceJob{w.tab_partials, w.tab_reduced, to.len / 4, tgrid};
         rj.j[1] = ReduceJob{w.own_partials, w.own_reduced, OWN_PARTIAL_LEN / 4, ogrid};
-        rj.blocks0 = (int)((to.len / 4 + 63) / 64);
-        reduce_partials_kernel<<<rj.blocks0 + (OWN_PARTIAL_LEN / 4 + 63) / 64, 256, 0, cx.st>>>(rj);
+        rj.blocks0 = (int)((to.len / 4 + RP_COLS - 1) / RP_COLS);
+        reduce_partials_kernel<<<rj.blocks0 + (OWN_PARTIAL_LEN / 4 + RP_COLS - 1) / RP_COLS, RP_COLS * RP_GROUPS, 0, cx.st>>>(rj);
         TEAM_LAUNCH_CHECK("reduce_partials_kernel");
     }
-    expand_table_kernel<<<d.Nsp + 1, 128, 0, cx.st>>>(d, w.tab_reduced, w.own_reduced, w.Rfull, w.Gfull.f, w.Gfull.h, w.hfull, w.dTT.f, w.dVFs.f, gr->ln_g, gr->ln_b, gr->b_fc);
-    TEAM_LAUNCH_CHECK("expand_table_kernel");
     const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
     const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
     const Mat dQo = sub(w.dQKVo, 0, 0), dKo = sub(w.dQKVo, 0, D), dVo = sub(w.dQKVo, 0, 2 * D);
     const Mat dQs = sub(w.dQKVs, 0, 0), dKs = sub(w.dQKVs, 0, D), dVs = sub(w.dQKVs, 0, 2 * D);
     Wave wv;
-    // ---- wave 5: dA = dYo VFs^T (into SQ), G VFs^T, dKo = dSK Qs, dVFs += Aext^T dYo + Pt^T G
+    // ---- wave 5: R/G coefficient GEMM (A1^T GG + A23^T VFo), dA = dYo VFs^T (into SQ), dKo = dSK Qs
+    seg(seg(wv.add(w.ldA, D, 0.f, fonly(w.RG, D)), true, w.A1, true, w.GG, d.B2), true, w.A23, true, w.VFo, d.B2);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, w.dYo, false, w.VFs, D);
-    seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.tmpNN, d.Nsp)), false, w.Gfull, false, w.VFs, D);
     seg(wv.add(d.B2, D, 0.f, dKo), false, w.dSK, true, Qs, d.Nsp);
-    seg(seg(wv.add(d.Nsp, D, 1.f, w.dVFs), true, w.Aext, true, w.dYo, d.B2), true, w.Pt, true, w.Gfull, d.Nsp);
+    seg(wv.add(d.Nsp, D, 0.f, fonly(w.dVFs_a, D)), true, w.Aext, true, w.dYo, d.B2);
+    RUN(wv);
+    expand_table_kernel<<<d.Nsp + EXP_SUM_BLOCKS, 128, 0, cx.st>>>(d, w.tab_reduced, w.own_reduced, w.RG, w.ldA / 2, w.NFt, w.S.f, w.VFs.f, hw->b_fc, w.Rfull, w.Gfull.f, w.Gfull.h, w.hfull, w.dTT.f, w.dVFs.f, w.dVFs_a, gr->ln_g, gr->ln_b, w.dbfc_parts);
+    TEAM_LAUNCH_CHECK("expand_table_kernel");
+    // ---- wave 6: G VFs^T, dVFs += Pt^T G
+    seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.tmpNN, d.Nsp)), false, w.Gfull, false, w.VFs, D);
+    seg(wv.add(d.Nsp, D, 1.f, w.dVFs), true, w.Pt, true, w.Gfull, d.Nsp);
     RUN(wv);
     {   // dS = Aext .* (dA - rowdot) / tau (in place);  dTT += Pt .* (G VFs^T - h) / tau
         const int64_t n4 = (int64_t)d.B2 * d.Nsp / 4;
@@ -389,7 +398,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         TEAM_LAUNCH_CHECK("dtt_kernel");
     }
     const Mat& dS = w.SQ;
-    // ---- wave 6: score gradients -> dQ/dK, fc folded into V, dWfc
+    // ---- wave 7: score gradients -> dQ/dK, fc folded into V, dWfc
     seg(wv.add(d.B2, D, 0.f, dQo), false, dS, true, Ks, d.Nsp);                                                    // dQo = dS Ks
     seg(seg(wv.add(d.Nsp, D, 0.f, dKs), true, dS, true, Qo, d.B2), true, w.dTT, true, Qs, d.Nsp);                  // dKs = dS^T Qo + dTT^T Qs
     seg(seg(wv.add(d.Nsp, D, 0.f, dQs), true, w.dSK, true, Ko, d.B2), false, w.dTT, true, Ks, d.Nsp);              // dQs = dSK^T Ko + dTT Ks
@@ -399,7 +408,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     RUN(wv);
     own_own_bwd_kernel<<<(d.B + 7) / 8, 256, 0, cx.st>>>(d, w.QKVo.f, w.dsown, w.dQKVo.f, w.dQKVo.h);
     TEAM_LAUNCH_CHECK("own_own_bwd_kernel");
-    // ---- wave 7: through the packed q/k/v projection
+    // ---- wave 8: through the packed q/k/v projection
     seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
     seg(wv.add(d.Nsp, D, 1.f, fonly(w.Rfull, D)), false, w.dQKVs, true, w.Wqkv, 3 * D);                            // dS_rows (in Rfull)
     {
@@ -433,7 +442,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         nrm_bwd_kernel<<<blocks, 256, 0, cx.st>>>(nl);
         TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
     }
-    // ---- wave 8: gradients of the newest projections and of the state embedding
+    // ---- wave 9: gradients of the newest projections and of the state embedding
     const Mat dz0 = sub(w.dXo, 0, 0), dz1 = sub(w.dXo, d.B, 0), dzp = sub(w.dZtab, 0, 0), dzs = sub(w.dZtab, d.C, 0);
     seg(seg(wv.add(D, D, 0.f, fonly(gr->w_img, D)), true, dz0, true, w.img, d.B), true, dzp, true, w.protos, d.C);  // dWi = dz0^T x + dzp^T protos
     seg(wv.add(D, D, 0.f, fonly(gr->w_text, D)), true, dz1, true, w.txt, d.B);
@@ -446,7 +455,8 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         for (int i = 0; i < 4; ++i) { fa.part[i] = nl.s[i].partial; fa.nblk[i] = nblk[i]; }
         fa.b_img = gr->b_img; fa.b_text = gr->b_text; fa.b_state = gr->b_state;
         fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
-        finish_bwd_kernel<<<3 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st>>>(fa);
+        fa.dbfc_parts = w.dbfc_parts; fa.dbfc = gr->b_fc;
+        finish_bwd_kernel<<<4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st>>>(fa);
         TEAM_LAUNCH_CHECK("finish_bwd_kernel");
     }
     return TEAM_OK;
@@ -554,7 +564,7 @@ extern "C" int team_head_encode_bwd(const team_head_weights* hw, int mode, int w
     memset(&fa, 0, sizeof(fa));
     fa.part[0] = w.nrm_partials; fa.nblk[0] = nblk;
     fa.b_img = g_b;
-    finish_bwd_kernel<<<1, 512, 0, cx.st>>>(fa);
+    finish_bwd_kernel<<<3, 512, 0, cx.st>>>(fa);
     TEAM_LAUNCH_CHECK("finish_bwd_kernel");
     return TEAM_OK;
 }

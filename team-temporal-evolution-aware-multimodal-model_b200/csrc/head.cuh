@@ -19,14 +19,6 @@ struct HeadDims {
     int nctas;  // CTAs of the per-sample reduction kernels (size of the partial buffers)
 };
 
-// length (floats) of one CTA's partial record written by table_rows_bwd
-__host__ __device__ inline size_t table_partial_len(const HeadDims& d) {
-    return (size_t)2 * d.Rt * D      // R, G
-           + (size_t)d.Rt            // h
-           + (size_t)d.Rt * 10       // dTT state columns
-           + (size_t)10 * D          // dVF of the state-table rows
-           + (size_t)2 * D;          // dgamma, dbeta
-}
 constexpr int OWN_PARTIAL_LEN = 3 * D;   // dgamma, dbeta, dbfc of the own rows
 constexpr int NRM_MAX_PARTIALS = 64;     // per-segment column-sum partials of nrm_bwd (bias gradients)
 
@@ -68,7 +60,7 @@ struct HeadWS {
     Mat Xo;                           // [B2][D]
     float* invo;                      // [B2]
     Mat QKVo;                         // [B2][3D]
-    float* VFo;                       // [B2][D]
+    Mat VFo;                          // [B2][D]
     Mat SQ;                           // [B2][Nsp]  scores of own queries; backward: dA then dS in place
     float* SK;                        // [B2][Nsp]
     Mat Aext;                         // [B2][Nsp]
@@ -90,6 +82,12 @@ struct HeadWS {
     Mat dVFs;                         // [Nsp][D]
     Mat dQKVs;                        // [Nsp][3D]
     Mat dZtab;                        // [Rt][D]
+    Mat GG;                           // [B2][D]   table-row cotangents .* gamma: rows [0,B) g_proto/C, rows [B,2B) g_state
+    Mat A1, A23;                      // [B2][ldA] coefficient matrices of the R/G GEMM (see table_rows_bwd_kernel)
+    float* RG;                        // [ldA][D]  A1^T GG + A23^T VFo
+    float* dVFs_a;                    // [Nsp][D]  Aext^T dYo
+    float* dbfc_parts;                // [8][D]
+    int ldA;                          // 2 * round_up(Rt, 64)
     float* tab_partials;              // [nctas][table_partial_len]
     float* tab_reduced;               // [table_partial_len]
     float* own_partials;              // [nctas][OWN_PARTIAL_LEN]

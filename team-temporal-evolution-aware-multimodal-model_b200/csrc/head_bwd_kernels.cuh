@@ -7,163 +7,230 @@
 
 namespace team {
 
-// offsets (floats) inside one table partial record: [R][G][dvfst][dgam][dbet][h][dtts][pad]
+// ---- per-CTA partial record of table_rows_bwd (floats): [dvfst 10xD][dgam D][dbet D][scal Rt x TQ_NSC]
+// scal row tr (table-query row: tr < C prototype row, tr = C + s the state row of state s):
+//   0..3  R coefficients: sum_b alpha*m1, sum_b beta*cw, sum_b beta, sum_b beta*mean
+//   4..7  the same, each term weighted by cw (G coefficients)
+//   8     h:  sum_b cw * <dY, Ybar>
+//   10..19 dTT state columns, 20..29 sum_b beta*a_s by state (R), 30..39 the same weighted by cw (G)
+constexpr int TQ_NSC = 40;
 struct TabOff {
-    size_t R, G, dvfst, dgam, dbet, h, dtts, len;
+    size_t dvfst, dgam, dbet, scal, len;
 };
 __host__ __device__ inline TabOff tab_offsets(const HeadDims& d) {
     TabOff o;
-    o.R = 0;
-    o.G = o.R + (size_t)d.Rt * D;
-    o.dvfst = o.G + (size_t)d.Rt * D;
-    o.dgam = o.dvfst + (size_t)10 * D;
+    o.dvfst = 0;
+    o.dgam = (size_t)10 * D;
     o.dbet = o.dgam + D;
-    o.h = o.dbet + D;
-    o.dtts = o.h + d.Rt;
-    o.len = (o.dtts + (size_t)d.Rt * 10 + 3) / 4 * 4;
+    o.scal = o.dbet + D;
+    o.len = (o.scal + (size_t)d.Rt * TQ_NSC + 3) / 4 * 4;
     return o;
+}
+__host__ __device__ inline size_t table_bwd_smem_floats(const HeadDims& d) {
+    return (size_t)(5 + 2 + 4 * TQ_WARPS + 1 + 10) * D + (size_t)d.Rt * TQ_NSC + 16;
 }
 
 // ------------------------------------------------------------------ table-query rows, backward
-// dynamic smem: slot[3][TR_WARPS][D] | dvfst[10][D] | lnp[3][D] (gamma,beta,bfc) | hacc[Rt] | dtts[Rt][10]
-__global__ void __launch_bounds__(TR_WARPS * 32)
+// Same work split as table_rows_fwd_kernel (one sample per CTA iteration, warp w owns rows w, w+4, ...).
+// Per row it recomputes the forward (Ybar, LayerNorm), forms dY = LN-backward of the row's cotangent and emits
+//   * the score gradients of the three own keys (dSK, dTT state columns),
+//   * the per-sample sums  sum_j a_i dY, sum_j a_t dY (-> dVFo) and sum_j a_s dY (-> dVF of the state-table row),
+//   * LayerNorm gamma/beta gradients,
+// and, instead of accumulating the batch reductions R_r = sum_b dY_br and G_r = sum_b cw_br dY_br as 512-wide
+// vectors, their COEFFICIENTS:  dY = alpha (gg - m1) - beta (u - mean)  with  u = cw NF_r + S_r + bfc + a_i VI_b +
+// a_t VT_b + a_s VS_b,  so  R = A1^T GG + A23^T VFo  (one two-segment tensor-core GEMM, K = 2B each) plus
+// rank-1 / table-row corrections assembled from the scalar sums in `scal` (expand_table_kernel).
+// A1 / A23 are [2B, ldA]: column tr holds the R coefficient, column ldA/2 + tr the G coefficient.
+// dynamic smem: vec[5][D] (VI, VT, VS, gamma.*g_proto/C, gamma.*g_state) | lnp[2][D] (gamma, bfc) | slots[TQ_WARPS][4][D] | xst[D] |
+//               dvfst[10][D] | scal[Rt][TQ_NSC] | red[16]
+__global__ void __launch_bounds__(TQ_WARPS * 32, 3)
 table_rows_bwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __restrict__ TT,
                       const float* __restrict__ mt, const float* __restrict__ Zt, const float* __restrict__ NFt,
                       const float* __restrict__ VFo, const float* __restrict__ VFs, const float* __restrict__ S,
-                      const float* __restrict__ bfc, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ bfc, const float* __restrict__ gamma,
                       const int64_t* __restrict__ state_ids, const float* __restrict__ g_proto,
                       const float* __restrict__ g_state, float* __restrict__ dSK, __nv_bfloat16* __restrict__ dSKh,
-                      float* __restrict__ dVFo, float* __restrict__ partials) {
+                      float* __restrict__ dVFo, float* __restrict__ GG, __nv_bfloat16* __restrict__ GGh,
+                      float* __restrict__ A1, __nv_bfloat16* __restrict__ A1h, float* __restrict__ A23,
+                      __nv_bfloat16* __restrict__ A23h, int ldA, float* __restrict__ partials) {
     extern __shared__ __align__(16) float tb_smem[];
-    float* slot = tb_smem;                                    // [3][TR_WARPS][D]
-    float* dvfst = slot + 3 * TR_WARPS * D;                   // [10][D]
-    float* lnp = dvfst + 10 * D;                              // [3][D]
-    float* hacc = lnp + 3 * D;                                // [Rt]
-    float* dtts = hacc + d.Rt;                                // [Rt][10]
+    float* vec = tb_smem;                                     // [5][D]
+    float* lnp = vec + 5 * D;                                 // [2][D]
+    float* slots = lnp + 2 * D;                               // [TQ_WARPS][4][D]
+    float* xst = slots + 4 * TQ_WARPS * D;                    // [D]
+    float* dvfst = xst + D;                                   // [10][D]
+    float* scal = dvfst + 10 * D;                             // [Rt][TQ_NSC]
+    float* red = scal + d.Rt * TQ_NSC;                        // [16]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TabOff off = tab_offsets(d);
-    float* rec = partials + (size_t)blockIdx.x * off.len;
-    for (size_t i = tid; i < off.len; i += blockDim.x) rec[i] = 0.f;
+    const int gcol = ldA / 2;
     for (int i = tid; i < 10 * D; i += blockDim.x) dvfst[i] = 0.f;
-    for (int i = tid; i < D; i += blockDim.x) { lnp[i] = gamma[i]; lnp[D + i] = beta[i]; lnp[2 * D + i] = bfc[i]; }
-    for (int i = tid; i < d.Rt * 11; i += blockDim.x) hacc[i] = 0.f;        // hacc + dtts are contiguous
-    __syncthreads();
-    float4 dgam[4], dbet[4];
-    zero_row(dgam); zero_row(dbet);
-    const int rounds = (d.C + 1 + TR_WARPS - 1) / TR_WARPS;
+    for (int i = tid; i < d.Rt * TQ_NSC; i += blockDim.x) scal[i] = 0.f;
+    reinterpret_cast<float4*>(lnp)[tid] = reinterpret_cast<const float4*>(gamma)[tid];
+    reinterpret_cast<float4*>(lnp + D)[tid] = reinterpret_cast<const float4*>(bfc)[tid];
+    float4 dgam = make_float4(0.f, 0.f, 0.f, 0.f), dbet = dgam;         // float4 column tid
+    const int nrows = d.C + 1 > warp ? (d.C + 1 - warp + TQ_WARPS - 1) / TQ_WARPS : 0;
     const float invC = d.C > 1 ? 1.0f / (float)d.C : 1.0f;
+    const __nv_bfloat16 hz = __float2bfloat16_rn(0.f);
     for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
         const int sid = clamp_state(state_ids[b]);
         const int srow = d.M + sid;
-        for (int i = tid; i < d.Nsp; i += blockDim.x) {
-            dSK[(size_t)b * d.Nsp + i] = 0.f;
-            dSK[(size_t)(d.B + b) * d.Nsp + i] = 0.f;
-            if (dSKh != nullptr) {
-                dSKh[(size_t)b * d.Nsp + i] = __float2bfloat16_rn(0.f);
-                dSKh[(size_t)(d.B + b) * d.Nsp + i] = __float2bfloat16_rn(0.f);
+        float4 gp_raw, gs_raw;                                // this thread's float4 column of g_proto/C and g_state
+        __syncthreads();                                      // previous sample's slots / vec fully consumed
+        {   // stage the sample's vectors; GG rows (cotangent .* gamma) for the coefficient GEMM; zero the sparse rows
+            const float4 g4 = reinterpret_cast<const float4*>(lnp)[tid];
+            float4 gp = reinterpret_cast<const float4*>(g_proto + (size_t)b * D)[tid];
+            const float4 gs = reinterpret_cast<const float4*>(g_state + (size_t)b * D)[tid];
+            gp.x *= invC; gp.y *= invC; gp.z *= invC; gp.w *= invC;
+            reinterpret_cast<float4*>(vec)[tid] = reinterpret_cast<const float4*>(VFo + (size_t)b * D)[tid];
+            reinterpret_cast<float4*>(vec + D)[tid] = reinterpret_cast<const float4*>(VFo + (size_t)(d.B + b) * D)[tid];
+            reinterpret_cast<float4*>(vec + 2 * D)[tid] = reinterpret_cast<const float4*>(VFs + (size_t)srow * D)[tid];
+            const float4 ggp = mul4(gp, g4), ggs = mul4(gs, g4);
+            reinterpret_cast<float4*>(vec + 3 * D)[tid] = ggp;
+            reinterpret_cast<float4*>(vec + 4 * D)[tid] = ggs;
+            gp_raw = gp; gs_raw = gs;
+            reinterpret_cast<float4*>(GG + (size_t)b * D)[tid] = ggp;
+            reinterpret_cast<float4*>(GG + (size_t)(d.B + b) * D)[tid] = ggs;
+            if (GGh != nullptr) {
+                reinterpret_cast<uint2*>(GGh + (size_t)b * D)[tid] = pack_bf16x4(ggp);
+                reinterpret_cast<uint2*>(GGh + (size_t)(d.B + b) * D)[tid] = pack_bf16x4(ggs);
+            }
+            const float sp = warp_sum(ggp.x + ggp.y + ggp.z + ggp.w), ss = warp_sum(ggs.x + ggs.y + ggs.z + ggs.w);
+            if (lane == 0) { red[2 * warp] = sp; red[2 * warp + 1] = ss; }
+            dbet.x += gp.x * d.C + gs.x; dbet.y += gp.y * d.C + gs.y; dbet.z += gp.z * d.C + gs.z; dbet.w += gp.w * d.C + gs.w;
+            for (int i = tid; i < d.Nsp; i += blockDim.x) {
+                dSK[(size_t)b * d.Nsp + i] = 0.f;
+                dSK[(size_t)(d.B + b) * d.Nsp + i] = 0.f;
+                if (dSKh != nullptr) { dSKh[(size_t)b * d.Nsp + i] = hz; dSKh[(size_t)(d.B + b) * d.Nsp + i] = hz; }
+            }
+            for (int i = tid; i < ldA; i += blockDim.x) {
+                A1[(size_t)b * ldA + i] = 0.f; A1[(size_t)(d.B + b) * ldA + i] = 0.f;
+                A23[(size_t)b * ldA + i] = 0.f; A23[(size_t)(d.B + b) * ldA + i] = 0.f;
+                if (A1h != nullptr) {
+                    A1h[(size_t)b * ldA + i] = hz; A1h[(size_t)(d.B + b) * ldA + i] = hz;
+                    A23h[(size_t)b * ldA + i] = hz; A23h[(size_t)(d.B + b) * ldA + i] = hz;
+                }
             }
         }
         __syncthreads();
-        float2 acc_i = make_float2(0.f, 0.f), acc_t = acc_i, acc_s = acc_i;   // columns 2*tid, 2*tid+1
-        for (int rd = 0; rd < rounds; ++rd) {
-            const int j = rd * TR_WARPS + warp;
-            if (j <= d.C) {
-                TableRowCtx cx;
-                float4 ybar[4], u[4], t[4], xh[4], du[4];
-                table_row_forward(d, b, j, srow, lane, SK, TT, mt, Zt, NFt, VFo, VFs, cx, ybar);
-                ld_row(S + (size_t)cx.r * D, lane, u);
-                add_row(u, ybar);
-                ld_row(lnp + 2 * D, lane, t); add_row(u, t);
-                float rstd;
-                {   // LayerNorm forward (normalised values only)
-                    const float mean = warp_sum(sum_part(u)) * (1.0f / D);
+        float m1p = 0.f, m1s = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) { xh[i].x = u[i].x - mean; xh[i].y = u[i].y - mean; xh[i].z = u[i].z - mean; xh[i].w = u[i].w - mean; }
-                    const float var = warp_sum(dot_part(xh, xh)) * (1.0f / D);
-                    rstd = 1.0f / sqrtf(var + LN_EPS);
-                    scale_row(xh, rstd);
-                }
-                // cotangent of this row
-                ld_row((j < d.C ? g_proto : g_state) + (size_t)b * D, lane, u);
-                if (j < d.C) scale_row(u, invC);
+        for (int w = 0; w < TQ_WARPS; ++w) { m1p += red[2 * w]; m1s += red[2 * w + 1]; }
+        m1p *= (1.0f / D); m1s *= (1.0f / D);
+        float4 acc_i[4], acc_t[4], acc_s[4], xs[4];
+        zero_row(acc_i); zero_row(acc_t); zero_row(acc_s); zero_row(xs);
+        for (int k0 = 0; k0 < nrows; k0 += 32) {
+            TableRowW mine;
+            mine.c_w = mine.a_i = mine.a_t = mine.a_s = 0.f; mine.r = 0;
+            if (k0 + lane < nrows) mine = table_row_weights(d, b, warp + (k0 + lane) * TQ_WARPS, srow, SK, TT, mt, Zt);
+            const int kn = min(32, nrows - k0);
+            for (int k = 0; k < kn; ++k) {
+                const TableRowW rw = shfl_row_weights(mine, k);
+                const int j = warp + (k0 + k) * TQ_WARPS;
+                const bool is_proto = j < d.C;
+                float4 ybar[4], xh[4], t[4];
+                ld_row(NFt + (size_t)rw.r * D, lane, ybar); scale_row(ybar, rw.c_w);
+                ld_row(vec, lane, t); axpy_row(ybar, rw.a_i, t);
+                ld_row(vec + D, lane, t); axpy_row(ybar, rw.a_t, t);
+                ld_row(vec + 2 * D, lane, t); axpy_row(ybar, rw.a_s, t);
+                ld_row(S + (size_t)rw.r * D, lane, xh); add_row(xh, ybar);
+                ld_row(lnp + D, lane, t); add_row(xh, t);
+                const float mean = warp_sum(sum_part(xh)) * (1.0f / D);
+                shift_row(xh, -mean);
+                const float var = warp_sum(dot_part(xh, xh)) * (1.0f / D);
+                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                scale_row(xh, rstd);
+                // gg = cotangent .* gamma (staged) ; dY = rstd (gg - m1 - xh m2)
+                float4 gg[4];
+                ld_row(vec + (is_proto ? 3 : 4) * D, lane, gg);
+                const float m1 = is_proto ? m1p : m1s;
+                const float m2 = warp_sum(dot_part(gg, xh)) * (1.0f / D);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    dgam[i].x = fmaf(u[i].x, xh[i].x, dgam[i].x); dgam[i].y = fmaf(u[i].y, xh[i].y, dgam[i].y);
-                    dgam[i].z = fmaf(u[i].z, xh[i].z, dgam[i].z); dgam[i].w = fmaf(u[i].w, xh[i].w, dgam[i].w);
+                for (int i = 0; i < 4; ++i) gg[i] = mul4s(rstd, fma4s(-m2, xh[i], add4s(-m1, gg[i])));
+                float p_yy = dot_part(gg, ybar);
+                ld_row(vec, lane, t);
+                float p_i = dot_part(gg, t);
+                axpy_row(acc_i, rw.a_i, gg);
+                ld_row(vec + D, lane, t);
+                float p_t = dot_part(gg, t);
+                axpy_row(acc_t, rw.a_t, gg);
+                ld_row(vec + 2 * D, lane, t);
+                float p_s = dot_part(gg, t);
+                axpy_row(acc_s, rw.a_s, gg);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {            // four reductions interleaved
+                    p_yy += __shfl_xor_sync(0xffffffffu, p_yy, o); p_i += __shfl_xor_sync(0xffffffffu, p_i, o);
+                    p_t += __shfl_xor_sync(0xffffffffu, p_t, o); p_s += __shfl_xor_sync(0xffffffffu, p_s, o);
                 }
-                add_row(dbet, u);
-                ld_row(lnp, lane, t);
-                ln_backward(u, xh, rstd, t, du);
-                const int tr = j < d.C ? j : d.C + sid;
-                // residual and shared-partial gradients (rows owned by this warp -> no races)
-                ld_row(rec + off.R + (size_t)tr * D, lane, t); add_row(t, du); st_row(rec + off.R + (size_t)tr * D, lane, t);
-                ld_row(rec + off.G + (size_t)tr * D, lane, t); axpy_row(t, cx.c_w, du); st_row(rec + off.G + (size_t)tr * D, lane, t);
-                const float dyy = warp_sum(dot_part(du, ybar));
-                ld_row(VFo + (size_t)b * D, lane, t);
-                const float d_i = warp_sum(dot_part(du, t));
-                ld_row(VFo + (size_t)(d.B + b) * D, lane, t);
-                const float d_t = warp_sum(dot_part(du, t));
-                ld_row(VFs + (size_t)srow * D, lane, t);
-                const float d_s = warp_sum(dot_part(du, t));
+                if (is_proto) add_row(xs, xh); else st_row(xst, lane, xh);
                 if (lane == 0) {
-                    hacc[tr] += cx.c_w * dyy;
-                    const float v_i = cx.a_i * (d_i - dyy) * INV_TAU, v_t = cx.a_t * (d_t - dyy) * INV_TAU;
-                    dSK[(size_t)b * d.Nsp + cx.r] = v_i;
-                    dSK[(size_t)(d.B + b) * d.Nsp + cx.r] = v_t;
+                    const int tr = is_proto ? j : d.C + sid;
+                    const float alpha = rstd, beta = rstd * rstd * m2, cw = rw.c_w;
+                    const float v_i = rw.a_i * (p_i - p_yy) * INV_TAU, v_t = rw.a_t * (p_t - p_yy) * INV_TAU;
+                    dSK[(size_t)b * d.Nsp + rw.r] = v_i;
+                    dSK[(size_t)(d.B + b) * d.Nsp + rw.r] = v_t;
                     if (dSKh != nullptr) {
-                        dSKh[(size_t)b * d.Nsp + cx.r] = __float2bfloat16_rn(v_i);
-                        dSKh[(size_t)(d.B + b) * d.Nsp + cx.r] = __float2bfloat16_rn(v_t);
+                        dSKh[(size_t)b * d.Nsp + rw.r] = __float2bfloat16_rn(v_i);
+                        dSKh[(size_t)(d.B + b) * d.Nsp + rw.r] = __float2bfloat16_rn(v_t);
                     }
-                    dtts[tr * 10 + sid] += cx.a_s * (d_s - dyy) * INV_TAU;
+                    const size_t ra = (size_t)(is_proto ? b : d.B + b) * ldA;        // GG row this query's cotangent lives in
+                    const size_t r0 = (size_t)b * ldA, r1 = (size_t)(d.B + b) * ldA;
+                    const float c23i = -beta * rw.a_i, c23t = -beta * rw.a_t;
+                    A1[ra + tr] = alpha; A1[ra + gcol + tr] = cw * alpha;
+                    A23[r0 + tr] = c23i; A23[r0 + gcol + tr] = cw * c23i;
+                    A23[r1 + tr] = c23t; A23[r1 + gcol + tr] = cw * c23t;
+                    if (A1h != nullptr) {
+                        A1h[ra + tr] = __float2bfloat16_rn(alpha); A1h[ra + gcol + tr] = __float2bfloat16_rn(cw * alpha);
+                        A23h[r0 + tr] = __float2bfloat16_rn(c23i); A23h[r0 + gcol + tr] = __float2bfloat16_rn(cw * c23i);
+                        A23h[r1 + tr] = __float2bfloat16_rn(c23t); A23h[r1 + gcol + tr] = __float2bfloat16_rn(cw * c23t);
+                    }
+                    float* sc = scal + tr * TQ_NSC;
+                    const float e0 = alpha * m1, e1 = beta * cw, e2 = beta, e3 = beta * mean, e4 = beta * rw.a_s;
+                    sc[0] += e0; sc[1] += e1; sc[2] += e2; sc[3] += e3;
+                    sc[4] += cw * e0; sc[5] += cw * e1; sc[6] += cw * e2; sc[7] += cw * e3;
+                    sc[8] += cw * p_yy;
+                    sc[10 + sid] += rw.a_s * (p_s - p_yy) * INV_TAU;
+                    sc[20 + sid] += e4;
+                    sc[30 + sid] += cw * e4;
                 }
-                float4 w4[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) w4[i] = make_float4(cx.a_i * du[i].x, cx.a_i * du[i].y, cx.a_i * du[i].z, cx.a_i * du[i].w);
-                st_row(slot + (0 * TR_WARPS + warp) * D, lane, w4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) w4[i] = make_float4(cx.a_t * du[i].x, cx.a_t * du[i].y, cx.a_t * du[i].z, cx.a_t * du[i].w);
-                st_row(slot + (1 * TR_WARPS + warp) * D, lane, w4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) w4[i] = make_float4(cx.a_s * du[i].x, cx.a_s * du[i].y, cx.a_s * du[i].z, cx.a_s * du[i].w);
-                st_row(slot + (2 * TR_WARPS + warp) * D, lane, w4);
             }
-            __syncthreads();
-            const int nvalid = min(TR_WARPS, d.C + 1 - rd * TR_WARPS);
-            for (int w = 0; w < nvalid; ++w) {
-                const float2 a = reinterpret_cast<const float2*>(slot + (0 * TR_WARPS + w) * D)[tid];
-                const float2 bb = reinterpret_cast<const float2*>(slot + (1 * TR_WARPS + w) * D)[tid];
-                const float2 c = reinterpret_cast<const float2*>(slot + (2 * TR_WARPS + w) * D)[tid];
-                acc_i.x += a.x; acc_i.y += a.y; acc_t.x += bb.x; acc_t.y += bb.y; acc_s.x += c.x; acc_s.y += c.y;
+        }
+        st_row(slots + (warp * 4 + 0) * D, lane, acc_i);
+        st_row(slots + (warp * 4 + 1) * D, lane, acc_t);
+        st_row(slots + (warp * 4 + 2) * D, lane, acc_s);
+        st_row(slots + (warp * 4 + 3) * D, lane, xs);
+        __syncthreads();
+        {
+            float4 f[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                f[q] = reinterpret_cast<const float4*>(slots + q * D)[tid];
+#pragma unroll
+                for (int w = 1; w < TQ_WARPS; ++w) {
+                    const float4 a = reinterpret_cast<const float4*>(slots + (w * 4 + q) * D)[tid];
+                    f[q].x += a.x; f[q].y += a.y; f[q].z += a.z; f[q].w += a.w;
+                }
             }
-            __syncthreads();
+            reinterpret_cast<float4*>(dVFo + (size_t)b * D)[tid] = f[0];
+            reinterpret_cast<float4*>(dVFo + (size_t)(d.B + b) * D)[tid] = f[1];
+            float4 o = reinterpret_cast<float4*>(dvfst + sid * D)[tid];
+            o.x += f[2].x; o.y += f[2].y; o.z += f[2].z; o.w += f[2].w;
+            reinterpret_cast<float4*>(dvfst + sid * D)[tid] = o;
+            // dgamma += (g_proto/C) .* sum_{j<C} xhat_j + g_state .* xhat_state
+            const float4 xq = reinterpret_cast<const float4*>(xst)[tid];
+            dgam = fma4(gp_raw, f[3], fma4(gs_raw, xq, dgam));
         }
-        reinterpret_cast<float2*>(dVFo + (size_t)b * D)[tid] = acc_i;
-        reinterpret_cast<float2*>(dVFo + (size_t)(d.B + b) * D)[tid] = acc_t;
-        float2 o = reinterpret_cast<float2*>(dvfst + sid * D)[tid];
-        o.x += acc_s.x; o.y += acc_s.y;
-        reinterpret_cast<float2*>(dvfst + sid * D)[tid] = o;
     }
-    // fold the per-warp LayerNorm gradients in warp order, then publish the record
     __syncthreads();
-    st_row(slot + (0 * TR_WARPS + warp) * D, lane, dgam);
-    st_row(slot + (1 * TR_WARPS + warp) * D, lane, dbet);
-    __syncthreads();
-    {
-        float2 sg = make_float2(0.f, 0.f), sb = sg;
-        for (int w = 0; w < TR_WARPS; ++w) {
-            const float2 a = reinterpret_cast<const float2*>(slot + (0 * TR_WARPS + w) * D)[tid];
-            const float2 bb = reinterpret_cast<const float2*>(slot + (1 * TR_WARPS + w) * D)[tid];
-            sg.x += a.x; sg.y += a.y; sb.x += bb.x; sb.y += bb.y;
-        }
-        reinterpret_cast<float2*>(rec + off.dgam)[tid] = sg;
-        reinterpret_cast<float2*>(rec + off.dbet)[tid] = sb;
-    }
+    float* rec = partials + (size_t)blockIdx.x * off.len;
     for (int i = tid; i < 10 * D; i += blockDim.x) rec[off.dvfst + i] = dvfst[i];
-    for (int i = tid; i < d.Rt; i += blockDim.x) rec[off.h + i] = hacc[i];
-    for (int i = tid; i < d.Rt * 10; i += blockDim.x) rec[off.dtts + i] = dtts[i];
+    reinterpret_cast<float4*>(rec + off.dgam)[tid] = dgam;
+    reinterpret_cast<float4*>(rec + off.dbet)[tid] = dbet;
+    for (int i = tid; i < d.Rt * TQ_NSC; i += blockDim.x) rec[off.scal + i] = scal[i];
+    for (size_t i = off.scal + (size_t)d.Rt * TQ_NSC + tid; i < off.len; i += blockDim.x) rec[i] = 0.f;
 }
 
-// out[i] = sum_p partials[p][i] in fixed order (4 interleaved lanes of p, folded in order); up to two
+// out[i] = sum_p partials[p][i] in fixed order (RP_GROUPS interleaved lanes of p, folded in order); up to two
 // independent jobs per launch (blocks [0, blocks0) -> job 0, the rest -> job 1).
 struct ReduceJob {
     const float* partials;
@@ -175,17 +242,28 @@ struct ReduceJobs {
     ReduceJob j[2];
     int blocks0;
 };
-__global__ void __launch_bounds__(256)
+constexpr int RP_COLS = 32;       // float4 columns per block
+constexpr int RP_GROUPS = 32;     // partial-interleaved groups per block
+__global__ void __launch_bounds__(RP_COLS * RP_GROUPS)
 reduce_partials_kernel(const __grid_constant__ ReduceJobs rj) {
-    __shared__ float4 fold[4][64];
+    __shared__ float4 fold[RP_GROUPS][RP_COLS];
     const bool second = (int)blockIdx.x >= rj.blocks0;
     const ReduceJob& job = rj.j[second ? 1 : 0];
-    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
-    const size_t i = (size_t)((int)blockIdx.x - (second ? rj.blocks0 : 0)) * 64 + c;
+    const int c = threadIdx.x % RP_COLS, g = threadIdx.x / RP_COLS;
+    const size_t i = (size_t)((int)blockIdx.x - (second ? rj.blocks0 : 0)) * RP_COLS + c;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < job.len4) {
-        for (int p = g; p < job.n_partials; p += 4) {
-            const float4 a = reinterpret_cast<const float4*>(job.partials)[(size_t)p * job.len4 + i];
+        const float4* base = reinterpret_cast<const float4*>(job.partials) + i;
+        int p = g;
+        for (; p + 3 * RP_GROUPS < job.n_partials; p += 4 * RP_GROUPS) {       // 4 loads in flight
+            float4 a[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = base[(size_t)(p + q * RP_GROUPS) * job.len4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { s.x += a[q].x; s.y += a[q].y; s.z += a[q].z; s.w += a[q].w; }
+        }
+        for (; p < job.n_partials; p += RP_GROUPS) {
+            const float4 a = base[(size_t)p * job.len4];
             s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
         }
     }
@@ -193,45 +271,84 @@ reduce_partials_kernel(const __grid_constant__ ReduceJobs rj) {
     __syncthreads();
     if (g == 0 && i < job.len4) {
         float4 r = fold[0][c];
-#pragma unroll
-        for (int q = 1; q < 4; ++q) { r.x += fold[q][c].x; r.y += fold[q][c].y; r.z += fold[q][c].z; r.w += fold[q][c].w; }
+        for (int q = 1; q < RP_GROUPS; ++q) { r.x += fold[q][c].x; r.y += fold[q][c].y; r.z += fold[q][c].z; r.w += fold[q][c].w; }
         reinterpret_cast<float4*>(job.out)[i] = r;
     }
 }
 
-// compact table-row gradients -> step-row indexed buffers (zeros for prompt / pad rows); block Nsp folds the
-// LayerNorm / fc-bias gradients: dgamma/dbeta = table part + own part, dbfc = own part + sum over table rows of R
+constexpr int EXP_SUM_BLOCKS = 8;
+__device__ __forceinline__ void combine_table_row(const HeadDims& d, const TabOff& off, const float* __restrict__ red,
+        const float* __restrict__ RG, int gcol, const float* __restrict__ NFt, const float* __restrict__ S,
+        const float* __restrict__ VFs, const float4 bf, int tr, int r, int t, float4& Rv, float4& Gv) {
+    const float* sc = red + off.scal + (size_t)tr * TQ_NSC;
+    const float4 nf = reinterpret_cast<const float4*>(NFt + (size_t)r * D)[t];
+    float4 sb = reinterpret_cast<const float4*>(S + (size_t)r * D)[t];
+    sb.x += bf.x; sb.y += bf.y; sb.z += bf.z; sb.w += bf.w;
+    Rv = reinterpret_cast<const float4*>(RG + (size_t)tr * D)[t];
+    Gv = reinterpret_cast<const float4*>(RG + (size_t)(gcol + tr) * D)[t];
+    const float r0 = sc[3] - sc[0], g0 = sc[7] - sc[4];
+    Rv.x += r0 - sc[1] * nf.x - sc[2] * sb.x; Rv.y += r0 - sc[1] * nf.y - sc[2] * sb.y;
+    Rv.z += r0 - sc[1] * nf.z - sc[2] * sb.z; Rv.w += r0 - sc[1] * nf.w - sc[2] * sb.w;
+    Gv.x += g0 - sc[5] * nf.x - sc[6] * sb.x; Gv.y += g0 - sc[5] * nf.y - sc[6] * sb.y;
+    Gv.z += g0 - sc[5] * nf.z - sc[6] * sb.z; Gv.w += g0 - sc[5] * nf.w - sc[6] * sb.w;
+    for (int s = 0; s < 10; ++s) {
+        const float wr = sc[20 + s], wg = sc[30 + s];
+        if (wr == 0.f && wg == 0.f) continue;
+        const float4 v = reinterpret_cast<const float4*>(VFs + (size_t)(d.M + s) * D)[t];
+        Rv.x -= wr * v.x; Rv.y -= wr * v.y; Rv.z -= wr * v.z; Rv.w -= wr * v.w;
+        Gv.x -= wg * v.x; Gv.y -= wg * v.y; Gv.z -= wg * v.z; Gv.w -= wg * v.w;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 expand_table_kernel(HeadDims d, const float* __restrict__ red, const float* __restrict__ own_red,
+                    const float* __restrict__ RG, int gcol, const float* __restrict__ NFt, const float* __restrict__ S,
+                    const float* __restrict__ VFs, const float* __restrict__ bfc,
                     float* __restrict__ Rfull, float* __restrict__ Gfull, __nv_bfloat16* __restrict__ Gfullh,
                     float* __restrict__ hfull, float* __restrict__ dTT, float* __restrict__ dVFs,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbfc) {
+                    const float* __restrict__ dVFs_a, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float* __restrict__ dbfc_parts) {
     const TabOff off = tab_offsets(d);
     const int r = blockIdx.x, t = threadIdx.x;
-    if (r == d.Nsp) {
-        const float4 a = reinterpret_cast<const float4*>(red + off.dgam)[t], b = reinterpret_cast<const float4*>(own_red)[t];
-        reinterpret_cast<float4*>(dgamma)[t] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-        const float4 c = reinterpret_cast<const float4*>(red + off.dbet)[t], e = reinterpret_cast<const float4*>(own_red + D)[t];
-        reinterpret_cast<float4*>(dbeta)[t] = make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w);
-        float4 s = reinterpret_cast<const float4*>(own_red + 2 * D)[t];
-        for (int tr = 0; tr < d.Rt; ++tr) {
-            const float4 q = reinterpret_cast<const float4*>(red + off.R + (size_t)tr * D)[t];
-            s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    const float4 bf = reinterpret_cast<const float4*>(bfc)[t];
+    if (r >= d.Nsp) {
+        // blocks Nsp .. Nsp+EXP_SUM_BLOCKS-1: fixed-order partial sums of R over the table rows (-> dbfc, finish_bwd_kernel);
+        // the first of them also folds dgamma / dbeta
+        const int q = r - d.Nsp;
+        if (q == 0) {
+            const float4 a = reinterpret_cast<const float4*>(red + off.dgam)[t], b = reinterpret_cast<const float4*>(own_red)[t];
+            reinterpret_cast<float4*>(dgamma)[t] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+            const float4 c = reinterpret_cast<const float4*>(red + off.dbet)[t], e = reinterpret_cast<const float4*>(own_red + D)[t];
+            reinterpret_cast<float4*>(dbeta)[t] = make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w);
         }
-        reinterpret_cast<float4*>(dbfc)[t] = s;
+        float4 s = q == 0 ? reinterpret_cast<const float4*>(own_red + 2 * D)[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int tr = q; tr < d.Rt; tr += EXP_SUM_BLOCKS) {
+            float4 Rv, Gv;
+            combine_table_row(d, off, red, RG, gcol, NFt, S, VFs, bf, tr, tr < d.C ? tr : d.M + (tr - d.C), t, Rv, Gv);
+            s.x += Rv.x; s.y += Rv.y; s.z += Rv.z; s.w += Rv.w;
+        }
+        reinterpret_cast<float4*>(dbfc_parts + (size_t)q * D)[t] = s;
         return;
     }
     const bool is_state = r >= d.M && r < d.Ns;
     const int tr = r < d.C ? r : (is_state ? d.C + (r - d.M) : -1);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    reinterpret_cast<float4*>(Rfull + (size_t)r * D)[t] = tr >= 0 ? reinterpret_cast<const float4*>(red + off.R + (size_t)tr * D)[t] : z;
-    const float4 gv = tr >= 0 ? reinterpret_cast<const float4*>(red + off.G + (size_t)tr * D)[t] : z;
-    reinterpret_cast<float4*>(Gfull + (size_t)r * D)[t] = gv;
-    if (Gfullh != nullptr) reinterpret_cast<uint2*>(Gfullh + (size_t)r * D)[t] = pack_bf16x4(gv);
-    reinterpret_cast<float4*>(dVFs + (size_t)r * D)[t] = is_state ? reinterpret_cast<const float4*>(red + off.dvfst + (size_t)(r - d.M) * D)[t] : z;
-    if (t == 0) hfull[r] = tr >= 0 ? red[off.h + tr] : 0.f;
+    float4 Rv = z, Gv = z;
+    if (tr >= 0) combine_table_row(d, off, red, RG, gcol, NFt, S, VFs, bf, tr, r, t, Rv, Gv);
+    reinterpret_cast<float4*>(Rfull + (size_t)r * D)[t] = Rv;
+    reinterpret_cast<float4*>(Gfull + (size_t)r * D)[t] = Gv;
+    if (Gfullh != nullptr) reinterpret_cast<uint2*>(Gfullh + (size_t)r * D)[t] = pack_bf16x4(Gv);
+    {   // dVFs = Aext^T dYo (wave 5) + the state-table part of the table rows; wave 6 adds Pt^T G
+        float4 v = reinterpret_cast<const float4*>(dVFs_a + (size_t)r * D)[t];
+        if (is_state) {
+            const float4 a = reinterpret_cast<const float4*>(red + off.dvfst + (size_t)(r - d.M) * D)[t];
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+        reinterpret_cast<float4*>(dVFs + (size_t)r * D)[t] = v;
+    }
+    if (t == 0) hfull[r] = tr >= 0 ? red[off.scal + (size_t)tr * TQ_NSC + 8] : 0.f;
     for (int j = t; j < d.Nsp; j += blockDim.x)
-        dTT[(size_t)r * d.Nsp + j] = (tr >= 0 && j >= d.M && j < d.Ns) ? red[off.dtts + tr * 10 + (j - d.M)] : 0.f;
+        dTT[(size_t)r * d.Nsp + j] = (tr >= 0 && j >= d.M && j < d.Ns) ? red[off.scal + (size_t)tr * TQ_NSC + 10 + (j - d.M)] : 0.f;
 }
 
 // ------------------------------------------------------------------ own rows: LayerNorm + softmax-output backward
@@ -424,7 +541,8 @@ nrm_bwd_kernel(const __grid_constant__ NrmList nl) {
 // last launch of the backward: projection-bias gradients from the nrm_bwd partials (fixed order) and the
 // prompt-row gradients (rows [C, C+P) of the step-row gradient).
 //   blocks 0..2: b_img = sum(part[0]) + sum(part[2]); b_text = sum(part[1]); b_state = sum(part[3])
-//   blocks 3.. : one prompt row each
+//   block 3    : dbfc = sum of the expand_table partial sums
+//   blocks 4.. : four prompt rows each
 struct FinishArgs {
     const float* part[4];
     int nblk[4];
@@ -432,11 +550,24 @@ struct FinishArgs {
     const float* Rfull;
     float* prompts;            // may be null
     int C, P;
+    const float* dbfc_parts;   // [EXP_SUM_BLOCKS][D] or null
+    float* dbfc;
 };
 __global__ void __launch_bounds__(512)
 finish_bwd_kernel(const __grid_constant__ FinishArgs fa) {
     __shared__ float4 fold[4][128];
     const int t = threadIdx.x & 127, g = threadIdx.x >> 7;     // 4 groups of 128 threads, each a quarter of the partials
+    if (blockIdx.x == 3) {
+        if (fa.dbfc_parts != nullptr && g == 0) {
+            float4 r = reinterpret_cast<const float4*>(fa.dbfc_parts)[t];
+            for (int q = 1; q < EXP_SUM_BLOCKS; ++q) {
+                const float4 a = reinterpret_cast<const float4*>(fa.dbfc_parts + (size_t)q * D)[t];
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+            }
+            reinterpret_cast<float4*>(fa.dbfc)[t] = r;
+        }
+        return;
+    }
     if (blockIdx.x < 3) {
         const int k = blockIdx.x;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -463,7 +594,7 @@ finish_bwd_kernel(const __grid_constant__ FinishArgs fa) {
         return;
     }
     // prompt rows: 4 rows per block
-    const int r = (blockIdx.x - 3) * 4 + g;
+    const int r = (blockIdx.x - 4) * 4 + g;
     if (fa.prompts != nullptr && r < fa.P)
         reinterpret_cast<float4*>(fa.prompts + (size_t)r * D)[t] = reinterpret_cast<const float4*>(fa.Rfull + (size_t)(fa.C + r) * D)[t];
 }

@@ -235,19 +235,25 @@ ln_own_fwd_kernel(HeadDims d, float* __restrict__ Ybo, const float* __restrict__
 }
 
 // ------------------------------------------------------------------ table-query rows (prototype + state outputs)
-// One warp evaluates one table-query row j of sample b: j < C -> prototype row j, j == C -> the state row.
-struct TableRowCtx {
-    float c_w;        // c / den   (weight of the shared partial)
-    float a_i, a_t, a_s;   // attention on own image / text / state keys
-    int r;            // step-row id of this query
+// The C prototype queries and the state query of one sample share the per-step softmax partial (m_r, Z_r, NF_r)
+// over the M shared keys; only the three own keys (image, text, state) are per sample.
+// One CTA (TQ_WARPS warps) works on one sample at a time; warp w owns the rows j = w, w + TQ_WARPS, ...
+// (j < C: prototype row j, j == C: the state row).  The softmax weights of a warp's rows are computed
+// lane-parallel (lane k -> k-th row of the warp) and broadcast with shuffles inside the row loop.
+constexpr int TQ_WARPS = 4;
+
+struct TableRowW {
+    float c_w;             // c / den   (weight of the shared partial NF_r)
+    float a_i, a_t, a_s;   // attention on the own image / text / state keys
+    int r;                 // step-row id of this query
 };
 
-__device__ __forceinline__ void table_row_forward(const HeadDims& d, int b, int j, int srow, int lane,
+__device__ __forceinline__ TableRowW table_row_weights(const HeadDims& d, int b, int j, int srow,
         const float* __restrict__ SK, const float* __restrict__ TT, const float* __restrict__ mt,
-        const float* __restrict__ Zt, const float* __restrict__ NFt, const float* __restrict__ VFo,
-        const float* __restrict__ VFs, TableRowCtx& cx, float4 (&ybar)[4]) {
+        const float* __restrict__ Zt) {
+    TableRowW o;
     const int r = j < d.C ? j : srow;
-    cx.r = r;
+    o.r = r;
     const float s_i = SK[(size_t)b * d.Nsp + r] * INV_TAU;
     const float s_t = SK[(size_t)(d.B + b) * d.Nsp + r] * INV_TAU;
     const float s_s = TT[(size_t)r * d.Nsp + srow] * INV_TAU;
@@ -255,53 +261,84 @@ __device__ __forceinline__ void table_row_forward(const HeadDims& d, int b, int 
     const float m2 = fmaxf(fmaxf(mr, s_i), fmaxf(s_t, s_s));
     const float c = expf(mr - m2), p_i = expf(s_i - m2), p_t = expf(s_t - m2), p_s = expf(s_s - m2);
     const float w = 1.0f / (c * Zt[r] + p_i + p_t + p_s);
-    cx.c_w = c * w; cx.a_i = p_i * w; cx.a_t = p_t * w; cx.a_s = p_s * w;
-    float4 t[4];
-    ld_row(NFt + (size_t)r * D, lane, ybar); scale_row(ybar, cx.c_w);
-    ld_row(VFo + (size_t)b * D, lane, t); axpy_row(ybar, cx.a_i, t);
-    ld_row(VFo + (size_t)(d.B + b) * D, lane, t); axpy_row(ybar, cx.a_t, t);
-    ld_row(VFs + (size_t)srow * D, lane, t); axpy_row(ybar, cx.a_s, t);
+    o.c_w = c * w; o.a_i = p_i * w; o.a_t = p_t * w; o.a_s = p_s * w;
+    return o;
+}
+__device__ __forceinline__ TableRowW shfl_row_weights(const TableRowW& v, int src) {
+    TableRowW o;
+    o.c_w = __shfl_sync(0xffffffffu, v.c_w, src); o.a_i = __shfl_sync(0xffffffffu, v.a_i, src);
+    o.a_t = __shfl_sync(0xffffffffu, v.a_t, src); o.a_s = __shfl_sync(0xffffffffu, v.a_s, src);
+    o.r = __shfl_sync(0xffffffffu, v.r, src);
+    return o;
 }
 
-__global__ void __launch_bounds__(TR_WARPS * 32)
+// out_proto[b] = gamma .* (1/C) sum_{j<C} xhat_bj + beta  (LayerNorm is affine in xhat, so gamma/beta are applied once);
+// out_state[b] = gamma .* xhat_bC + beta.
+__global__ void __launch_bounds__(TQ_WARPS * 32)
 table_rows_fwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __restrict__ TT,
                       const float* __restrict__ mt, const float* __restrict__ Zt, const float* __restrict__ NFt,
                       const float* __restrict__ VFo, const float* __restrict__ VFs, const float* __restrict__ S,
                       const float* __restrict__ bfc, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const int64_t* __restrict__ state_ids, float* __restrict__ out_proto,
                       float* __restrict__ out_state) {
-    __shared__ __align__(16) float slot[TR_WARPS][D];          // 16 KB
+    __shared__ __align__(16) float slot[TQ_WARPS][D];          // 8 KB
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 g[4], be[4], bf[4];
-    ld_row(gamma, lane, g); ld_row(beta, lane, be); ld_row(bfc, lane, bf);
-    const int rounds = (d.C + 1 + TR_WARPS - 1) / TR_WARPS;
+    float4 bf[4];
+    ld_row(bfc, lane, bf);
+    const int nrows = d.C + 1 > warp ? (d.C + 1 - warp + TQ_WARPS - 1) / TQ_WARPS : 0;     // rows of this warp
     const float invC = 1.0f / (float)d.C;
     for (int b = blockIdx.x; b < d.B; b += gridDim.x) {
         const int srow = d.M + clamp_state(state_ids[b]);
-        float2 acc = make_float2(0.f, 0.f);                       // columns 2t, 2t+1 of the prototype mean
-        for (int rd = 0; rd < rounds; ++rd) {
-            const int j = rd * TR_WARPS + warp;
-            if (j <= d.C) {
-                TableRowCtx cx;
-                float4 u[4], t[4], xh[4], o[4];
-                table_row_forward(d, b, j, srow, lane, SK, TT, mt, Zt, NFt, VFo, VFs, cx, u);
-                add_row(u, bf);
-                ld_row(S + (size_t)cx.r * D, lane, t); add_row(u, t);
-                float rstd;
-                ln_forward(u, g, be, xh, rstd, o);
-                if (j < d.C) st_row(slot[warp], lane, o);
-                else st_row(out_state + (size_t)b * D, lane, o);
+        float4 vi[4], vt[4], vs[4], acc[4];
+        ld_row(VFo + (size_t)b * D, lane, vi);
+        ld_row(VFo + (size_t)(d.B + b) * D, lane, vt);
+        ld_row(VFs + (size_t)srow * D, lane, vs);
+        zero_row(acc);
+        for (int k0 = 0; k0 < nrows; k0 += 32) {
+            TableRowW mine;
+            mine.c_w = mine.a_i = mine.a_t = mine.a_s = 0.f; mine.r = 0;
+            if (k0 + lane < nrows) mine = table_row_weights(d, b, warp + (k0 + lane) * TQ_WARPS, srow, SK, TT, mt, Zt);
+            const int kn = min(32, nrows - k0);
+            for (int k = 0; k < kn; ++k) {
+                const TableRowW rw = shfl_row_weights(mine, k);
+                const int j = warp + (k0 + k) * TQ_WARPS;
+                float4 u[4], t[4];
+                ld_row(NFt + (size_t)rw.r * D, lane, u);
+                ld_row(S + (size_t)rw.r * D, lane, t);
+                scale_row(u, rw.c_w);
+                axpy_row(u, rw.a_i, vi); axpy_row(u, rw.a_t, vt); axpy_row(u, rw.a_s, vs);
+                add_row(u, bf); add_row(u, t);
+                const float mean = warp_sum(sum_part(u)) * (1.0f / D);
+                shift_row(u, -mean);
+                const float var = warp_sum(dot_part(u, u)) * (1.0f / D);
+                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                if (j < d.C) {
+                    axpy_row(acc, rstd, u);
+                } else {
+                    float4 g[4], be[4];
+                    ld_row(gamma, lane, g); ld_row(beta, lane, be);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) u[i] = fma4(mul4s(rstd, u[i]), g[i], be[i]);
+                    st_row(out_state + (size_t)b * D, lane, u);
+                }
             }
-            __syncthreads();
-            const int nvalid = min(TR_WARPS, d.C - rd * TR_WARPS);
-            for (int w = 0; w < nvalid; ++w) {
-                const float2 a = reinterpret_cast<const float2*>(slot[w])[threadIdx.x];
-                acc.x += a.x; acc.y += a.y;
-            }
-            __syncthreads();
         }
-        if (d.C > 1) { acc.x *= invC; acc.y *= invC; }
-        reinterpret_cast<float2*>(out_proto + (size_t)b * D)[threadIdx.x] = acc;
+        st_row(slot[warp], lane, acc);
+        __syncthreads();
+        {
+            const int t = threadIdx.x;                              // float4 column t of the 512-wide row
+            float4 s = reinterpret_cast<const float4*>(slot[0])[t];
+#pragma unroll
+            for (int w = 1; w < TQ_WARPS; ++w) {
+                const float4 a = reinterpret_cast<const float4*>(slot[w])[t];
+                s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            }
+            const float4 g = reinterpret_cast<const float4*>(gamma)[t], be = reinterpret_cast<const float4*>(beta)[t];
+            s.x = fmaf(s.x * invC, g.x, be.x); s.y = fmaf(s.y * invC, g.y, be.y);
+            s.z = fmaf(s.z * invC, g.z, be.z); s.w = fmaf(s.w * invC, g.w, be.w);
+            reinterpret_cast<float4*>(out_proto + (size_t)b * D)[t] = s;
+        }
+        __syncthreads();
     }
 }
 

@@ -28,29 +28,58 @@ __device__ __forceinline__ void st_row_h(__nv_bfloat16* p, int lane, const float
 #pragma unroll
     for (int i = 0; i < 4; ++i) reinterpret_cast<uint2*>(p)[lane + 32 * i] = pack_bf16x4(v[i]);
 }
+// ---- 512-wide row arithmetic on packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one instruction per two
+// lanes of a float4, rounding identical to the scalar fmaf / add / mul)
+__device__ __forceinline__ float2 xy(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 zw(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float4 f4(float2 a, float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+    return f4(__ffma2_rn(xy(a), xy(b), xy(c)), __ffma2_rn(zw(a), zw(b), zw(c)));
+}
+__device__ __forceinline__ float4 fma4s(float a, float4 b, float4 c) {
+    const float2 aa = make_float2(a, a);
+    return f4(__ffma2_rn(aa, xy(b), xy(c)), __ffma2_rn(aa, zw(b), zw(c)));
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return f4(__fadd2_rn(xy(a), xy(b)), __fadd2_rn(zw(a), zw(b))); }
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return f4(__fmul2_rn(xy(a), xy(b)), __fmul2_rn(zw(a), zw(b))); }
+__device__ __forceinline__ float4 mul4s(float a, float4 b) {
+    const float2 aa = make_float2(a, a);
+    return f4(__fmul2_rn(aa, xy(b)), __fmul2_rn(aa, zw(b)));
+}
+__device__ __forceinline__ float4 add4s(float a, float4 b) {
+    const float2 aa = make_float2(a, a);
+    return f4(__fadd2_rn(aa, xy(b)), __fadd2_rn(aa, zw(b)));
+}
+
 __device__ __forceinline__ float dot_part(const float4 (&a)[4], const float4 (&b)[4]) {
-    float s = 0.f;
+    float2 s0 = __fmul2_rn(xy(a[0]), xy(b[0])), s1 = __fmul2_rn(zw(a[0]), zw(b[0]));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s += a[i].x * b[i].x + a[i].y * b[i].y + a[i].z * b[i].z + a[i].w * b[i].w;
-    return s;
+    for (int i = 1; i < 4; ++i) { s0 = __ffma2_rn(xy(a[i]), xy(b[i]), s0); s1 = __ffma2_rn(zw(a[i]), zw(b[i]), s1); }
+    const float2 s = __fadd2_rn(s0, s1);
+    return s.x + s.y;
 }
 __device__ __forceinline__ float sum_part(const float4 (&a)[4]) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s += a[i].x + a[i].y + a[i].z + a[i].w;
-    return s;
+    float2 s0 = __fadd2_rn(xy(a[0]), zw(a[0])), s1 = __fadd2_rn(xy(a[1]), zw(a[1]));
+    s0 = __fadd2_rn(s0, __fadd2_rn(xy(a[2]), zw(a[2])));
+    s1 = __fadd2_rn(s1, __fadd2_rn(xy(a[3]), zw(a[3])));
+    const float2 s = __fadd2_rn(s0, s1);
+    return s.x + s.y;
 }
 __device__ __forceinline__ void axpy_row(float4 (&y)[4], float a, const float4 (&x)[4]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        y[i].x = fmaf(a, x[i].x, y[i].x); y[i].y = fmaf(a, x[i].y, y[i].y);
-        y[i].z = fmaf(a, x[i].z, y[i].z); y[i].w = fmaf(a, x[i].w, y[i].w);
-    }
+    for (int i = 0; i < 4; ++i) y[i] = fma4s(a, x[i], y[i]);
 }
-__device__ __forceinline__ void add_row(float4 (&y)[4], const float4 (&x)[4]) { axpy_row(y, 1.0f, x); }
+__device__ __forceinline__ void add_row(float4 (&y)[4], const float4 (&x)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = add4(y[i], x[i]);
+}
 __device__ __forceinline__ void scale_row(float4 (&y)[4], float a) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { y[i].x *= a; y[i].y *= a; y[i].z *= a; y[i].w *= a; }
+    for (int i = 0; i < 4; ++i) y[i] = mul4s(a, y[i]);
+}
+__device__ __forceinline__ void shift_row(float4 (&y)[4], float a) {            // y += a
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = add4s(a, y[i]);
 }
 __device__ __forceinline__ void zero_row(float4 (&y)[4]) {
 #pragma unroll
@@ -62,16 +91,13 @@ __device__ __forceinline__ void ln_forward(const float4 (&u)[4], const float4 (&
                                            float4 (&xh)[4], float& rstd, float4 (&o)[4]) {
     const float mean = warp_sum(sum_part(u)) * (1.0f / D);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        xh[i].x = u[i].x - mean; xh[i].y = u[i].y - mean; xh[i].z = u[i].z - mean; xh[i].w = u[i].w - mean;
-    }
+    for (int i = 0; i < 4; ++i) xh[i] = add4s(-mean, u[i]);
     const float var = warp_sum(dot_part(xh, xh)) * (1.0f / D);
     rstd = 1.0f / sqrtf(var + LN_EPS);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        xh[i].x *= rstd; xh[i].y *= rstd; xh[i].z *= rstd; xh[i].w *= rstd;
-        o[i].x = fmaf(xh[i].x, g[i].x, be[i].x); o[i].y = fmaf(xh[i].y, g[i].y, be[i].y);
-        o[i].z = fmaf(xh[i].z, g[i].z, be[i].z); o[i].w = fmaf(xh[i].w, g[i].w, be[i].w);
+        xh[i] = mul4s(rstd, xh[i]);
+        o[i] = fma4(xh[i], g[i], be[i]);
     }
 }
 // du = rstd * (gg - mean(gg) - xh * mean(gg*xh)),  gg = go * gamma
@@ -79,14 +105,11 @@ __device__ __forceinline__ void ln_backward(const float4 (&go)[4], const float4 
                                             const float4 (&g)[4], float4 (&du)[4]) {
     float4 gg[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) gg[i] = make_float4(go[i].x * g[i].x, go[i].y * g[i].y, go[i].z * g[i].z, go[i].w * g[i].w);
+    for (int i = 0; i < 4; ++i) gg[i] = mul4(go[i], g[i]);
     const float m1 = warp_sum(sum_part(gg)) * (1.0f / D);
     const float m2 = warp_sum(dot_part(gg, xh)) * (1.0f / D);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        du[i].x = rstd * (gg[i].x - m1 - xh[i].x * m2); du[i].y = rstd * (gg[i].y - m1 - xh[i].y * m2);
-        du[i].z = rstd * (gg[i].z - m1 - xh[i].z * m2); du[i].w = rstd * (gg[i].w - m1 - xh[i].w * m2);
-    }
+    for (int i = 0; i < 4; ++i) du[i] = mul4s(rstd, fma4s(-m2, xh[i], add4s(-m1, gg[i])));
 }
 
 __device__ __forceinline__ int clamp_state(int64_t s) { return s < 0 ? 0 : (s > 9 ? 9 : (int)s); }
