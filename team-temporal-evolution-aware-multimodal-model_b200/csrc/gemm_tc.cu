@@ -17,9 +17,11 @@
 //              (multiple of 16, <= 128); the accumulator lives in TMEM.
 //   epilogue : tcgen05.ld (warp w owns TMEM lanes 32w..32w+31) -> padded shared-memory tile ->
 //              row-contiguous 128-bit global stores (fp32) / 64-bit (bf16).
-//   split-K  : partial tiles go to a workspace; the LAST arriving CTA of a tile (atomic ticket) folds
-//              all partials in split order - deterministic - and runs the epilogue, so there is no
-//              second reduction kernel.  Tickets reset themselves.
+//   split-K  : the 2 / 4 / 8 CTAs that share an output tile form (part of) a thread-block CLUSTER; each keeps
+//              its fp32 partial tile in its own shared memory and, after a cluster barrier, reduces one
+//              row slice of the tile over all partials through distributed shared memory
+//              (ld.shared::cluster) in split order - deterministic, no global-memory round trip, no
+//              second kernel - and runs the epilogue for that slice.
 //   PDL      : griddepcontrol.launch_dependents / .wait bracket the prologue (barrier init, TMEM
 //              alloc, tensor-map prefetch) so it overlaps the previous kernel's tail when the launch
 //              carries the programmatic-stream-serialization attribute.
@@ -44,7 +46,7 @@ constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
 constexpr int tc_smem_bytes(int stages) { return stages * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }   // 3 stages: 97.25 KB -> 2 CTAs / SM
 constexpr uint32_t TC_TMEM_COLS = 128;
 constexpr int TC_MAXP = 8;           // problems per launch (kernel parameter space: 8 * 768 B; CUDA >= 12.1 allows 32 KB)
-constexpr int TC_MAX_TICKETS = 4096; // split-K tickets at the head of the workspace
+constexpr int TC_MAX_SPLITS = 8;     // = largest portable cluster size
 constexpr int TC_TARGET_CTAS = 2 * NUM_SMS;
 
 static_assert(TC_BM * (TC_MAX_BN + 4) * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilogue staging must fit in the operand ring");
@@ -58,17 +60,16 @@ struct alignas(64) TcProb {
     float* C;
     __nv_bfloat16* Cb;
     const float* bias;
-    float* partial;
-    unsigned* ticket;
     long long ldc, ldcb;
     float alpha, beta;
     int M, N;
-    int bn, tiles_n, cta_begin, splits, kb_per_split;
+    int bn, tiles_n, n_tiles, cta_begin, splits, kb_per_split;
 };
 struct TcGroup {
     TcProb p[TC_MAXP];
     int n;
     int stages;
+    int cluster;                 // CTAs per cluster (1, 2, 4 or 8) = largest split count of the group
     unsigned long long* dbg;     // optional [cta][16] globaltimer stamps (tools/gemm_probe.py), else null
 };
 __device__ __forceinline__ unsigned long long gtime() {
@@ -137,6 +138,20 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
         : "r"(taddr));
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // shared-memory matrix descriptors (SWIZZLE_128B, descriptor version 1)
 //   K-major : rows of 128 B (64 bf16 along K); 8-row groups SBO = 1024 B apart.
 //   MN-major: rows of 128 B (64 bf16 along M/N), one row per k; 8-k groups SBO = 1024 B apart;
@@ -162,7 +177,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;
     uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    uint32_t* last_flag = tmem_slot + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) TC_STAMP(0);
 
@@ -172,6 +186,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     const TcProb& P = g.p[pi];
     const int local = (int)blockIdx.x - P.cta_begin;
     const int split = local % P.splits, tile = local / P.splits;
+    if (tile >= P.n_tiles) {           // padding CTA of a cluster: only keeps the cluster barriers balanced
+        if (P.splits > 1) { cluster_sync_all(); cluster_sync_all(); }
+        return;
+    }
     const int m0 = (tile / P.tiles_n) * TC_BM, bn = P.bn, n0 = (tile % P.tiles_n) * bn;
     const int nkb0 = P.s[0].nkb;
     const int nkb = nkb0 + P.s[1].nkb;
@@ -286,71 +304,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
                 *reinterpret_cast<float4*>(my + c + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
         }
     }
-    __syncwarp();
     if (threadIdx.x == 64) TC_STAMP(8);
-    // each warp now streams out its own 32 rows, lanes along the columns: lane -> (row offset rr_off, float4 column cc)
-    const int lpr = bn >> 2;                                   // float4 columns per row (4..32)
-    const int rpp = 32 / lpr;                                  // rows per pass (1..8)
-    const int rr_off = lane / lpr, cc = lane - rr_off * lpr;   // the only divisions, hoisted out of the loops
-    const bool lane_on = rr_off < rpp;
+    // split-K: every CTA of the tile publishes its partial (cluster barrier), then owns rows [row0, row0 + nrow)
     const int splits = P.splits;
-    bool is_last = true;
+    int row0 = 0, nrow = TC_BM;
+    uint32_t rank0 = 0;
     if (splits > 1) {
-        float* mine = P.partial + ((size_t)tile * splits + split) * (size_t)(TC_BM * bn);
-        if (lane_on) {
-#pragma unroll 4
-            for (int r0 = 0; r0 < 32; r0 += rpp) {
-                const int row = warp * 32 + r0 + rr_off;
-                *reinterpret_cast<float4*>(mine + (size_t)row * bn + 4 * cc) = *reinterpret_cast<const float4*>(stg + (size_t)row * sld + 4 * cc);
-            }
-        }
-        if (threadIdx.x == 64) TC_STAMP(9);
-        __threadfence();
+        cluster_sync_all();
+        nrow = TC_BM / splits;
+        row0 = split * nrow;
+        uint32_t myrank;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(myrank));
+        rank0 = myrank - (uint32_t)split;              // rank of split 0 of this tile
+    } else {
         __syncthreads();
-        if (threadIdx.x == 64) TC_STAMP(10);
-        if (threadIdx.x == 0) {
-            const unsigned old = atomicAdd(P.ticket + tile, 1u);
-            const bool last = old == (unsigned)(splits - 1);
-            if (last) P.ticket[tile] = 0;            // every split has taken its ticket: reset for the next launch
-            *last_flag = last ? 1u : 0u;
-        }
-        __syncthreads();
-        is_last = *last_flag != 0;
-        if (is_last) {
-            __threadfence();
-            // fold all partials in split order (deterministic) back into the smem tile, 8 rows of loads in flight
-            if (lane_on) {
-                const float* src = P.partial + (size_t)tile * splits * (size_t)(TC_BM * bn) + 4 * cc;
-                constexpr int FB = 16;                     // rows of loads in flight per lane
-                const int step = FB * rpp;
-                for (int r0 = 0; r0 < 32; r0 += step) {
-                    float4 acc[FB];
-#pragma unroll
-                    for (int j = 0; j < FB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int z = 0; z < splits; ++z) {
-                        float4 a[FB];
-#pragma unroll
-                        for (int j = 0; j < FB; ++j) {
-                            const int lr = r0 + j * rpp + rr_off;
-                            a[j] = lr < 32 ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)z * (TC_BM * bn) + (size_t)(warp * 32 + lr) * bn))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int j = 0; j < FB; ++j) { acc[j].x += a[j].x; acc[j].y += a[j].y; acc[j].z += a[j].z; acc[j].w += a[j].w; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < FB; ++j) {
-                        const int lr = r0 + j * rpp + rr_off;
-                        if (lr < 32) *reinterpret_cast<float4*>(stg + (size_t)(warp * 32 + lr) * sld + 4 * cc) = acc[j];
-                    }
-                }
-            }
-            __syncwarp();
-            if (threadIdx.x == 64) TC_STAMP(11);
-        }
     }
-    if (threadIdx.x == 64) TC_STAMP(13);
-    if (is_last && lane_on) {
+    if (threadIdx.x == 64) TC_STAMP(9);
+    {
         const int M = P.M, N = P.N;
         float* const C = P.C;
         __nv_bfloat16* const Cb = P.Cb;
@@ -358,70 +328,93 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
         const bool vec_ok = (N % 4 == 0) && (C == nullptr || ((ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0))) &&
                             (Cb == nullptr || ((ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 7) == 0)));
         const float alpha = P.alpha, beta = P.beta;
-        const int col = n0 + 4 * cc;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (P.bias != nullptr) {
-            if (col < N) bv.x = __ldg(P.bias + col);
-            if (col + 1 < N) bv.y = __ldg(P.bias + col + 1);
-            if (col + 2 < N) bv.z = __ldg(P.bias + col + 2);
-            if (col + 3 < N) bv.w = __ldg(P.bias + col + 3);
-        }
-        if (threadIdx.x == 64) TC_STAMP(12);
-        // rows this lane streams out: local rows lrow0, lrow0 + rpp, ... (nvalid of them inside M)
-        const int lrow0 = warp * 32 + rr_off;
-        int nvalid = 32 / rpp;
-        {
-            const int left = M - (m0 + lrow0);                 // rows of the matrix at or below this lane's first row
-            const int cap = left <= 0 ? 0 : (left + rpp - 1) / rpp;
-            if (cap < nvalid) nvalid = cap;
-        }
-        const float* sp = stg + (size_t)lrow0 * sld + 4 * cc;
-        const int sstep = rpp * sld;
-        if (col < N && vec_ok) {
-            float* cp = C != nullptr ? C + (long long)(m0 + lrow0) * ldc + col : nullptr;
-            __nv_bfloat16* bp = Cb != nullptr ? Cb + (long long)(m0 + lrow0) * ldcb + col : nullptr;
-            const long long cstep = (long long)rpp * ldc, bstep = (long long)rpp * ldcb;
-            const bool acc_c = beta != 0.f && cp != nullptr;
-            for (int q0 = 0; q0 < nvalid; q0 += 8) {           // 8 smem reads in flight, then 8 row-contiguous stores
-                float4 v[8], o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (q0 + j < nvalid) v[j] = *reinterpret_cast<const float4*>(sp + (size_t)(q0 + j) * sstep);
-                if (acc_c) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (q0 + j < nvalid) o[j] = *reinterpret_cast<const float4*>(cp + (q0 + j) * cstep);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (q0 + j >= nvalid) continue;
-                    float4 x = make_float4(fmaf(alpha, v[j].x, bv.x), fmaf(alpha, v[j].y, bv.y), fmaf(alpha, v[j].z, bv.z), fmaf(alpha, v[j].w, bv.w));
-                    if (acc_c) { x.x = fmaf(beta, o[j].x, x.x); x.y = fmaf(beta, o[j].y, x.y); x.z = fmaf(beta, o[j].z, x.z); x.w = fmaf(beta, o[j].w, x.w); }
-                    if (cp != nullptr) *reinterpret_cast<float4*>(cp + (q0 + j) * cstep) = x;
-                    if (bp != nullptr) *reinterpret_cast<uint2*>(bp + (q0 + j) * bstep) = pack_bf16x4(x);
-                }
-                if (threadIdx.x == 64 && q0 == 0) TC_STAMP(14);
+        const bool acc_c = beta != 0.f && C != nullptr;
+        const float* bias = P.bias;
+        // thread -> (row offset r_off, float4 column c4): lanes run along the columns, rpp rows per pass
+        const int lpr = bn >> 2;                                   // float4 columns per row (4..32)
+        const int rpp = TC_THREADS / lpr;                          // rows per pass (4..32)
+        const int r_off = (int)threadIdx.x / lpr, c4 = (int)threadIdx.x - r_off * lpr;
+        const int col = n0 + 4 * c4;
+        if (r_off < rpp && col < N) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias != nullptr) {
+                bv.x = __ldg(bias + col);
+                if (col + 1 < N) bv.y = __ldg(bias + col + 1);
+                if (col + 2 < N) bv.z = __ldg(bias + col + 2);
+                if (col + 3 < N) bv.w = __ldg(bias + col + 3);
             }
-        } else if (col < N) {
-            // ragged N / unaligned outputs: element-wise with guards
-            for (int q = 0; q < nvalid; ++q) {
-                const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)q * sstep);
-                const long long row = m0 + lrow0 + (long long)q * rpp;
-                const float xs[4] = {fmaf(alpha, v.x, bv.x), fmaf(alpha, v.y, bv.y), fmaf(alpha, v.z, bv.z), fmaf(alpha, v.w, bv.w)};
+            // rows of this thread: row0 + r_off + q * rpp, q = 0 .. nq-1, clipped to the slice and to M
+            int nq = (nrow - r_off + rpp - 1) / rpp;
+            {
+                const int left = M - (m0 + row0 + r_off);
+                const int cap = left <= 0 ? 0 : (left + rpp - 1) / rpp;
+                if (cap < nq) nq = cap;
+            }
+            const uint32_t stg_addr = smem_u32(stg);
+            const uint32_t off0 = (uint32_t)(((row0 + r_off) * sld + 4 * c4) * 4), ostep = (uint32_t)(rpp * sld * 4);
+            const unsigned char* lp = reinterpret_cast<const unsigned char*>(stg) + off0;
+            uint32_t rbase[TC_MAX_SPLITS];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (col + i >= N) continue;
-                    float y = xs[i];
-                    if (C != nullptr) {
-                        float* dst = C + row * ldc + col + i;
-                        if (beta != 0.f) y = fmaf(beta, *dst, y);
-                        *dst = y;
+            for (int z = 0; z < TC_MAX_SPLITS; ++z) rbase[z] = z < splits ? map_to_cta(stg_addr + off0, rank0 + (uint32_t)z) : 0u;
+            float* cp = C != nullptr ? C + (long long)(m0 + row0 + r_off) * ldc + col : nullptr;
+            __nv_bfloat16* bp = Cb != nullptr ? Cb + (long long)(m0 + row0 + r_off) * ldcb + col : nullptr;
+            const long long cstep = (long long)rpp * ldc, bstep = (long long)rpp * ldcb;
+            constexpr int UN = 8;                                  // rows in flight per thread
+            for (int q0 = 0; q0 < nq; q0 += UN) {
+                float4 v[UN], o[UN];
+                if (splits == 1) {
+#pragma unroll
+                    for (int j = 0; j < UN; ++j)
+                        if (q0 + j < nq) v[j] = *reinterpret_cast<const float4*>(lp + (size_t)(q0 + j) * ostep);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < UN; ++j)
+                        if (q0 + j < nq) v[j] = ld_cluster_f4(rbase[0] + (uint32_t)(q0 + j) * ostep);
+#pragma unroll
+                    for (int z = 1; z < TC_MAX_SPLITS; ++z) {      // fixed order: deterministic
+                        if (z >= splits) break;
+                        float4 a[UN];
+#pragma unroll
+                        for (int j = 0; j < UN; ++j)
+                            if (q0 + j < nq) a[j] = ld_cluster_f4(rbase[z] + (uint32_t)(q0 + j) * ostep);
+#pragma unroll
+                        for (int j = 0; j < UN; ++j)
+                            if (q0 + j < nq) { v[j].x += a[j].x; v[j].y += a[j].y; v[j].z += a[j].z; v[j].w += a[j].w; }
                     }
-                    if (Cb != nullptr) Cb[row * ldcb + col + i] = __float2bfloat16_rn(y);
+                }
+                if (acc_c && vec_ok) {
+#pragma unroll
+                    for (int j = 0; j < UN; ++j)
+                        if (q0 + j < nq) o[j] = *reinterpret_cast<const float4*>(cp + (q0 + j) * cstep);
+                }
+#pragma unroll
+                for (int j = 0; j < UN; ++j) {
+                    if (q0 + j >= nq) continue;
+                    float4 x = make_float4(fmaf(alpha, v[j].x, bv.x), fmaf(alpha, v[j].y, bv.y), fmaf(alpha, v[j].z, bv.z), fmaf(alpha, v[j].w, bv.w));
+                    if (vec_ok) {
+                        if (acc_c) { x.x = fmaf(beta, o[j].x, x.x); x.y = fmaf(beta, o[j].y, x.y); x.z = fmaf(beta, o[j].z, x.z); x.w = fmaf(beta, o[j].w, x.w); }
+                        if (cp != nullptr) *reinterpret_cast<float4*>(cp + (q0 + j) * cstep) = x;
+                        if (bp != nullptr) *reinterpret_cast<uint2*>(bp + (q0 + j) * bstep) = pack_bf16x4(x);
+                    } else {
+                        // ragged N / unaligned outputs: element-wise with guards
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (col + i >= N) continue;
+                            float y = xs[i];
+                            if (cp != nullptr) {
+                                float* dst = cp + (q0 + j) * cstep + i;
+                                if (acc_c) y = fmaf(beta, *dst, y);
+                                *dst = y;
+                            }
+                            if (bp != nullptr) bp[(q0 + j) * bstep + i] = __float2bfloat16_rn(y);
+                        }
+                    }
                 }
             }
         }
     }
+    if (splits > 1) cluster_sync_all();        // peers may still be reading this CTA's partial
     if (threadIdx.x == 64) TC_STAMP(6);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -498,13 +491,9 @@ static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t o
     return TEAM_OK;
 }
 
-size_t tc_workspace_bytes(size_t partial_bytes) { return (size_t)TC_MAX_TICKETS * sizeof(unsigned) + partial_bytes; }
-
-int tc_workspace_init(cudaStream_t st, void* ws, size_t ws_bytes) {
-    if (ws == nullptr || ws_bytes < (size_t)TC_MAX_TICKETS * sizeof(unsigned)) return TEAM_OK;
-    TEAM_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)TC_MAX_TICKETS * sizeof(unsigned), st));
-    return TEAM_OK;
-}
+// split-K no longer goes through global memory: the workspace arguments are kept for ABI stability only
+size_t tc_workspace_bytes(size_t) { return 256; }
+int tc_workspace_init(cudaStream_t, void*, size_t) { return TEAM_OK; }
 
 static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double flops, double bytes) {
     static bool attr_set = false;
@@ -513,17 +502,25 @@ static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double
         attr_set = true;
     }
     const int pslot = prof_enabled() ? prof_begin(st, 1, flops, bytes) : -1;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)total_ctas, 1, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = tc_smem_bytes(grp.stages);
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (grp.cluster > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)grp.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (g_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel, grp);
     if (pslot >= 0) prof_end(st, pslot);
     count_launch();
@@ -532,41 +529,49 @@ static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double
 }
 
 // Plans tiles / splits for ops[0..n) and launches them in chunks of TC_MAXP problems.
+//   * N tile: 128 wide unless the whole launch would leave most SMs without a tile, then 64;
+//   * split-K: while the launch stays within two CTAs per SM, the problem with the most k-blocks per CTA is
+//     split further (2 / 4 / 8 ways), so that a [512,512] weight gradient over K = 2B rows does not run as 16 long CTAs
+//     next to hundreds of short ones.  The largest split count is the cluster size of the launch.
 int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t ws_bytes) {
+    (void)ws; (void)ws_bytes;
     int rc = get_encode();
     if (rc) return rc;
-    unsigned* tickets = reinterpret_cast<unsigned*>(ws);
-    char* part_base = ws ? reinterpret_cast<char*>(ws) + (size_t)TC_MAX_TICKETS * sizeof(unsigned) : nullptr;
-    const size_t part_cap = (ws && ws_bytes > (size_t)TC_MAX_TICKETS * sizeof(unsigned)) ? ws_bytes - (size_t)TC_MAX_TICKETS * sizeof(unsigned) : 0;
     for (int base = 0; base < n; base += TC_MAXP) {
         const int cnt = n - base < TC_MAXP ? n - base : TC_MAXP;
         TcGroup grp;
         memset(&grp, 0, sizeof(grp));
-        int np = 0;
-        int tiles[TC_MAXP], nkbs[TC_MAXP];
-        double kflops[TC_MAXP];
+        const TcGemm* sel[TC_MAXP];
+        int np = 0, tiles128 = 0;
         for (int i = 0; i < cnt; ++i) {
             const TcGemm& g = ops[base + i];
             if (g.M <= 0 || g.N <= 0) continue;
             TEAM_REQUIRE(g.nseg == 1 || g.nseg == 2, "gemm_bf16: nseg %d", g.nseg);
             TEAM_REQUIRE(g.C != nullptr || g.Cb != nullptr, "gemm_bf16: no output");
-            bool any_b_mn = false;
             for (int q = 0; q < g.nseg; ++q) {
                 const TcSeg& sg = g.s[q];
                 TEAM_REQUIRE(sg.K > 0 && sg.lda % 8 == 0 && sg.ldb % 8 == 0, "gemm_bf16: K=%lld lda=%lld ldb=%lld (leading dims must be multiples of 8)", (long long)sg.K, (long long)sg.lda, (long long)sg.ldb);
                 TEAM_REQUIRE((reinterpret_cast<uintptr_t>(sg.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(sg.B) & 15) == 0, "gemm_bf16: operands must be 16-byte aligned");
-                any_b_mn = any_b_mn || sg.b_mn;
             }
-            TcProb& p = grp.p[np];
+            sel[np++] = &g;
+            tiles128 += (int)((g.M + TC_BM - 1) / TC_BM) * (int)((g.N + TC_MAX_BN - 1) / TC_MAX_BN);
+        }
+        if (np == 0) continue;
+        const bool narrow = tiles128 < NUM_SMS;
+        int tiles[TC_MAXP], nkbs[TC_MAXP];
+        double kflops[TC_MAXP];
+        for (int i = 0; i < np; ++i) {
+            const TcGemm& g = *sel[i];
+            bool any_b_mn = false;
+            for (int q = 0; q < g.nseg; ++q) any_b_mn = any_b_mn || g.s[q].b_mn;
+            TcProb& p = grp.p[i];
             const int tiles_m = (int)((g.M + TC_BM - 1) / TC_BM);
-            // N tile: up to 128 wide; halve it while the problem alone would leave most SMs without a tile
-            int bn;
             const int nt128 = (int)((g.N + TC_MAX_BN - 1) / TC_MAX_BN);
-            const bool narrow = tiles_m * nt128 * 2 <= NUM_SMS && g.N > 64;
+            int bn;
             if (any_b_mn) {
                 bn = (g.N > 64 && !narrow) ? 128 : 64;
             } else {
-                const int nt = narrow ? (int)((g.N + 63) / 64) : nt128;
+                const int nt = (narrow && g.N > 64) ? (int)((g.N + 63) / 64) : nt128;
                 bn = (int)(((g.N + nt - 1) / nt + 15) / 16 * 16);
             }
             p.bn = bn;
@@ -574,8 +579,8 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
             p.M = (int)g.M; p.N = (int)g.N;
             p.alpha = g.alpha; p.beta = g.beta;
             p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias;
-            nkbs[np] = 0;
-            kflops[np] = 0;
+            nkbs[i] = 0;
+            kflops[i] = 0;
             for (int q = 0; q < g.nseg; ++q) {
                 const TcSeg& sg = g.s[q];
                 TcSegDev& sd = p.s[q];
@@ -586,52 +591,44 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
                 if (rc) return rc;
                 if (!sg.b_mn) rc = make_map(&sd.mb, sg.B, sg.K, g.N, sg.ldb, TC_BK, bn); else rc = make_map(&sd.mb, sg.B, g.N, sg.K, sg.ldb, 64, TC_BK);
                 if (rc) return rc;
-                nkbs[np] += sd.nkb;
-                kflops[np] += (double)sg.K;
+                nkbs[i] += sd.nkb;
+                kflops[i] += (double)sg.K;
             }
-            tiles[np] = tiles_m * p.tiles_n;
+            tiles[i] = tiles_m * p.tiles_n;
+            p.n_tiles = tiles[i];
             p.splits = 1;
-            ++np;
         }
-        if (np == 0) continue;
-        // split-K: long-K problems get ~12 k-blocks per CTA while the launch stays within two CTAs per SM
+        // split-K by doubling: always the problem with the most k-blocks per CTA, while two CTAs per SM can hold the launch
         int total = 0;
         for (int i = 0; i < np; ++i) total += tiles[i];
-        if (part_base != nullptr) {
-            for (;;) {
-                int best = -1, best_kb = 12;
-                for (int i = 0; i < np; ++i) {
-                    const int per = (nkbs[i] + grp.p[i].splits - 1) / grp.p[i].splits;
-                    if (per > best_kb && grp.p[i].splits < 16 && total + tiles[i] <= TC_TARGET_CTAS) { best = i; best_kb = per; }
-                }
-                if (best < 0) break;
-                grp.p[best].splits += 1;
-                total += tiles[best];
+        const bool allow_split = getenv("TEAM_NO_SPLITK") == nullptr;
+        while (allow_split) {
+            int best = -1, best_kb = 10;
+            for (int i = 0; i < np; ++i) {
+                const int s = grp.p[i].splits;
+                const int per = (nkbs[i] + s - 1) / s;
+                const int per2 = (nkbs[i] + 2 * s - 1) / (2 * s);
+                const bool valid = 2 * s <= TC_MAX_SPLITS && (2 * s - 1) * per2 < nkbs[i];     // every split keeps >= 1 k-block
+                if (per > best_kb && valid && total + tiles[i] * s <= TC_TARGET_CTAS) { best = i; best_kb = per; }
             }
+            if (best < 0) break;
+            total += tiles[best] * grp.p[best].splits;
+            grp.p[best].splits *= 2;
         }
-        size_t part_off = 0;
-        int ticket_off = 0, cta = 0;
+        int cluster = 1;
+        for (int i = 0; i < np; ++i) cluster = grp.p[i].splits > cluster ? grp.p[i].splits : cluster;
+        int cta = 0;
         double flops = 0, bytes = 0;
         for (int i = 0; i < np; ++i) {
             TcProb& p = grp.p[i];
-            int kbps = (nkbs[i] + p.splits - 1) / p.splits;
-            p.splits = (nkbs[i] + kbps - 1) / kbps;
-            if (p.splits > 1) {
-                const size_t need = (size_t)tiles[i] * p.splits * TC_BM * p.bn * sizeof(float);
-                if (part_off + need > part_cap || ticket_off + tiles[i] > TC_MAX_TICKETS) { p.splits = 1; kbps = nkbs[i]; }
-                else {
-                    p.partial = reinterpret_cast<float*>(part_base + part_off);
-                    p.ticket = tickets + ticket_off;
-                    part_off += need; ticket_off += tiles[i];
-                }
-            }
-            p.kb_per_split = kbps;
+            p.kb_per_split = (nkbs[i] + p.splits - 1) / p.splits;
             p.cta_begin = cta;
-            cta += tiles[i] * p.splits;
+            cta += (tiles[i] * p.splits + cluster - 1) / cluster * cluster;        // whole clusters per problem
             flops += 2.0 * p.M * p.N * kflops[i];
             bytes += 2.0 * ((double)p.M + (double)p.N) * kflops[i] + (p.C ? 4.0 : 0.0) * p.M * p.N + (p.Cb ? 2.0 : 0.0) * p.M * p.N;
         }
         grp.n = np;
+        grp.cluster = cluster;
         grp.stages = cta <= NUM_SMS ? TC_MAX_STAGES : TC_STAGES;
         grp.dbg = g_dbg;
         if ((rc = tc_launch(st, grp, cta, flops, bytes))) return rc;
