@@ -269,7 +269,7 @@ typedef struct team_gemm_desc {
 int team_gemm_bf16_group(const team_gemm_desc* descs, int32_t n, void* workspace, size_t workspace_bytes, void* stream);
 /* programmatic dependent launch for the library's kernels (default: env TEAM_PDL, else off) */
 int team_set_pdl(int on);
-/* debugging aid: if buf != NULL every GEMM CTA writes 8 globaltimer stamps to buf[cta*8..] (tools/gemm_probe.py) */
+/* debugging aid: if buf != NULL (32 x 1024 x 16 uint64) every GEMM CTA writes globaltimer stamps of its phases into the slot of its launch (tools/wave_stamps.py) */
 int team_gemm_debug_stamps(void* buf);
 /* fp32 [rows,cols] -> bf16 hi (and optional lo residual) */
 int team_f32_to_bf16(const float* src, int64_t lds, int64_t rows, int64_t cols, void* hi, void* lo,

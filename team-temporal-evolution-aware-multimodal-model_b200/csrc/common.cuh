@@ -37,6 +37,36 @@ void count_launch();
         if (!(cond)) { team::set_error(__VA_ARGS__); return TEAM_EINVAL; } \
     } while (0)
 
+// Programmatic dependent launch: every kernel of the library releases its dependents at once and then waits
+// for its own prerequisites before touching global memory, so launch latency, block scheduling and the
+// prologue (barrier init, TMEM alloc, parameter loads) of kernel N+1 overlap the tail of kernel N.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+void pdl_set(bool on);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
+// launch + count + status check (the kernel must start with pdl_trigger(); pdl_wait();)
+#define TEAM_LAUNCH(kernel, grid, block, smem, st, ...)                                         \
+    do {                                                                                        \
+        cudaError_t _e = team::launch_pdl(kernel, (unsigned)(grid), (unsigned)(block), (size_t)(smem), st, __VA_ARGS__); \
+        team::count_launch();                                                                   \
+        if (_e != cudaSuccess) return team::cuda_fail(_e, #kernel);                             \
+    } while (0)
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

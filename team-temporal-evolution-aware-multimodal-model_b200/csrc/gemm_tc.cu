@@ -77,7 +77,7 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-#define TC_STAMP(slot) do { if (g.dbg != nullptr) g.dbg[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+#define TC_STAMP(slot) do { if (g.dbg != nullptr && blockIdx.x < 1024) g.dbg[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,6 +178,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
     if (threadIdx.x == 0) TC_STAMP(0);
 
     int pi = 0;
@@ -217,8 +218,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     const uint32_t tmem_base = *tmem_slot;
     // PDL: let the next kernel start its own prologue; wait until everything before us has completed
     if (threadIdx.x == 0) TC_STAMP(1);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
     if (threadIdx.x == 0) TC_STAMP(2);
 
     if (threadIdx.x == 0) {
@@ -451,11 +451,11 @@ f32_to_bf16_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int
 // ------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
-static bool g_pdl = false;
 static unsigned long long* g_dbg = nullptr;
+static int g_dbg_launch = 0;      // launch slot inside the stamp buffer (32 slots x 1024 CTAs x 16 stamps)
 
-void tc_set_pdl(bool on) { g_pdl = on; }
-bool tc_pdl() { return g_pdl; }
+void tc_set_pdl(bool on) { pdl_set(on); }
+bool tc_pdl() { return pdl_enabled(); }
 
 static int get_encode() {
     std::call_once(g_encode_once, [] {
@@ -464,8 +464,6 @@ static int get_encode() {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
             g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-        const char* e = getenv("TEAM_PDL");
-        if (e != nullptr) g_pdl = e[0] != '0';
     });
     if (g_encode == nullptr) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -514,7 +512,7 @@ static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double
         at[na].val.clusterDim.x = (unsigned)grp.cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (g_pdl) {
+    if (pdl_enabled()) {
         at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
@@ -630,7 +628,7 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
         grp.n = np;
         grp.cluster = cluster;
         grp.stages = cta <= NUM_SMS ? TC_MAX_STAGES : TC_STAGES;
-        grp.dbg = g_dbg;
+        grp.dbg = g_dbg != nullptr ? g_dbg + (size_t)(g_dbg_launch++ % 32) * 1024 * 16 : nullptr;
         if ((rc = tc_launch(st, grp, cta, flops, bytes))) return rc;
     }
     return TEAM_OK;
@@ -709,6 +707,7 @@ extern "C" int team_f32_to_bf16(const float* src, int64_t lds, int64_t rows, int
 
 extern "C" int team_gemm_debug_stamps(void* buf) {
     g_dbg = reinterpret_cast<unsigned long long*>(buf);
+    g_dbg_launch = 0;
     return TEAM_OK;
 }
 

@@ -205,8 +205,7 @@ static int prologue(HeadCtx& cx, const team_head_weights* hw, int nsum, const fl
     if (image) conv_add(cl, blocks, image, nullptr, w.img.h, batch * D);
     if (text) conv_add(cl, blocks, text, nullptr, w.txt.h, batch * D);
     if (text_cls && d.Tc > 0) conv_add(cl, blocks, text_cls, nullptr, w.tcls.h, (int64_t)d.Tc * D);
-    prep_kernel<<<cl.sum_blocks + blocks, 256, 0, cx.st>>>(ps, cl);
-    TEAM_LAUNCH_CHECK("prep_kernel");
+    TEAM_LAUNCH(prep_kernel, cl.sum_blocks + blocks, 256, 0, cx.st, ps, cl);
     return TEAM_OK;
 }
 
@@ -279,12 +278,13 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     if ((rc = prologue(cx, hw, 3, image_feat, text_feat, want_cls ? text_cls : nullptr, batch))) return rc;
     const int fill_rows = d.P + (d.Nsp - d.Ns);
     if (fill_rows > 0) {
-        fill_prompt_rows_kernel<<<fill_rows, 128, 0, cx.st>>>(plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S.f, w.S.h);
-        TEAM_LAUNCH_CHECK("fill_prompt_rows_kernel");
+        TEAM_LAUNCH(fill_prompt_rows_kernel, fill_rows, 128, 0, cx.st, plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S.f, w.S.h);
     }
     Wave wv;
     const Mat none{nullptr, nullptr, 0};
     auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
+    // outputs that are only ever GEMM operands: in BF16 mode the fp32 copy is not written at all
+    auto honly = [&](const Mat& m) { return cx.mode == TEAM_MODE_BF16 ? Mat{nullptr, m.h, m.ld} : m; };
     // ---- wave 1: every projection of the step (prototype rows, state table, image rows, text rows, class text)
     seg(wv.add(d.C, D, 0.f, fonly(w.Ztab, D), w.bsum[0]), false, w.protos, false, w.Wsum[0], D);
     seg(wv.add(10, D, 0.f, fonly(w.Ztab + (size_t)d.C * D, D), w.bsum[2]), false, w.E, false, w.Wsum[2], D);
@@ -300,12 +300,11 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         norm_add(nl, blocks, w.Ztab, w.S.f, w.S.h, w.invS, d.C);
         norm_add(nl, blocks, w.Ztab + (size_t)d.C * D, w.S.f + (size_t)d.M * D, w.S.h ? w.S.h + (size_t)d.M * D : nullptr, w.invS + d.M, 10);
         norm_add(nl, blocks, w.Xo.f, w.Xo.f, w.Xo.h, w.invo, d.B2);
-        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
-        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
+        TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
     }
     // ---- wave 2: q/k/v of the step rows and of the own rows against the packed [3D, D] weight
-    seg(wv.add(d.Nsp, 3 * D, 0.f, w.QKVs), false, w.S, false, w.Wqkv, D);
-    seg(wv.add(d.B2, 3 * D, 0.f, w.QKVo), false, w.Xo, false, w.Wqkv, D);
+    seg(wv.add(d.Nsp, 3 * D, 0.f, honly(w.QKVs)), false, w.S, false, w.Wqkv, D);
+    seg(wv.add(d.B2, 3 * D, 0.f, honly(w.QKVo)), false, w.Xo, false, w.Wqkv, D);
     RUN(wv);
     // ---- wave 3: fc folded into V, and every score matrix
     const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
@@ -316,19 +315,15 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
     RUN(wv);
-    table_prep_kernel<<<(d.Nsp + 7) / 8, 256, 0, cx.st>>>(w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
-    TEAM_LAUNCH_CHECK("table_prep_kernel");
-    attn_own_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.SQ.f, w.QKVo.f, state_ids, w.Aext.f, w.Aext.h, w.aown);
-    TEAM_LAUNCH_CHECK("attn_own_kernel");
+    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+    TEAM_LAUNCH(attn_own_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, state_ids, w.Aext.f, w.Aext.h, w.aown);
     // ---- wave 4: probabilities x (fc-space) values
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
     seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
     RUN(wv);
-    ln_own_fwd_kernel<<<(d.B2 + 7) / 8, 256, 0, cx.st>>>(d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
-    TEAM_LAUNCH_CHECK("ln_own_fwd_kernel");
+    TEAM_LAUNCH(ln_own_fwd_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
     const int tgrid = d.B < 6 * NUM_SMS ? d.B : 6 * NUM_SMS;
-    table_rows_fwd_kernel<<<tgrid, TQ_WARPS * 32, 0, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
-    TEAM_LAUNCH_CHECK("table_rows_fwd_kernel");
+    TEAM_LAUNCH(table_rows_fwd_kernel, tgrid, TQ_WARPS * 32, 0, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
     if (want_cls) {
         // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
         if ((rc = cosine_logits_launch(cx.st, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
@@ -353,25 +348,24 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     bind_inputs(cx, hw, image_feat, text_feat, nullptr);
     const TabOff to = tab_offsets(d);
     auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
+    const bool bf = cx.mode == TEAM_MODE_BF16;
+    auto honly = [&](const Mat& m) { return bf ? Mat{nullptr, m.h, m.ld} : m; };
     // ---- table-query rows (prototype / state outputs)
     const int tgrid = d.B < d.nctas ? d.B : d.nctas;
     const size_t tsm = table_bwd_smem_floats(d) * sizeof(float);
     TEAM_REQUIRE(tsm <= 200 * 1024, "head bwd: too many classes for the table-row kernel (%d)", d.C);
     TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    table_rows_bwd_kernel<<<tgrid, TQ_WARPS * 32, tsm, cx.st>>>(d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
-    TEAM_LAUNCH_CHECK("table_rows_bwd_kernel");
+    TEAM_LAUNCH(table_rows_bwd_kernel, tgrid, TQ_WARPS * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
     // ---- own query rows
     int ogrid = (d.B + 7) / 8;
     if (ogrid > NUM_SMS) ogrid = NUM_SMS;
-    ln_own_bwd_kernel<<<ogrid, 256, 0, cx.st>>>(d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo.f, w.dVFo.h, w.own_partials);
-    TEAM_LAUNCH_CHECK("ln_own_bwd_kernel");
+    TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, cx.st, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo.f, w.dVFo.h, w.own_partials);
     {
         ReduceJobs rj;
         rj.j[0] = ReduceJob{w.tab_partials, w.tab_reduced, to.len / 4, tgrid};
         rj.j[1] = ReduceJob{w.own_partials, w.own_reduced, OWN_PARTIAL_LEN / 4, ogrid};
         rj.blocks0 = (int)((to.len / 4 + RP_COLS - 1) / RP_COLS);
-        reduce_partials_kernel<<<rj.blocks0 + (OWN_PARTIAL_LEN / 4 + RP_COLS - 1) / RP_COLS, RP_COLS * RP_GROUPS, 0, cx.st>>>(rj);
-        TEAM_LAUNCH_CHECK("reduce_partials_kernel");
+        TEAM_LAUNCH(reduce_partials_kernel, rj.blocks0 + (OWN_PARTIAL_LEN / 4 + RP_COLS - 1) / RP_COLS, RP_COLS * RP_GROUPS, 0, cx.st, rj);
     }
     const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
     const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
@@ -381,33 +375,29 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     // ---- wave 5: R/G coefficient GEMM (A1^T GG + A23^T VFo), dA = dYo VFs^T (into SQ), dKo = dSK Qs
     seg(seg(wv.add(w.ldA, D, 0.f, fonly(w.RG, D)), true, w.A1, true, w.GG, d.B2), true, w.A23, true, w.VFo, d.B2);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, w.dYo, false, w.VFs, D);
-    seg(wv.add(d.B2, D, 0.f, dKo), false, w.dSK, true, Qs, d.Nsp);
+    seg(wv.add(d.B2, D, 0.f, fonly(dKo.f, dKo.ld)), false, w.dSK, true, Qs, d.Nsp);      // bf16 shadow: own_own_bwd_kernel
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.dVFs_a, D)), true, w.Aext, true, w.dYo, d.B2);
     RUN(wv);
-    expand_table_kernel<<<d.Nsp + EXP_SUM_BLOCKS, 128, 0, cx.st>>>(d, w.tab_reduced, w.own_reduced, w.RG, w.ldA / 2, w.NFt, w.S.f, w.VFs.f, hw->b_fc, w.Rfull, w.Gfull.f, w.Gfull.h, w.hfull, w.dTT.f, w.dVFs.f, w.dVFs_a, gr->ln_g, gr->ln_b, w.dbfc_parts);
-    TEAM_LAUNCH_CHECK("expand_table_kernel");
+    TEAM_LAUNCH(expand_table_kernel, d.Nsp + EXP_SUM_BLOCKS, 128, 0, cx.st, d, w.tab_reduced, w.own_reduced, w.RG, w.ldA / 2, w.NFt, w.S.f, w.VFs.f, hw->b_fc, w.Rfull, w.Gfull.f, w.Gfull.h, w.hfull, w.dTT.f, w.dVFs.f, w.dVFs_a, gr->ln_g, gr->ln_b, w.dbfc_parts);
     // ---- wave 6: G VFs^T, dVFs += Pt^T G
     seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.tmpNN, d.Nsp)), false, w.Gfull, false, w.VFs, D);
     seg(wv.add(d.Nsp, D, 1.f, w.dVFs), true, w.Pt, true, w.Gfull, d.Nsp);
     RUN(wv);
     {   // dS = Aext .* (dA - rowdot) / tau (in place);  dTT += Pt .* (G VFs^T - h) / tau
         const int64_t n4 = (int64_t)d.B2 * d.Nsp / 4;
-        ds_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, cx.st>>>(n4, d.Nsp / 4, w.Aext.f, w.rowdot, w.SQ.f, w.SQ.h);
-        TEAM_LAUNCH_CHECK("ds_kernel");
-        dtt_kernel<<<(d.Nsp * d.Nsp + 255) / 256, 256, 0, cx.st>>>(d.Nsp, d.M, w.Pt.f, w.tmpNN, w.hfull, w.dTT.f, w.dTT.h);
-        TEAM_LAUNCH_CHECK("dtt_kernel");
+        TEAM_LAUNCH(ds_kernel, (unsigned)((n4 + 255) / 256), 256, 0, cx.st, n4, d.Nsp / 4, w.Aext.f, w.rowdot, w.SQ.f, w.SQ.h, bf ? 0 : 1);
+        TEAM_LAUNCH(dtt_kernel, (d.Nsp * d.Nsp + 255) / 256, 256, 0, cx.st, d.Nsp, d.M, w.Pt.f, w.tmpNN, w.hfull, w.dTT.f, w.dTT.h);
     }
     const Mat& dS = w.SQ;
     // ---- wave 7: score gradients -> dQ/dK, fc folded into V, dWfc
-    seg(wv.add(d.B2, D, 0.f, dQo), false, dS, true, Ks, d.Nsp);                                                    // dQo = dS Ks
-    seg(seg(wv.add(d.Nsp, D, 0.f, dKs), true, dS, true, Qo, d.B2), true, w.dTT, true, Qs, d.Nsp);                  // dKs = dS^T Qo + dTT^T Qs
-    seg(seg(wv.add(d.Nsp, D, 0.f, dQs), true, w.dSK, true, Ko, d.B2), false, w.dTT, true, Ks, d.Nsp);              // dQs = dSK^T Ko + dTT Ks
-    seg(wv.add(d.B2, D, 0.f, dVo), false, w.dVFo, true, w.Wfc, D);                                                 // dVo = dVFo Wfc
-    seg(wv.add(d.Nsp, D, 0.f, dVs), false, w.dVFs, true, w.Wfc, D);
+    seg(wv.add(d.B2, D, 0.f, fonly(dQo.f, dQo.ld)), false, dS, true, Ks, d.Nsp);                                                    // dQo = dS Ks
+    seg(seg(wv.add(d.Nsp, D, 0.f, honly(dKs)), true, dS, true, Qo, d.B2), true, w.dTT, true, Qs, d.Nsp);                  // dKs = dS^T Qo + dTT^T Qs
+    seg(seg(wv.add(d.Nsp, D, 0.f, honly(dQs)), true, w.dSK, true, Ko, d.B2), false, w.dTT, true, Ks, d.Nsp);              // dQs = dSK^T Ko + dTT Ks
+    seg(wv.add(d.B2, D, 0.f, honly(dVo)), false, w.dVFo, true, w.Wfc, D);                                                 // dVo = dVFo Wfc
+    seg(wv.add(d.Nsp, D, 0.f, honly(dVs)), false, w.dVFs, true, w.Wfc, D);
     seg(seg(wv.add(D, D, 0.f, fonly(gr->w_fc, D)), true, w.dVFo, true, Vo, d.B2), true, w.dVFs, true, Vs, d.Nsp);  // dWfc = dVFo^T Vo + dVFs^T Vs
     RUN(wv);
-    own_own_bwd_kernel<<<(d.B + 7) / 8, 256, 0, cx.st>>>(d, w.QKVo.f, w.dsown, w.dQKVo.f, w.dQKVo.h);
-    TEAM_LAUNCH_CHECK("own_own_bwd_kernel");
+    TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, cx.st, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, w.dQKVo.h);
     // ---- wave 8: through the packed q/k/v projection
     seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
     seg(wv.add(d.Nsp, D, 1.f, fonly(w.Rfull, D)), false, w.dQKVs, true, w.Wqkv, 3 * D);                            // dS_rows (in Rfull)
@@ -439,8 +429,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         add(w.dXo.f, w.Xo.f, w.invo, w.dXo.f + (size_t)d.B * D, w.dXo.h ? w.dXo.h + (size_t)d.B * D : nullptr, d.B, d.B);   // dz1
         add(w.Rfull, w.S.f, w.invS, w.dZtab.f, w.dZtab.h, d.C, 0);                                                 // dzp
         add(w.Rfull, w.S.f, w.invS, w.dZtab.f + (size_t)d.C * D, w.dZtab.h ? w.dZtab.h + (size_t)d.C * D : nullptr, 10, d.M);   // dzs
-        nrm_bwd_kernel<<<blocks, 256, 0, cx.st>>>(nl);
-        TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
+        TEAM_LAUNCH(nrm_bwd_kernel, blocks, 256, 0, cx.st, nl);
     }
     // ---- wave 9: gradients of the newest projections and of the state embedding
     const Mat dz0 = sub(w.dXo, 0, 0), dz1 = sub(w.dXo, d.B, 0), dzp = sub(w.dZtab, 0, 0), dzs = sub(w.dZtab, d.C, 0);
@@ -456,8 +445,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         fa.b_img = gr->b_img; fa.b_text = gr->b_text; fa.b_state = gr->b_state;
         fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
         fa.dbfc_parts = w.dbfc_parts; fa.dbfc = gr->b_fc;
-        finish_bwd_kernel<<<4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st>>>(fa);
-        TEAM_LAUNCH_CHECK("finish_bwd_kernel");
+        TEAM_LAUNCH(finish_bwd_kernel, 4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st, fa);
     }
     return TEAM_OK;
 }
@@ -496,18 +484,15 @@ extern "C" int team_head_encode(const team_head_weights* hw, int mode, int which
         seg(wv.add(10, D, 0.f, fonly(w.Ztab, D), w.bsum[2]), false, w.E, false, w.Wsum[2], D);
         RUN(wv);
         norm_add(nl, blocks, w.Ztab, w.Ztab, nullptr, nullptr, 10);
-        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
-        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
-        gather_rows_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, cx.st>>>(w.Ztab, reinterpret_cast<const int64_t*>(x), n_rows, out);
-        TEAM_LAUNCH_CHECK("gather_rows_kernel");
+        TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
+        TEAM_LAUNCH(gather_rows_kernel, (unsigned)((n_rows + 7) / 8), 256, 0, cx.st, w.Ztab, reinterpret_cast<const int64_t*>(x), n_rows, out);
         return TEAM_OK;
     }
     seg(wv.add(n_rows, D, 0.f, fonly(out, D), w.bsum[k]), false, which == 3 ? w.protos : w.img, false, w.Wsum[k], D);
     RUN(wv);
     if (normalize) {
         norm_add(nl, blocks, out, out, nullptr, nullptr, n_rows);
-        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
-        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
+        TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
     }
     return TEAM_OK;
 }
@@ -543,8 +528,7 @@ extern "C" int team_head_encode_bwd(const team_head_weights* hw, int mode, int w
         nl.do_normalize = 1;
         int blocks = 0;
         norm_add(nl, blocks, w.Xo.f, w.Xo.f, nullptr, w.invo, n_rows);
-        rows_normalize_kernel<<<blocks, 256, 0, cx.st>>>(nl);
-        TEAM_LAUNCH_CHECK("rows_normalize_kernel");
+        TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
     }
     NrmList nl;
     memset(&nl, 0, sizeof(nl));
@@ -556,15 +540,13 @@ extern "C" int team_head_encode_bwd(const team_head_weights* hw, int mode, int w
     sg.rows_per_block = rpb; sg.blk0 = 0; sg.partial = w.nrm_partials;
     nl.n = 1;
     const int nblk = (int)((n_rows + rpb - 1) / rpb);
-    nrm_bwd_kernel<<<nblk, 256, 0, cx.st>>>(nl);
-    TEAM_LAUNCH_CHECK("nrm_bwd_kernel");
+    TEAM_LAUNCH(nrm_bwd_kernel, nblk, 256, 0, cx.st, nl);
     seg(wv.add(D, D, 0.f, fonly(g_w, D)), true, sub(w.dXo, 0, 0), true, w.img, n_rows);
     RUN(wv);
     FinishArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.part[0] = w.nrm_partials; fa.nblk[0] = nblk;
     fa.b_img = g_b;
-    finish_bwd_kernel<<<3, 512, 0, cx.st>>>(fa);
-    TEAM_LAUNCH_CHECK("finish_bwd_kernel");
+    TEAM_LAUNCH(finish_bwd_kernel, 3, 512, 0, cx.st, fa);
     return TEAM_OK;
 }

@@ -53,6 +53,8 @@ table_rows_bwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __r
                       float* __restrict__ dVFo, float* __restrict__ GG, __nv_bfloat16* __restrict__ GGh,
                       float* __restrict__ A1, __nv_bfloat16* __restrict__ A1h, float* __restrict__ A23,
                       __nv_bfloat16* __restrict__ A23h, int ldA, float* __restrict__ partials) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float tb_smem[];
     float* vec = tb_smem;                                     // [5][D]
     float* lnp = vec + 5 * D;                                 // [2][D]
@@ -124,6 +126,7 @@ table_rows_bwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __r
             mine.c_w = mine.a_i = mine.a_t = mine.a_s = 0.f; mine.r = 0;
             if (k0 + lane < nrows) mine = table_row_weights(d, b, warp + (k0 + lane) * TQ_WARPS, srow, SK, TT, mt, Zt);
             const int kn = min(32, nrows - k0);
+            float k_alpha = 0.f, k_beta = 0.f, k_mean = 0.f, k_m1 = 0.f, k_yy = 0.f, k_i = 0.f, k_t = 0.f, k_s = 0.f;
             for (int k = 0; k < kn; ++k) {
                 const TableRowW rw = shfl_row_weights(mine, k);
                 const int j = warp + (k0 + k) * TQ_WARPS;
@@ -163,37 +166,45 @@ table_rows_bwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __r
                     p_t += __shfl_xor_sync(0xffffffffu, p_t, o); p_s += __shfl_xor_sync(0xffffffffu, p_s, o);
                 }
                 if (is_proto) add_row(xs, xh); else st_row(xst, lane, xh);
-                if (lane == 0) {
-                    const int tr = is_proto ? j : d.C + sid;
-                    const float alpha = rstd, beta = rstd * rstd * m2, cw = rw.c_w;
-                    const float v_i = rw.a_i * (p_i - p_yy) * INV_TAU, v_t = rw.a_t * (p_t - p_yy) * INV_TAU;
-                    dSK[(size_t)b * d.Nsp + rw.r] = v_i;
-                    dSK[(size_t)(d.B + b) * d.Nsp + rw.r] = v_t;
-                    if (dSKh != nullptr) {
-                        dSKh[(size_t)b * d.Nsp + rw.r] = __float2bfloat16_rn(v_i);
-                        dSKh[(size_t)(d.B + b) * d.Nsp + rw.r] = __float2bfloat16_rn(v_t);
-                    }
-                    const size_t ra = (size_t)(is_proto ? b : d.B + b) * ldA;        // GG row this query's cotangent lives in
-                    const size_t r0 = (size_t)b * ldA, r1 = (size_t)(d.B + b) * ldA;
-                    const float c23i = -beta * rw.a_i, c23t = -beta * rw.a_t;
-                    A1[ra + tr] = alpha; A1[ra + gcol + tr] = cw * alpha;
-                    A23[r0 + tr] = c23i; A23[r0 + gcol + tr] = cw * c23i;
-                    A23[r1 + tr] = c23t; A23[r1 + gcol + tr] = cw * c23t;
-                    if (A1h != nullptr) {
-                        A1h[ra + tr] = __float2bfloat16_rn(alpha); A1h[ra + gcol + tr] = __float2bfloat16_rn(cw * alpha);
-                        A23h[r0 + tr] = __float2bfloat16_rn(c23i); A23h[r0 + gcol + tr] = __float2bfloat16_rn(cw * c23i);
-                        A23h[r1 + tr] = __float2bfloat16_rn(c23t); A23h[r1 + gcol + tr] = __float2bfloat16_rn(cw * c23t);
-                    }
-                    float* sc = scal + tr * TQ_NSC;
-                    const float e0 = alpha * m1, e1 = beta * cw, e2 = beta, e3 = beta * mean, e4 = beta * rw.a_s;
-                    sc[0] += e0; sc[1] += e1; sc[2] += e2; sc[3] += e3;
-                    sc[4] += cw * e0; sc[5] += cw * e1; sc[6] += cw * e2; sc[7] += cw * e3;
-                    sc[8] += cw * p_yy;
-                    sc[10 + sid] += rw.a_s * (p_s - p_yy) * INV_TAU;
-                    sc[20 + sid] += e4;
-                    sc[30 + sid] += cw * e4;
+                if (lane == k) {                              // lane k keeps the (warp-uniform) scalars of its row
+                    k_alpha = rstd; k_beta = rstd * rstd * m2; k_mean = mean; k_m1 = m1;
+                    k_yy = p_yy; k_i = p_i; k_t = p_t; k_s = p_s;
                 }
             }
+            // scalar outputs of the chunk's rows, one row per lane
+            if (lane < kn) {
+                const int j = warp + (k0 + lane) * TQ_WARPS;
+                const bool is_proto = j < d.C;
+                const int tr = is_proto ? j : d.C + sid;
+                const float cw = mine.c_w;
+                const float v_i = mine.a_i * (k_i - k_yy) * INV_TAU, v_t = mine.a_t * (k_t - k_yy) * INV_TAU;
+                dSK[(size_t)b * d.Nsp + mine.r] = v_i;
+                dSK[(size_t)(d.B + b) * d.Nsp + mine.r] = v_t;
+                if (dSKh != nullptr) {
+                    dSKh[(size_t)b * d.Nsp + mine.r] = __float2bfloat16_rn(v_i);
+                    dSKh[(size_t)(d.B + b) * d.Nsp + mine.r] = __float2bfloat16_rn(v_t);
+                }
+                const size_t ra = (size_t)(is_proto ? b : d.B + b) * ldA;        // GG row this query's cotangent lives in
+                const size_t r0 = (size_t)b * ldA, r1 = (size_t)(d.B + b) * ldA;
+                const float c23i = -k_beta * mine.a_i, c23t = -k_beta * mine.a_t;
+                A1[ra + tr] = k_alpha; A1[ra + gcol + tr] = cw * k_alpha;
+                A23[r0 + tr] = c23i; A23[r0 + gcol + tr] = cw * c23i;
+                A23[r1 + tr] = c23t; A23[r1 + gcol + tr] = cw * c23t;
+                if (A1h != nullptr) {
+                    A1h[ra + tr] = __float2bfloat16_rn(k_alpha); A1h[ra + gcol + tr] = __float2bfloat16_rn(cw * k_alpha);
+                    A23h[r0 + tr] = __float2bfloat16_rn(c23i); A23h[r0 + gcol + tr] = __float2bfloat16_rn(cw * c23i);
+                    A23h[r1 + tr] = __float2bfloat16_rn(c23t); A23h[r1 + gcol + tr] = __float2bfloat16_rn(cw * c23t);
+                }
+                float* sc = scal + tr * TQ_NSC;               // row tr is only ever touched by this lane's warp
+                const float e0 = k_alpha * k_m1, e1 = k_beta * cw, e2 = k_beta, e3 = k_beta * k_mean, e4 = k_beta * mine.a_s;
+                sc[0] += e0; sc[1] += e1; sc[2] += e2; sc[3] += e3;
+                sc[4] += cw * e0; sc[5] += cw * e1; sc[6] += cw * e2; sc[7] += cw * e3;
+                sc[8] += cw * k_yy;
+                sc[10 + sid] += mine.a_s * (k_s - k_yy) * INV_TAU;
+                sc[20 + sid] += e4;
+                sc[30 + sid] += cw * e4;
+            }
+            __syncwarp();
         }
         st_row(slots + (warp * 4 + 0) * D, lane, acc_i);
         st_row(slots + (warp * 4 + 1) * D, lane, acc_t);
@@ -246,6 +257,8 @@ constexpr int RP_COLS = 32;       // float4 columns per block
 constexpr int RP_GROUPS = 32;     // partial-interleaved groups per block
 __global__ void __launch_bounds__(RP_COLS * RP_GROUPS)
 reduce_partials_kernel(const __grid_constant__ ReduceJobs rj) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 fold[RP_GROUPS][RP_COLS];
     const bool second = (int)blockIdx.x >= rj.blocks0;
     const ReduceJob& job = rj.j[second ? 1 : 0];
@@ -308,6 +321,8 @@ expand_table_kernel(HeadDims d, const float* __restrict__ red, const float* __re
                     float* __restrict__ hfull, float* __restrict__ dTT, float* __restrict__ dVFs,
                     const float* __restrict__ dVFs_a, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     float* __restrict__ dbfc_parts) {
+    pdl_trigger();
+    pdl_wait();
     const TabOff off = tab_offsets(d);
     const int r = blockIdx.x, t = threadIdx.x;
     const float4 bf = reinterpret_cast<const float4*>(bfc)[t];
@@ -359,6 +374,8 @@ ln_own_bwd_kernel(HeadDims d, const float* __restrict__ Ybo, const float* __rest
                   const float* __restrict__ g_text, float* __restrict__ dYo, __nv_bfloat16* __restrict__ dYoh,
                   float* __restrict__ dXo, float* __restrict__ rowdot, float* __restrict__ dsown,
                   float* __restrict__ dVFo, __nv_bfloat16* __restrict__ dVFoh, float* __restrict__ partials) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float fold[3][8][D];        // 48 KB
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 dgam[4], dbet[4], dbf[4];
@@ -429,7 +446,9 @@ ln_own_bwd_kernel(HeadDims d, const float* __restrict__ Ybo, const float* __rest
 // dS = A .* (dA - rowdot) / tau, in place over dA (fp32 + bf16 shadow); 4 columns per thread (Nsp % 16 == 0)
 __global__ void __launch_bounds__(256)
 ds_kernel(int64_t n4, int Nsp4, const float* __restrict__ Aext, const float* __restrict__ rowdot, float* __restrict__ dA,
-          __nv_bfloat16* __restrict__ dSh) {
+          __nv_bfloat16* __restrict__ dSh, int write_f) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float rd = rowdot[i / Nsp4];
@@ -437,21 +456,24 @@ ds_kernel(int64_t n4, int Nsp4, const float* __restrict__ Aext, const float* __r
     float4 v = reinterpret_cast<const float4*>(dA)[i];
     v.x = a.x * (v.x - rd) * INV_TAU; v.y = a.y * (v.y - rd) * INV_TAU;
     v.z = a.z * (v.z - rd) * INV_TAU; v.w = a.w * (v.w - rd) * INV_TAU;
-    reinterpret_cast<float4*>(dA)[i] = v;
+    if (write_f) reinterpret_cast<float4*>(dA)[i] = v;
     if (dSh != nullptr) reinterpret_cast<uint2*>(dSh)[i] = pack_bf16x4(v);
 }
 
 // own-query x own-key score gradients (the 2x2 per-sample block)
 __global__ void __launch_bounds__(256)
-own_own_bwd_kernel(HeadDims d, const float* __restrict__ QKVo, const float* __restrict__ dsown,
-                   float* __restrict__ dQKVo, __nv_bfloat16* __restrict__ dQKVoh) {
+own_own_bwd_kernel(HeadDims d, const float* __restrict__ QKVo, const __nv_bfloat16* __restrict__ QKVoh,
+                   const float* __restrict__ dsown, float* __restrict__ dQKVo, __nv_bfloat16* __restrict__ dQKVoh) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (b >= d.B) return;
     const size_t r0 = (size_t)b * 3 * D, r1 = (size_t)(d.B + b) * 3 * D;
     float4 q0[4], q1[4], k0[4], k1[4], t[4];
-    ld_row(QKVo + r0, lane, q0); ld_row(QKVo + r1, lane, q1);
-    ld_row(QKVo + r0 + D, lane, k0); ld_row(QKVo + r1 + D, lane, k1);
+    const bool hq = QKVoh != nullptr;
+    ld_row_any(QKVo + r0, hq ? QKVoh + r0 : nullptr, lane, q0); ld_row_any(QKVo + r1, hq ? QKVoh + r1 : nullptr, lane, q1);
+    ld_row_any(QKVo + r0 + D, hq ? QKVoh + r0 + D : nullptr, lane, k0); ld_row_any(QKVo + r1 + D, hq ? QKVoh + r1 + D : nullptr, lane, k1);
     const float s00 = dsown[2 * b], s01 = dsown[2 * b + 1];
     const float s10 = dsown[2 * (d.B + b)], s11 = dsown[2 * (d.B + b) + 1];
     __nv_bfloat16* const hn = nullptr;
@@ -469,6 +491,8 @@ own_own_bwd_kernel(HeadDims d, const float* __restrict__ QKVo, const float* __re
 __global__ void __launch_bounds__(256)
 dtt_kernel(int Nsp, int M, const float* __restrict__ Pt, const float* __restrict__ GV, const float* __restrict__ h,
            float* __restrict__ dTT, __nv_bfloat16* __restrict__ dTTh) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Nsp * Nsp) return;
     const int r = i / Nsp, j = i % Nsp;
@@ -499,6 +523,8 @@ struct NrmList {
 };
 __global__ void __launch_bounds__(256)
 nrm_bwd_kernel(const __grid_constant__ NrmList nl) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float fold[8][D];
     int si = 0;
     for (int q = 1; q < nl.n; ++q)
@@ -555,6 +581,8 @@ struct FinishArgs {
 };
 __global__ void __launch_bounds__(512)
 finish_bwd_kernel(const __grid_constant__ FinishArgs fa) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 fold[4][128];
     const int t = threadIdx.x & 127, g = threadIdx.x >> 7;     // 4 groups of 128 threads, each a quarter of the partials
     if (blockIdx.x == 3) {

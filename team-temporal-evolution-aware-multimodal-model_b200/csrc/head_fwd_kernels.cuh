@@ -39,6 +39,8 @@ constexpr int PREP_SUM_BLOCKS_PER_W = D * D / 4 / 256;      // 256
 
 __global__ void __launch_bounds__(256)
 prep_kernel(const __grid_constant__ PrepSum ps, const __grid_constant__ ConvList cl) {
+    pdl_trigger();
+    pdl_wait();
     if ((int)blockIdx.x < cl.sum_blocks) {
         const int k = blockIdx.x / PREP_SUM_BLOCKS_PER_W;
         const int i = (blockIdx.x % PREP_SUM_BLOCKS_PER_W) * 256 + threadIdx.x;        // float4 index
@@ -100,6 +102,8 @@ struct NormList {
 };
 __global__ void __launch_bounds__(256)
 rows_normalize_kernel(const __grid_constant__ NormList nl) {
+    pdl_trigger();
+    pdl_wait();
     int si = 0;
     for (int q = 1; q < nl.n; ++q)
         if ((int)blockIdx.x >= nl.s[q].blk0) si = q;
@@ -123,6 +127,8 @@ rows_normalize_kernel(const __grid_constant__ NormList nl) {
 // out[r] = table[clamp(ids[r])]  (state-embedding style gather of 512-wide rows)
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, int64_t n_rows, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= n_rows) return;
@@ -135,6 +141,8 @@ gather_rows_kernel(const float* __restrict__ table, const int64_t* __restrict__ 
 __global__ void __launch_bounds__(128)
 fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float* __restrict__ S,
                         __nv_bfloat16* __restrict__ Sh) {
+    pdl_trigger();
+    pdl_wait();
     const int r = blockIdx.x;                    // 0 .. P + (Nsp-Ns) - 1
     const int P = prompts.n * ppt;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -154,6 +162,8 @@ fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float*
 __global__ void __launch_bounds__(256)
 table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restrict__ mt, float* __restrict__ Zt,
                   float* __restrict__ Pt, __nv_bfloat16* __restrict__ Pth) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= Nsp) return;
@@ -175,18 +185,21 @@ table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restric
 // keys: M shared step rows, the sample's state-table row (column M+sid), own image key, own text key.
 __global__ void __launch_bounds__(256)
 attn_own_kernel(HeadDims d, const float* __restrict__ SQ, const float* __restrict__ QKVo,
-                const int64_t* __restrict__ state_ids, float* __restrict__ Aext, __nv_bfloat16* __restrict__ Aexth,
+                const __nv_bfloat16* __restrict__ QKVoh, const int64_t* __restrict__ state_ids, float* __restrict__ Aext, __nv_bfloat16* __restrict__ Aexth,
                 float* __restrict__ aown) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= d.B2) return;
     const int b = row < d.B ? row : row - d.B;
     const int scol = d.M + clamp_state(state_ids[b]);
     float4 q[4], k[4];
-    ld_row(QKVo + (size_t)row * 3 * D, lane, q);
-    ld_row(QKVo + (size_t)b * 3 * D + D, lane, k);
+    const bool hq = QKVoh != nullptr;
+    ld_row_any(QKVo + (size_t)row * 3 * D, hq ? QKVoh + (size_t)row * 3 * D : nullptr, lane, q);
+    ld_row_any(QKVo + (size_t)b * 3 * D + D, hq ? QKVoh + (size_t)b * 3 * D + D : nullptr, lane, k);
     const float s_img = warp_sum(dot_part(q, k)) * INV_TAU;
-    ld_row(QKVo + (size_t)(d.B + b) * 3 * D + D, lane, k);
+    ld_row_any(QKVo + (size_t)(d.B + b) * 3 * D + D, hq ? QKVoh + (size_t)(d.B + b) * 3 * D + D : nullptr, lane, k);
     const float s_txt = warp_sum(dot_part(q, k)) * INV_TAU;
     float mx = fmaxf(s_img, s_txt);
     for (int j = lane; j < d.Nsp; j += 32)
@@ -215,6 +228,8 @@ ln_own_fwd_kernel(HeadDims d, float* __restrict__ Ybo, const float* __restrict__
                   const float* __restrict__ VFo, const float* __restrict__ Xo, const float* __restrict__ bfc,
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   float* __restrict__ out_image, float* __restrict__ out_text) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= d.B2) return;
@@ -281,6 +296,8 @@ table_rows_fwd_kernel(HeadDims d, const float* __restrict__ SK, const float* __r
                       const float* __restrict__ bfc, const float* __restrict__ gamma, const float* __restrict__ beta,
                       const int64_t* __restrict__ state_ids, float* __restrict__ out_proto,
                       float* __restrict__ out_state) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float slot[TQ_WARPS][D];          // 8 KB
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 bf[4];

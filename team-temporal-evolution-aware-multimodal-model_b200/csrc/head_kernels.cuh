@@ -22,6 +22,19 @@ __device__ __forceinline__ void st_row(float* p, int lane, const float4 (&v)[4])
 #pragma unroll
     for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(p)[lane + 32 * i] = v[i];
 }
+// 512-wide row from its bf16 shadow when there is one (BF16 mode: the fp32 copy of a pure GEMM operand is not
+// materialised), else from the fp32 buffer; same lane -> column mapping as ld_row
+__device__ __forceinline__ void ld_row_any(const float* f, const __nv_bfloat16* h, int lane, float4 (&v)[4]) {
+    if (h != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint2 u = reinterpret_cast<const uint2*>(h)[lane + 32 * i];
+            v[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+        }
+    } else {
+        ld_row(f, lane, v);
+    }
+}
 // bf16 shadow of a 512-wide row (same lane -> column mapping); p may be null (F32 mode)
 __device__ __forceinline__ void st_row_h(__nv_bfloat16* p, int lane, const float4 (&v)[4]) {
     if (p == nullptr) return;
