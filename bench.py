@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,10 +83,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Index of the next sample line: only lines read after mark() are reported."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        self.lines = self.lines[getattr(self, "first", 0):]
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -236,12 +240,27 @@ def run_team(a):
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
-        for i in range(warmup):
-            step(i)
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for i in range(warmup):
+            step(i)
+        barrier()
+        # nvidia-smi needs a few hundred ms before its first sample: keep the same load running (extra
+        # untimed warm-up steps) so that the samples are taken under load
+        def load(seconds):            # the step's kernels without the collective: loop counts may differ per rank
+            t_w, j = time.perf_counter(), 0
+            while time.perf_counter() - t_w < seconds:
+                for _ in range(50):
+                    if graphs is not None:
+                        graphs[j % rot].replay()
+                    else:
+                        eager_step(j)
+                    j += 1
+                torch.cuda.synchronize()
+        load(1.0)
+        if rank == 0:
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
@@ -250,7 +269,12 @@ def run_team(a):
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
+        # the timed region of K steps can be shorter than one nvidia-smi period: keep replaying the same
+        # steps (untimed) for 0.3 s so that the sampler sees the load the timed region ran under
+        load(0.3)
         clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None:
+            clocks["window"] = "timed region + 0.3 s of the same replayed steps (25 ms nvidia-smi period)"
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
