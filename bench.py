@@ -313,58 +313,47 @@ def run_team(a):
                 "how": f"CUDA events around each launch of the kernel on the launching stream, {nprof} extra eager steps "
                        "after the timed region"}
 
-    # ---- end to end through the public API, host buffers in, scalar out
+    # ---- end to end through the public API (head.HostBatchPipeline): every step copies its batch from pinned
+    # host memory (copy stream, double-buffered), replays the fwd+bwd graph, all-reduces the gradient bucket
+    # (N > 1) and copies the step's predictions back to the host, where they are compared with the labels
     e2e = None
     if not a.no_e2e:
-        names = ["projs_img", "projs_text", "projs_state"]
-        pe = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in pdev.items()}
-        for k in pe:      # freeze old tasks like freeze_projection_weight_new (utils/inc_net.py:494-507)
-            for n in names:
-                if k.startswith(n) and not k.startswith(f"{n}.{T - 1}."):
-                    pe[k].requires_grad_(False)
-            if k.startswith("context_prompts.") and k != f"context_prompts.{T - 1}":
-                pe[k].requires_grad_(False)
-            if "temporal_gcn" in k or k == "convnet.logit_scale":
-                pe[k].requires_grad_(False)
-        pack_e = head.HeadParamPack.from_state_dict(pe)
-        trainable = [v for v in pe.values() if v.requires_grad]
         nrot = min(rot, 16)
         h_img = [imgs[j].cpu().pin_memory() for j in range(nrot)]
         h_txt = [txts[j].cpu().pin_memory() for j in range(nrot)]
         h_sid = [sids[j].cpu().pin_memory() for j in range(nrot)]
-        h_lab = [synth.make_batch(B, C, step=rank * 1000 + j)["label"].pin_memory() for j in range(nrot)]
+        h_lab = [synth.make_batch(B, C, step=rank * 1000 + j)["label"] for j in range(nrot)]
+        after = (lambda r: dist.all_reduce(r.flat_grads)) if world > 1 else None
+        pipe = head.HostBatchPipeline(pack, protos, B, text_cls, mode=mode, depth=2, after_step=after)
+        correct = [0]
 
         def e2e_step(i):
             j = i % nrot
-            x = h_img[j].to(dev, non_blocking=True); t = h_txt[j].to(dev, non_blocking=True)
-            s = h_sid[j].to(dev, non_blocking=True); y = h_lab[j].to(dev, non_blocking=True)
-            for v in trainable:
-                v.grad = None
-            o = head.forward_tri_modal(pack_e, x, t, s, protos, text_cls=text_cls, mode=mode)
-            cj = cots[j]
-            torch.autograd.backward(o[:4], [cj[0], cj[1].view(B, 1, 512), cj[2], cj[3]])
-            if world > 1:
-                flat = torch.cat([v.grad.reshape(-1) for v in trainable])
-                dist.all_reduce(flat)
-            return int((o[5] == y).sum().item())          # D2H: number of correct predictions of the step
+            pred = pipe.submit(h_img[j], h_txt[j], h_sid[j], cots[j])
+            if pred is not None:
+                correct[0] += int((pred == h_lab[(i - 1) % nrot]).sum())      # host-side metric on the D2H result
 
-        with torch.cuda.stream(stream):
-            for i in range(3):
-                e2e_step(i)
-            barrier()
-            ksteps = min(a.steps, 30)
-            t0 = time.perf_counter()
-            for i in range(ksteps):
-                e2e_step(3 + i)
-            barrier()
-            dt = time.perf_counter() - t0
+        for i in range(4):
+            e2e_step(i)
+        pipe.drain()
+        barrier()
+        ksteps = a.steps
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            e2e_step(4 + i)
+        pipe.drain()
+        barrier()
+        dt = time.perf_counter() - t0
         if world > 1:
             tt = torch.tensor([dt], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": world * B * ksteps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": B * 512 * 4 * 2 + B * 8 * 2, "d2h_bytes_per_step": 8,
-               "steps": ksteps, "api": "team_b200.head.forward_tri_modal + torch.autograd.backward (pinned host inputs)"}
+               "h2d_bytes_per_step": pipe.h2d_bytes_per_step, "d2h_bytes_per_step": pipe.d2h_bytes_per_step,
+               "steps": ksteps, "ms_per_step": dt / ksteps * 1e3,
+               "api": "team_b200.head.HostBatchPipeline.submit: pinned host image/text/state batch -> H2D on a copy "
+                      "stream (2 slots) -> graph replay of fwd+bwd -> D2H of the predictions; wall clock over all steps "
+                      "incl. drain; cotangents device-resident (the loss is the caller's)"}
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

@@ -320,3 +320,97 @@ class HeadStepRunner:
     def step(self, image, text, sid, text_cls, cots):
         self.forward(image, text, sid, text_cls)
         self.backward(image, text, sid, cots)
+
+
+class HostBatchPipeline:
+    """Training-loop form of the step for batches that live in (pinned) HOST memory - what a DataLoader
+    hands to ``Learner._train_proj_with_replay`` (models/proof.py:403-451): every ``submit`` copies the
+    batch host->device on a copy stream, replays the captured fwd+bwd step (one CUDA graph per input
+    slot) on the compute stream and copies the step's predictions (``argmax`` of the classification
+    logits, models/proof.py:415-418) device->host.  ``depth`` input slots let the copy of step i+1 run
+    under the kernels of step i; ``submit`` returns the predictions of the step submitted ``depth - 1``
+    calls earlier (None while the pipeline fills), ``drain`` returns the outstanding ones.
+
+    The gradients of the most recent replay are in ``runner.flat_grads`` (the bucket a data-parallel
+    caller all-reduces); ``after_step`` - if given - is called on the compute stream right after each
+    replay (optimizer step / all-reduce), before the next replay can overwrite them."""
+
+    def __init__(self, pack: HeadParamPack, img_prototypes: torch.Tensor, batch: int, text_cls: torch.Tensor,
+                 mode: int = MODE_F32, depth: int = 2, after_step=None):
+        capi.require_device()
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        dev = pack.flat[0].device
+        self.dev, self.B, self.depth, self.after_step = dev, batch, depth, after_step
+        self.text_cls = _f32c(text_cls, dev)
+        self.runner = HeadStepRunner(pack, img_prototypes, batch, int(self.text_cls.shape[0]), mode)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.compute_stream = torch.cuda.Stream(device=dev)
+        mk = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append({
+                "image": mk(batch, capi.D), "text": mk(batch, capi.D), "state": mk(batch, dt=torch.int64),
+                "cots": [mk(batch, capi.D) for _ in range(4)],
+                "pred": torch.empty((batch,), dtype=torch.int64).pin_memory(),
+                "loaded": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(),
+                "graph": None, "busy": False})
+        self._n = 0
+        self.h2d_bytes_per_step = 0              # set by submit: bytes of the arguments that were host tensors
+        self.d2h_bytes_per_step = batch * 8
+
+    def _capture(self, sl):
+        r = self.runner
+        with torch.cuda.stream(self.compute_stream):
+            r.step(sl["image"], sl["text"], sl["state"], self.text_cls, sl["cots"])       # warm (lazy init outside capture)
+            self.compute_stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.compute_stream):
+                r.step(sl["image"], sl["text"], sl["state"], self.text_cls, sl["cots"])
+        sl["graph"] = g
+
+    def submit(self, image: torch.Tensor, text: torch.Tensor, state_ids: torch.Tensor, cotangents: Sequence[torch.Tensor]):
+        """Host tensors in (pinned for real overlap): image/text [B,512] fp32, state_ids [B] int64, four
+        cotangents [B,512] (the loss gradients w.r.t. the four feature outputs; the loss itself is the caller's -
+        cotangents that are already device tensors are copied device-to-device)."""
+        sl = self.slots[self._n % self.depth]
+        self.h2d_bytes_per_step = sum(t.numel() * t.element_size() for t in (image, text, state_ids, *cotangents)
+                                      if not t.is_cuda)
+        out = None
+        if sl["busy"]:
+            sl["done"].synchronize()
+            out = sl["pred"].clone()
+            sl["busy"] = False
+        with torch.cuda.stream(self.copy_stream):
+            if sl["graph"] is not None:
+                self.copy_stream.wait_event(sl["free"])          # the replay that last read this slot has finished
+            sl["image"].copy_(image, non_blocking=True)
+            sl["text"].copy_(text, non_blocking=True)
+            sl["state"].copy_(state_ids, non_blocking=True)
+            for d, s in zip(sl["cots"], cotangents):
+                d.copy_(s.reshape(self.B, capi.D), non_blocking=True)
+            sl["loaded"].record(self.copy_stream)
+        if sl["graph"] is None:
+            self.copy_stream.synchronize()
+            self._capture(sl)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(sl["loaded"])
+            sl["graph"].replay()
+            sl["free"].record(self.compute_stream)
+            if self.after_step is not None:
+                self.after_step(self.runner)
+            sl["pred"].copy_(self.runner.argmax, non_blocking=True)
+            sl["done"].record(self.compute_stream)
+        sl["busy"] = True
+        self._n += 1
+        return out
+
+    def drain(self) -> List[torch.Tensor]:
+        outs = []
+        for k in range(self.depth):
+            sl = self.slots[(self._n + k) % self.depth]
+            if sl["busy"]:
+                sl["done"].synchronize()
+                outs.append(sl["pred"].clone())
+                sl["busy"] = False
+        return outs

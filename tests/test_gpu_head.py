@@ -135,3 +135,41 @@ def test_head_bf16_mode(T, B):
     gref = torch.autograd.grad(ref[:4], [p64[n] for n in names], grad_outputs=[c.double() for c in cots])
     for n, gr in zip(names, gref):
         assert rel(grads[n], gr) < 1.5e-2, (n, rel(grads[n], gr))
+
+
+def test_host_batch_pipeline_matches_direct_step():
+    """HostBatchPipeline (pinned host batches, copy stream, graph replay, D2H predictions) gives the same
+    predictions and the same gradient bucket as a direct HeadStepRunner step on the same data."""
+    from team_b200 import head
+    dev = torch.device("cuda")
+    T, B = 3, 40
+    C = 2 * T
+    params = synth.make_params(T, seed=5)
+    pack = head.HeadParamPack.from_state_dict({k: v.to(dev) for k, v in params.items()})
+    protos = synth.make_prototypes(C, seed=3).to(dev)
+    text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
+    batches = [synth.make_batch(B, C, step=s) for s in range(5)]
+    cots = [[c.reshape(B, 512) for c in synth.make_cotangents(B, step=s)] for s in range(5)]
+    ref = head.HeadStepRunner(pack, protos, B, C, head.MODE_F32)
+    want_pred, want_grad = [], []
+    for b, c in zip(batches, cots):
+        ref.step(b["image"].to(dev), b["text"].to(dev), b["state"].to(dev), text_cls, [x.to(dev) for x in c])
+        torch.cuda.synchronize()
+        want_pred.append(ref.argmax.cpu().clone()); want_grad.append(ref.flat_grads.cpu().clone())
+    seen_grads = []
+    pipe = head.HostBatchPipeline(pack, protos, B, text_cls, mode=head.MODE_F32, depth=2,
+                                  after_step=lambda r: seen_grads.append(r.flat_grads.clone()))
+    got = []
+    for b, c in zip(batches, cots):
+        out = pipe.submit(b["image"].pin_memory(), b["text"].pin_memory(), b["state"].pin_memory(),
+                          [x.pin_memory() for x in c])
+        if out is not None:
+            got.append(out)
+    got += pipe.drain()
+    assert len(got) == 5
+    assert pipe.h2d_bytes_per_step == B * 512 * 4 * 6 + B * 8 and pipe.d2h_bytes_per_step == B * 8
+    for g, w in zip(got, want_pred):
+        assert torch.equal(g, w)
+    torch.cuda.synchronize()
+    for g, w in zip(seen_grads, want_grad):
+        assert torch.equal(g.cpu(), w)          # same kernels, same order: bit-identical
