@@ -174,6 +174,20 @@ int team_head_encode_bwd(const team_head_weights* w, int mode, int which, const 
                          int normalize, const float* g_out, float* g_w, float* g_b,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* PROOF fusion forward.
+ * Replaces: Proof_Net.forward                     utils/inc_net.py:436-463
+ *           Proof_Net.forward_transformer         utils/inc_net.py:465-492 (transformer=True; inputs_encoded = 1:
+ *           image_feat / text_feat are then rows already produced by encode_image / encode_text(normalize=True))
+ * tokens of sample b = [image_b | num_text class-text rows | C prototype rows | P prompt rows].
+ * image_feat [B,512], text_feat [num_text,512] fp32.  Outputs (fp32): out_image [B,512],
+ * out_text [num_text,512] and out_proto [C,512] = means over the batch of the text / prototype rows.
+ * Forward only (the TEAM learner never calls this path).
+ * workspace: team_head_workspace_bytes(batch, num_text + C, P, num_text, mode). */
+int team_head_proof_fwd(const team_head_weights* w, int mode, int64_t batch, const float* image_feat,
+                        const float* text_feat, int64_t num_text, int inputs_encoded,
+                        float* out_image, float* out_text, float* out_proto,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ temporal GCN + state distances
  * Replaces: TemporalStateGCN.forward / TemporalGCNBlock.forward   models/dynamic_modal_graph.py:239-337
  *           (called under no_grad from InsectLifecycleModel.evolve_and_update, models/state_evolution.py:326-327).

@@ -125,6 +125,8 @@ def _declare(lib):
                                           C.POINTER(HeadGrads), vp, sz, vp]
         lib.team_head_encode.restype = i32
         lib.team_head_encode.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, sz, vp]
+        lib.team_head_proof_fwd.restype = i32
+        lib.team_head_proof_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, i32, vp, vp, vp, vp, sz, vp]
         lib.team_head_encode_bwd.restype = i32
         lib.team_head_encode_bwd.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, vp, vp, sz, vp]
 

@@ -1,7 +1,7 @@
 // Host orchestration + C ABI of the fusion head: team_head_tri_fwd / team_head_tri_bwd /
 // team_head_encode (include/team_b200.h).  Every launch goes to the caller's stream, there is
 // no synchronisation and no allocation, so a whole step can be captured into a CUDA graph.
-#include "head_bwd_kernels.cuh"
+#include "head_proof_kernels.cuh"
 #include "gemm_tc.cuh"
 
 namespace team {
@@ -200,7 +200,7 @@ static int prologue(HeadCtx& cx, const team_head_weights* hw, int nsum, const fl
     if (hw->w_k) conv_add(cl, blocks, hw->w_k, w.Wqkv.f + (size_t)D * D, w.Wqkv.h ? w.Wqkv.h + (size_t)D * D : nullptr, (int64_t)D * D);
     if (hw->w_v) conv_add(cl, blocks, hw->w_v, w.Wqkv.f + (size_t)2 * D * D, w.Wqkv.h ? w.Wqkv.h + (size_t)2 * D * D : nullptr, (int64_t)D * D);
     if (hw->w_fc) conv_add(cl, blocks, hw->w_fc, nullptr, w.Wfc.h, (int64_t)D * D);
-    if (hw->prototypes) conv_add(cl, blocks, hw->prototypes, nullptr, w.protos.h, (int64_t)d.C * D);
+    if (hw->prototypes) conv_add(cl, blocks, hw->prototypes, nullptr, w.protos.h, (int64_t)hw->num_classes * D);
     if (hw->state_emb) conv_add(cl, blocks, hw->state_emb, nullptr, w.E.h, (int64_t)10 * D);
     if (image) conv_add(cl, blocks, image, nullptr, w.img.h, batch * D);
     if (text) conv_add(cl, blocks, text, nullptr, w.txt.h, batch * D);
@@ -447,6 +447,102 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         fa.dbfc_parts = w.dbfc_parts; fa.dbfc = gr->b_fc;
         TEAM_LAUNCH(finish_bwd_kernel, 4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st, fa);
     }
+    return TEAM_OK;
+}
+
+// PROOF fusion forward (Proof_Net.forward, utils/inc_net.py:436-463; forward_transformer with transformer=True,
+// :465-492, when inputs_encoded != 0: image_feat / text_feat are then the already projected + normalised rows).
+// 14 launches.  workspace: team_head_workspace_bytes(batch, num_text + C, P, num_text, mode).
+extern "C" int team_head_proof_fwd(const team_head_weights* hw, int mode, int64_t batch, const float* image_feat,
+                                   const float* text_feat, int64_t num_text, int inputs_encoded, float* out_image,
+                                   float* out_text, float* out_proto, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+    HeadCtx cx;
+    int rc = validate(hw, mode, batch);
+    if (rc) return rc;
+    TEAM_REQUIRE(image_feat && text_feat && out_image && out_text && out_proto, "head proof fwd: null pointer");
+    TEAM_REQUIRE(num_text >= 1 && num_text <= 2048, "head proof fwd: num_text %lld out of range", (long long)num_text);
+    TEAM_REQUIRE(hw->w_q && hw->w_k && hw->w_v && hw->w_fc && hw->b_fc && hw->ln_g && hw->ln_b && hw->prototypes, "head proof fwd: null weight");
+    const int Tn = (int)num_text, C = hw->num_classes, P = hw->num_tasks * hw->prompts_per_task;
+    const int R = Tn + C;                                  // shared rows whose outputs are returned (batch means)
+    cx.st = (cudaStream_t)stream;
+    cx.mode = mode;
+    cx.d = head_dims(batch, R, P, Tn);                     // "classes" of the layout = text rows + prototype rows
+    head_plan(cx.d, mode, workspace, &cx.w);
+    if (workspace == nullptr || workspace_bytes < cx.w.total_bytes) {
+        set_error("head proof fwd: workspace %zu < %zu bytes", workspace_bytes, cx.w.total_bytes);
+        return TEAM_EWORKSPACE;
+    }
+    TEAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "head: workspace must be 256-byte aligned");
+    const HeadDims& d = cx.d;
+    HeadWS& w = cx.w;
+    const int M = d.M, B = d.B;                            // M = Tn + C + P shared keys; the 10 state rows of the layout stay zero
+    bind_inputs(cx, hw, image_feat, nullptr, text_feat);
+    {
+        team_head_weights tmp = *hw;
+        tmp.state_emb = nullptr;
+        if ((rc = prologue(cx, &tmp, 2, inputs_encoded ? nullptr : image_feat, nullptr, inputs_encoded ? nullptr : text_feat, batch))) return rc;
+    }
+    if (inputs_encoded) {                                  // rows arrive projected + normalised: straight into Xo / S
+        PrepSum ps;
+        memset(&ps, 0, sizeof(ps));
+        ConvList cl;
+        memset(&cl, 0, sizeof(cl));
+        int blocks = 0;
+        conv_add(cl, blocks, image_feat, w.Xo.f, w.Xo.h, batch * D);
+        conv_add(cl, blocks, text_feat, w.S.f, w.S.h, (int64_t)Tn * D);
+        TEAM_LAUNCH(prep_kernel, blocks, 256, 0, cx.st, ps, cl);
+    }
+    TEAM_LAUNCH(fill_prompt_rows_kernel, P + (d.Nsp - M), 128, 0, cx.st, plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, R, M, d.Nsp, w.S.f, w.S.h);
+    Wave wv;
+    auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
+    auto honly = [&](const Mat& m) { return cx.mode == TEAM_MODE_BF16 ? Mat{nullptr, m.h, m.ld} : m; };
+    // ---- wave 1: projections (class-text rows, prototype rows, image rows)
+    if (!inputs_encoded) seg(wv.add(Tn, D, 0.f, fonly(w.Ztab, D), w.bsum[1]), false, w.tcls, false, w.Wsum[1], D);
+    seg(wv.add(C, D, 0.f, fonly(w.Ztab + (size_t)Tn * D, D), w.bsum[0]), false, w.protos, false, w.Wsum[0], D);
+    if (!inputs_encoded) seg(wv.add(B, D, 0.f, fonly(w.Xo.f, D), w.bsum[0]), false, w.img, false, w.Wsum[0], D);
+    RUN(wv);
+    {
+        NormList nl;
+        memset(&nl, 0, sizeof(nl));
+        nl.do_normalize = 1;
+        int blocks = 0;
+        if (!inputs_encoded) {
+            norm_add(nl, blocks, w.Ztab, w.S.f, w.S.h, w.invS, R);
+            norm_add(nl, blocks, w.Xo.f, w.Xo.f, w.Xo.h, w.invo, B);
+        } else {
+            norm_add(nl, blocks, w.Ztab + (size_t)Tn * D, w.S.f + (size_t)Tn * D, w.S.h ? w.S.h + (size_t)Tn * D : nullptr, w.invS + Tn, C);
+        }
+        TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
+    }
+    // ---- wave 2: q/k/v of the shared rows and of the image rows
+    seg(wv.add(d.Nsp, 3 * D, 0.f, honly(w.QKVs)), false, w.S, false, w.Wqkv, D);
+    seg(wv.add(B, 3 * D, 0.f, honly(w.QKVo)), false, w.Xo, false, w.Wqkv, D);
+    RUN(wv);
+    // ---- wave 3: fc folded into V; score matrices
+    const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
+    const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
+    seg(wv.add(d.Nsp, D, 0.f, w.VFs), false, Vs, false, w.Wfc, D);
+    seg(wv.add(B, D, 0.f, fonly(w.VFo.f, D)), false, Vo, false, w.Wfc, D);
+    seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.TT, d.Nsp)), false, Qs, false, Ks, D);
+    seg(wv.add(B, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
+    seg(wv.add(B, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
+    RUN(wv);
+    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+    TEAM_LAUNCH(proof_attn_own_kernel, (B + 7) / 8, 256, 0, cx.st, B, M, d.Nsp, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, w.Aext.f, w.Aext.h, w.aown);
+    // ---- wave 4: probabilities x (fc-space) values
+    seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
+    seg(wv.add(B, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
+    RUN(wv);
+    TEAM_LAUNCH(proof_ln_own_fwd_kernel, (B + 7) / 8, 256, 0, cx.st, B, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image);
+    // ---- shared-row queries: per-CTA sums over a contiguous sample block, then the fixed-order batch mean
+    int per_cta = (B + 2 * NUM_SMS - 1) / (2 * NUM_SMS);
+    if (per_cta < 4) per_cta = 4;
+    const int nparts = (B + per_cta - 1) / per_cta;
+    TEAM_REQUIRE((size_t)nparts * R * D * sizeof(float) <= w.gemm_ws_bytes, "head proof fwd: partial buffer too small");
+    float* partials = reinterpret_cast<float*>(w.gemm_ws);
+    TEAM_LAUNCH(proof_table_rows_fwd_kernel, nparts, PT_WARPS * 32, 0, cx.st, B, R, d.Nsp, per_cta, w.SK, w.mt, w.Zt, w.NFt, w.VFo.f, w.S.f, hw->b_fc, partials);
+    TEAM_LAUNCH(proof_finalize_kernel, R, 512, 0, cx.st, partials, nparts, R, Tn, 1.0f / (float)B, hw->ln_g, hw->ln_b, out_text, out_proto);
     return TEAM_OK;
 }
 

@@ -182,6 +182,33 @@ def encode(pack: HeadParamPack, which: str, x: Optional[torch.Tensor], img_proto
     return out
 
 
+def forward_proof(pack: HeadParamPack, image: torch.Tensor, text: torch.Tensor, img_prototypes: torch.Tensor, *,
+                  inputs_encoded: bool = False, mode: int = MODE_F32):
+    """PROOF fusion forward - ``Proof_Net.forward`` (utils/inc_net.py:436-463) on post-CLIP features, or
+    ``forward_transformer(..., transformer=True)`` (:465-492) when ``inputs_encoded`` (rows already projected +
+    normalised).  Returns (image [B,512], text [Tn,512] batch mean, proto [C,512] batch mean).  No autograd."""
+    capi.require_device()
+    if not image.is_cuda:
+        raise capi.TeamB200Error("forward_proof needs CUDA tensors (no CPU fallback)")
+    dev = image.device
+    image, text, protos = _f32c(image, dev), _f32c(text, dev), _f32c(img_prototypes, dev)
+    B, Tn = image.shape[0], text.shape[0]
+    if image.shape != (B, capi.D) or text.shape != (Tn, capi.D) or B < 1 or Tn < 1:
+        raise ValueError("image must be [B,512] and text [num_text,512]")
+    flat = [_f32c(p, dev) for p in pack.flat]
+    hw = _fill_weights(pack.T, pack.ppt, flat, protos)
+    L = capi.lib()
+    nbytes = L.team_head_workspace_bytes(B, Tn + hw.num_classes, pack.T * pack.ppt, Tn, mode)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    o_img = torch.empty((B, capi.D), dtype=torch.float32, device=dev)
+    o_txt = torch.empty((Tn, capi.D), dtype=torch.float32, device=dev)
+    o_pro = torch.empty((hw.num_classes, capi.D), dtype=torch.float32, device=dev)
+    capi.check(L.team_head_proof_fwd(C.byref(hw), mode, B, image.data_ptr(), text.data_ptr(), Tn, int(inputs_encoded),
+                                     o_img.data_ptr(), o_txt.data_ptr(), o_pro.data_ptr(), ws.data_ptr(), nbytes,
+                                     _stream_ptr()), "team_head_proof_fwd")
+    return o_img, o_txt, o_pro
+
+
 class _EncodeFn(torch.autograd.Function):
     """encode_image / encode_text with autograd to the projections (the ClipLoss branch of the training
     step, models/proof.py:428-431).  No gradient flows into the (frozen-backbone) features."""

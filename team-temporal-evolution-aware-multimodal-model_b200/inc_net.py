@@ -306,10 +306,25 @@ class Proof_Net(nn.Module):
             return ops.cosine_logits(xi, ti, want_argmax=True)
 
     def forward(self, image, text):
-        raise NotImplementedError("PROOF fusion forward (utils/inc_net.py:436-463) is never called by the TEAM learner; "
-                                  "only its oracle + golden vector exist (DESIGN.md section 1, row a8)")
+        """PROOF fusion (utils/inc_net.py:436-463): (image [B,512], text [Tn,512] batch mean, exp(logit_scale),
+        proto [C,512] batch mean).  Forward only - the TEAM learner never trains through this path."""
+        img = self.convnet.encode_image(image.to(self._device))
+        if isinstance(text, list):
+            text = self.tokenizer(text)
+        txt = self.convnet.encode_text(text.to(self._device) if torch.is_tensor(text) else text)
+        with torch.no_grad():
+            o = head.forward_proof(self._pack(), img, txt, self._protos(), mode=self.team_mode)
+        return o[0], o[1], self.convnet.logit_scale.exp(), o[2]
 
-    forward_transformer = forward
+    def forward_transformer(self, image_features, text_features, transformer=False):
+        """utils/inc_net.py:465-492: the same fusion on rows the caller already encoded (encode_image /
+        encode_text with normalize=True); transformer=False returns the inputs and the encoded prototypes."""
+        if not transformer:
+            return image_features, text_features, self.convnet.logit_scale.exp(), self.encode_prototpyes(normalize=True)
+        with torch.no_grad():
+            o = head.forward_proof(self._pack(), image_features.to(self._device), text_features.to(self._device),
+                                   self._protos(), inputs_encoded=True, mode=self.team_mode)
+        return o[0], o[1], self.convnet.logit_scale.exp(), o[2]
 
     # ------------------------------------------------------------------ prototypes / graph
     def evolve_state_prototypes(self):
