@@ -11,7 +11,8 @@ head fwd+bwd, 10 incremental tasks (C=20 classes, P=100 prompts, L=123 tokens), 
 per GPU, synthetic IIMinsects202-shaped 512-d features, reference-initialised weights.
 One step = no-grad classification logits (models/proof.py:415-418) + forward_tri_modal
 (:424-425) + VJP with fixed N(0,1) cotangents on the four feature outputs (stands for :444),
-plus, for N>1, the NCCL all-reduce of the flat 1.85 M-element head-gradient bucket.
+plus, for N>1, the NCCL all-reduce of the flat 1.85 M-element head-gradient buffer in three buckets
+(w_fc | w_q,w_k,w_v | rest) started on a side stream as the backward finishes each of them.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -47,6 +48,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl", "nccl-buckets"],
+                    help="N>1 gradient exchange: own NVLink peer-memory kernel inside the step graph (default), one NCCL "
+                         "all-reduce after the step, or three NCCL buckets overlapped with the backward")
     return ap.parse_args()
 
 
@@ -199,7 +203,14 @@ def run_team(a):
         c = synth.make_cotangents(B, step=rank * 1000 + i)
         cots.append([c[0].to(dev), c[1].reshape(B, 512).to(dev), c[2].to(dev), c[3].to(dev)])
     text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
-    runner = head.HeadStepRunner(pack, protos, B, C, mode)
+    # N > 1: the gradient buffer lives in symmetric memory and is summed over the ranks by ONE kernel over NVLink
+    # peer memory, captured at the end of the step's graph (--comm nccl: torch.distributed all-reduce after the replay)
+    peer = None
+    if world > 1 and a.comm == "peer":
+        from team_b200 import parallel
+        peer = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev)
+    runner = head.HeadStepRunner(pack, protos, B, C, mode, grad_events=world > 1 and a.comm == "nccl-buckets",
+                                 grad_buffer=peer.buffer if peer is not None else None)
     stream = torch.cuda.Stream(device=dev)
 
     def eager_step(i):
@@ -223,6 +234,8 @@ def run_team(a):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
                     runner.step(imgs[j], txts[j], sids[j], text_cls, cots[j])
+                    if peer is not None:
+                        peer()
                 graphs.append(g)
         torch.cuda.synchronize()
 
@@ -231,8 +244,10 @@ def run_team(a):
             graphs[i % rot].replay()
         else:
             eager_step(i)
-        if world > 1:
-            dist.all_reduce(runner.flat_grads)        # gradient bucket: the only per-step collective
+            if peer is not None:
+                peer()
+        if world > 1 and peer is None:
+            runner.allreduce_grads()                  # NCCL: the only per-step collective
 
     def barrier():
         if world > 1:
@@ -248,16 +263,17 @@ def run_team(a):
         barrier()
         # nvidia-smi needs a few hundred ms before its first sample: keep the same load running (extra
         # untimed warm-up steps) so that the samples are taken under load
-        def load(seconds):            # the step's kernels without the collective: loop counts may differ per rank
-            t_w, j = time.perf_counter(), 0
-            while time.perf_counter() - t_w < seconds:
-                for _ in range(50):
-                    if graphs is not None:
-                        graphs[j % rot].replay()
-                    else:
-                        eager_step(j)
-                    j += 1
-                torch.cuda.synchronize()
+        def load(seconds):            # keep the GPU under the step's load; the SAME replay count on every rank
+            t_w = time.perf_counter()         # (the peer all-reduce inside the graphs is a collective)
+            for j in range(20):
+                step(j)
+            torch.cuda.synchronize()
+            n = torch.tensor([max(1, int(seconds / max((time.perf_counter() - t_w) / 20, 2e-5)))], device=dev)
+            if world > 1:
+                dist.broadcast(n, 0)
+            for j in range(int(n.item())):
+                step(j)
+            torch.cuda.synchronize()
         load(1.0)
         if rank == 0:
             sampler.mark()
@@ -323,8 +339,11 @@ def run_team(a):
         h_txt = [txts[j].cpu().pin_memory() for j in range(nrot)]
         h_sid = [sids[j].cpu().pin_memory() for j in range(nrot)]
         h_lab = [synth.make_batch(B, C, step=rank * 1000 + j)["label"] for j in range(nrot)]
-        after = (lambda r: dist.all_reduce(r.flat_grads)) if world > 1 else None
-        pipe = head.HostBatchPipeline(pack, protos, B, text_cls, mode=mode, depth=2, after_step=after)
+        after = (lambda r: r.allreduce_grads()) if world > 1 and peer is None else None
+        peer2 = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev) if peer is not None else None
+        pipe = head.HostBatchPipeline(pack, protos, B, text_cls, mode=mode, depth=2, after_step=after,
+                                      grad_events=world > 1 and a.comm == "nccl-buckets",
+                                      grad_buffer=peer2.buffer if peer2 is not None else None, in_graph=peer2)
         correct = [0]
 
         def e2e_step(i):
@@ -365,12 +384,12 @@ def run_team(a):
                 "dtype": a.mode, "data": "synthetic",
                 "config": {"workload": f"TEAM/PROOF head fwd+bwd (BASELINE configs[2]): T={T} tasks, C={C} classes, "
                                        f"P={10 * T} prompts, L={3 + 12 * T} tokens, batch {B} per GPU",
-                           "tasks": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "tasks": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_exchange": (a.comm if world > 1 else None),
                            "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2",
                            "cuda_graphs": graphs is not None,
                            "alg_flops_per_sample_survey": 55.07e6},
                 "roofline": roof, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches_per_step) * a.steps,
+                "gpu_launches": (int(launches_per_step) + (1 if peer is not None else 0)) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -132,6 +132,12 @@ typedef struct team_head_grads {            /* all OVERWRITTEN by team_head_tri_
     float* w_q; float* w_k; float* w_v;
     float* w_fc; float* b_fc;
     float* ln_g; float* ln_b;
+    /* Optional cudaEvent_t handles (NULL = none) recorded on the call's stream as soon as a group of gradients is
+     * final, so a data-parallel caller can start their all-reduce on another stream while the rest of the backward
+     * still runs: ev_w_fc after w_fc, ev_w_qkv after w_q / w_k / w_v (everything else is final when the call's last
+     * kernel ends).  Under stream capture they become external event-record nodes (cudaEventRecordExternal). */
+    void* ev_w_fc;
+    void* ev_w_qkv;
 } team_head_grads;
 
 size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, int32_t num_prompts,
@@ -187,6 +193,19 @@ int team_head_proof_fwd(const team_head_weights* w, int mode, int64_t batch, con
                         const float* text_feat, int64_t num_text, int inputs_encoded,
                         float* out_image, float* out_text, float* out_proto,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ gradient all-reduce over NVLink peer memory
+ * The reference has no working multi-GPU path (its nn.DataParallel wrap crashes, models/proof.py:312-313 vs :248);
+ * this is the exchange step of the data-parallel training step (the sum autograd would produce on one big batch,
+ * models/proof.py:444).  In-place sum of n fp32 values: bufs[r] / flags[r] (r < world, HOST arrays of device
+ * pointers) are every rank's buffer and flag array as mapped on THIS device (symmetric memory); flags are
+ * team_peer_allreduce_flag_bytes() bytes each, zeroed once before the first call.  One kernel, two-shot, summed in
+ * rank order (bit-identical on all ranks); every rank must make the matching call.  n % 4 == 0.
+ * multicast: NVLS multicast mapping of the same buffers (NULL = none): the switch then adds (multimem.ld_reduce)
+ * and replicates (multimem.st); the sum order is the switch's, still identical on all ranks. */
+size_t team_peer_allreduce_flag_bytes(void);
+int team_peer_allreduce_f32(void* const* bufs, void* const* flags, void* multicast, int32_t rank, int32_t world,
+                            int64_t n, void* stream);
 
 /* ------------------------------------------------------------------ temporal GCN + state distances
  * Replaces: TemporalStateGCN.forward / TemporalGCNBlock.forward   models/dynamic_modal_graph.py:239-337

@@ -43,7 +43,7 @@ class HeadWeights(C.Structure):
 class HeadGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts", "state_emb",
-                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b")]
+                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "ev_w_fc", "ev_w_qkv")]
 
 
 class TgcnBlock(C.Structure):
@@ -125,6 +125,10 @@ def _declare(lib):
                                           C.POINTER(HeadGrads), vp, sz, vp]
         lib.team_head_encode.restype = i32
         lib.team_head_encode.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, sz, vp]
+        lib.team_peer_allreduce_flag_bytes.restype = sz
+        lib.team_peer_allreduce_flag_bytes.argtypes = []
+        lib.team_peer_allreduce_f32.restype = i32
+        lib.team_peer_allreduce_f32.argtypes = [C.POINTER(vp), C.POINTER(vp), vp, i32, i32, i64, vp]
         lib.team_head_proof_fwd.restype = i32
         lib.team_head_proof_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, i32, vp, vp, vp, vp, sz, vp]
         lib.team_head_encode_bwd.restype = i32

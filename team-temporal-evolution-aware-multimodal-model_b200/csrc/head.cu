@@ -235,6 +235,15 @@ static int setup(HeadCtx& cx, const team_head_weights* hw, int mode, int64_t bat
     return TEAM_OK;
 }
 
+// gradient-ready event (team_head_grads.ev_*): an external record node under capture, a plain record otherwise
+static int record_ready(cudaStream_t st, void* ev) {
+    if (ev == nullptr) return TEAM_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    TEAM_CUDA_CHECK(cudaStreamIsCapturing(st, &cs));
+    TEAM_CUDA_CHECK(cudaEventRecordWithFlags((cudaEvent_t)ev, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    return TEAM_OK;
+}
+
 static void norm_add(NormList& nl, int& blocks, const float* Z, float* X, __nv_bfloat16* Xh, float* inv, int64_t rows) {
     if (rows <= 0) return;
     NormSeg& s = nl.s[nl.n++];
@@ -397,6 +406,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.Nsp, D, 0.f, honly(dVs)), false, w.dVFs, true, w.Wfc, D);
     seg(seg(wv.add(D, D, 0.f, fonly(gr->w_fc, D)), true, w.dVFo, true, Vo, d.B2), true, w.dVFs, true, Vs, d.Nsp);  // dWfc = dVFo^T Vo + dVFs^T Vs
     RUN(wv);
+    if ((rc = record_ready(cx.st, gr->ev_w_fc))) return rc;
     TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, cx.st, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, w.dQKVo.h);
     // ---- wave 8: through the packed q/k/v projection
     seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
@@ -407,6 +417,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
             seg(seg(wv.add(D, D, 0.f, fonly(dW[i], D)), true, sub(w.dQKVo, 0, i * D), true, w.Xo, d.B2), true, sub(w.dQKVs, 0, i * D), true, w.S, d.Nsp);
     }
     RUN(wv);
+    if ((rc = record_ready(cx.st, gr->ev_w_qkv))) return rc;
     // ---- normalisation backward of own rows, prototype rows and state-table rows (+ bias-gradient partials)
     NrmList nl;
     memset(&nl, 0, sizeof(nl));

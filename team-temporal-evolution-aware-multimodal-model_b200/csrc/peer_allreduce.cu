@@ -1,0 +1,153 @@
+// In-place fp32 all-reduce (sum) of one buffer per GPU over NVLink peer memory - the gradient exchange of the
+// data-parallel head step (1.85 M floats, far too small for a ring to reach wire speed).
+//
+// Every rank maps every peer's buffer and flag array (symmetric memory; the host hands in the W pointers).  ONE
+// kernel per rank, two-shot:
+//   barrier A  (per block: "my gradients are complete" flags written into every peer, wait for all peers)
+//   reduce     rank r sums slice r of all W buffers in rank order 0..W-1 (=> bit-identical on every rank)
+//   broadcast  and stores the result into slice r of every peer's buffer (and its own)
+//              [with a multicast mapping: multimem.ld_reduce / multimem.st - the NVSwitch adds and replicates]
+//   barrier B  (per block: "my slice is written everywhere")
+// Flags carry a monotonically increasing epoch kept in the rank's own flag array, so nothing is ever reset and the
+// launch can sit inside a replayed CUDA graph.  Block b of every rank works on the same float4 indices, so the
+// barriers are per block (no grid-wide sync); the grid is small enough to be co-resident.
+#include "common.cuh"
+
+namespace team {
+
+constexpr int AR_MAX_RANKS = 8;
+constexpr int AR_BLOCKS = 64;
+constexpr int AR_THREADS = 512;
+// flag array layout (uint32): [0, AR_BLOCKS) own epoch per block | A flags [AR_BLOCKS][8] | B flags [AR_BLOCKS][8]
+constexpr int AR_FLAG_WORDS = AR_BLOCKS + 2 * AR_BLOCKS * AR_MAX_RANKS;
+
+struct ArArgs {
+    float* buf[AR_MAX_RANKS];
+    uint32_t* flag[AR_MAX_RANKS];
+    float* mc;                 // multicast (NVLS) mapping of the same buffer on all ranks, or null
+    int rank, world;
+    long long n4;              // float4 count
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// All threads of the block call it; threads [0, world) of warp 0 each handle one peer.
+//   START barrier (release_writes = false): what the peers are about to read was written by EARLIER kernels of
+//   this rank (complete and at its home L2 when this kernel runs), so plain volatile flag stores / polls suffice.
+//   END barrier (release_writes = true): this block's stores into the peers' buffers must be performed before the
+//   flag - one system-scope release per polling thread (the CTA barrier in front makes the whole block's writes
+//   part of it).  The readers of the result are LATER kernels (kernel boundary), so no acquire fence is needed.
+// MEMBAR.SYS, not the NVLink round trip, is the expensive part of such a barrier: 1 instead of 4 per call.
+__device__ __forceinline__ void ar_barrier(const ArArgs& a, int phase, uint32_t epoch, bool release_writes) {
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < a.world) {
+        const int slot = AR_BLOCKS + (phase * AR_BLOCKS + (int)blockIdx.x) * AR_MAX_RANKS;
+        if (release_writes) st_release_sys(a.flag[t] + slot + a.rank, epoch);      // tell peer t
+        else st_volatile_u32(a.flag[t] + slot + a.rank, epoch);
+        const uint32_t* mine = a.flag[a.rank] + slot + t;                          // hear from peer t
+        long long spins = 0;
+        while ((int)(ld_volatile_u32(mine) - epoch) < 0) {
+            if (++spins > (1ll << 27)) __trap();                                   // a lost peer traps instead of hanging the GPU
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(AR_THREADS)
+peer_allreduce_f32_kernel(const __grid_constant__ ArArgs a) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) {
+        uint32_t* e = a.flag[a.rank] + blockIdx.x;
+        s_epoch = *e + 1;
+        *e = s_epoch;
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch;
+    ar_barrier(a, 0, epoch, false);
+    const int W = a.world;
+    const long long c0 = a.n4 * a.rank / W, c1 = a.n4 * (a.rank + 1) / W;
+    if (a.mc != nullptr) {
+        // NVLS: the switch sums the W copies on the way in (multimem.ld_reduce) and replicates the result on the way
+        // out (multimem.st), so each rank moves 2/W of the buffer over its own links instead of 2 (W-1)/W
+        float4* mc = reinterpret_cast<float4*>(a.mc);
+        constexpr int U = 4;                                   // independent round trips in flight per thread
+        const long long stride = (long long)AR_BLOCKS * AR_THREADS;
+        for (long long i0 = c0 + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < c1; i0 += U * stride) {
+            float4 s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u * stride < c1)
+                    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                 : "=f"(s[u].x), "=f"(s[u].y), "=f"(s[u].z), "=f"(s[u].w) : "l"(mc + i0 + u * stride) : "memory");
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u * stride < c1)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                                 ::"l"(mc + i0 + u * stride), "f"(s[u].x), "f"(s[u].y), "f"(s[u].z), "f"(s[u].w) : "memory");
+        }
+    } else
+    for (long long i = c0 + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < c1; i += (long long)AR_BLOCKS * AR_THREADS) {
+        float4 v[AR_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < AR_MAX_RANKS; ++r)
+            if (r < W) v[r] = ld_volatile_f4(reinterpret_cast<const float4*>(a.buf[r]) + i);
+        float4 s = v[0];
+#pragma unroll
+        for (int r = 1; r < AR_MAX_RANKS; ++r)
+            if (r < W) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+        for (int r = 0; r < AR_MAX_RANKS; ++r)
+            if (r < W) reinterpret_cast<float4*>(a.buf[r])[i] = s;
+    }
+    ar_barrier(a, 1, epoch, true);
+}
+
+}  // namespace team
+
+using namespace team;
+
+extern "C" size_t team_peer_allreduce_flag_bytes(void) { return (size_t)AR_FLAG_WORDS * sizeof(uint32_t); }
+
+extern "C" int team_peer_allreduce_f32(void* const* bufs, void* const* flags, void* multicast, int32_t rank,
+                                       int32_t world, int64_t n, void* stream) {
+    TEAM_REQUIRE(bufs != nullptr && flags != nullptr, "peer_allreduce: null pointer table");
+    TEAM_REQUIRE(world >= 1 && world <= AR_MAX_RANKS && rank >= 0 && rank < world, "peer_allreduce: rank %d / world %d", rank, world);
+    TEAM_REQUIRE(n >= 0 && n % 4 == 0, "peer_allreduce: element count %lld must be a multiple of 4", (long long)n);
+    if (n == 0 || world == 1) return TEAM_OK;
+    ArArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < world; ++r) {
+        TEAM_REQUIRE(bufs[r] != nullptr && flags[r] != nullptr && (reinterpret_cast<uintptr_t>(bufs[r]) & 15) == 0, "peer_allreduce: bad pointer of rank %d", r);
+        a.buf[r] = reinterpret_cast<float*>(bufs[r]);
+        a.flag[r] = reinterpret_cast<uint32_t*>(flags[r]);
+    }
+    a.mc = reinterpret_cast<float*>(multicast);
+    a.rank = rank; a.world = world; a.n4 = n / 4;
+    TEAM_LAUNCH(peer_allreduce_f32_kernel, AR_BLOCKS, AR_THREADS, 0, (cudaStream_t)stream, a);
+    return TEAM_OK;
+}

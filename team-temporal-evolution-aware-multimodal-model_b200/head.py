@@ -290,10 +290,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.T
     return out.reshape(shape)
 
 
-GRAD_LAYOUT = (("w_img", capi.D * capi.D), ("b_img", capi.D), ("w_text", capi.D * capi.D), ("b_text", capi.D),
-               ("w_state", capi.D * capi.D), ("b_state", capi.D), ("state_emb", capi.NUM_STATES * capi.D),
+# order of the flat gradient buffer = order in which the backward finishes its groups (w_fc first, then
+# w_q / w_k / w_v, then everything else), so each all-reduce bucket is one contiguous slice
+GRAD_LAYOUT = (("w_fc", capi.D * capi.D),
                ("w_q", capi.D * capi.D), ("w_k", capi.D * capi.D), ("w_v", capi.D * capi.D),
-               ("w_fc", capi.D * capi.D), ("b_fc", capi.D), ("ln_g", capi.D), ("ln_b", capi.D))
+               ("w_img", capi.D * capi.D), ("b_img", capi.D), ("w_text", capi.D * capi.D), ("b_text", capi.D),
+               ("w_state", capi.D * capi.D), ("b_state", capi.D), ("state_emb", capi.NUM_STATES * capi.D),
+               ("b_fc", capi.D), ("ln_g", capi.D), ("ln_b", capi.D))
 
 
 class HeadStepRunner:
@@ -303,7 +306,7 @@ class HeadStepRunner:
     parallelism)."""
 
     def __init__(self, pack: HeadParamPack, img_prototypes: torch.Tensor, batch: int, num_text_cls: int,
-                 mode: int = MODE_F32):
+                 mode: int = MODE_F32, grad_events: bool = False, grad_buffer: Optional[torch.Tensor] = None):
         capi.require_device()
         dev = pack.flat[0].device
         self.dev, self.B, self.mode, self.n_cls = dev, batch, mode, num_text_cls
@@ -318,8 +321,13 @@ class HeadStepRunner:
         self.logits = torch.empty((batch, max(num_text_cls, 1)), dtype=torch.float32, device=dev)
         self.argmax = torch.empty((batch,), dtype=torch.int64, device=dev)
         P = pack.T * pack.ppt
-        n = sum(sz for _, sz in GRAD_LAYOUT) + max(P, 1) * capi.D
-        self.flat_grads = torch.zeros((n,), dtype=torch.float32, device=dev)
+        n = self.grad_numel(pack)
+        if grad_buffer is not None:              # e.g. parallel.PeerAllReduce.buffer (symmetric memory)
+            if grad_buffer.numel() != n or grad_buffer.dtype != torch.float32 or not grad_buffer.is_contiguous():
+                raise ValueError(f"grad_buffer must be a contiguous fp32 tensor of {n} elements")
+            self.flat_grads = grad_buffer
+        else:
+            self.flat_grads = torch.zeros((n,), dtype=torch.float32, device=dev)
         self.hg = capi.HeadGrads()
         self.grad_views: Dict[str, torch.Tensor] = {}
         off = 0
@@ -328,6 +336,47 @@ class HeadStepRunner:
             self.grad_views[name] = v
             setattr(self.hg, name, v.data_ptr())
             off += sz
+        # all-reduce buckets in the order the backward completes them (see team_head_grads.ev_*)
+        d2 = capi.D * capi.D
+        self.buckets = (self.flat_grads[:d2], self.flat_grads[d2:4 * d2], self.flat_grads[4 * d2:])
+        self.ready_events = None
+        self.comm_stream = None
+        if grad_events:
+            # external=True: recorded from inside a captured graph, waited on by a stream outside it
+            self.ready_events = [torch.cuda.Event(external=True) for _ in range(2)]
+            for ev in self.ready_events:
+                ev.record()                       # materialises the handle
+            torch.cuda.current_stream().synchronize()
+            self.hg.ev_w_fc = self.ready_events[0].cuda_event
+            self.hg.ev_w_qkv = self.ready_events[1].cuda_event
+            self.comm_stream = torch.cuda.Stream(device=dev)
+
+    @staticmethod
+    def grad_numel(pack: HeadParamPack) -> int:
+        return sum(sz for _, sz in GRAD_LAYOUT) + max(pack.T * pack.ppt, 1) * capi.D
+
+    def allreduce_grads(self, group=None):
+        """Sum ``flat_grads`` over the ranks.  Call right after the step (eager call or graph replay) has been
+        enqueued on the current stream.  With ``grad_events`` the three buckets are reduced on a side stream as
+        soon as the backward has finished each of them (w_fc, then w_q/w_k/w_v, then the rest), overlapping the
+        remaining kernels of the step; the current stream then waits for the side stream."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        if self.ready_events is None:
+            dist.all_reduce(self.flat_grads, group=group)
+            return
+        cur = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(cur)                           # end of the step as enqueued so far
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(self.ready_events[0])
+            dist.all_reduce(self.buckets[0], group=group)
+            self.comm_stream.wait_event(self.ready_events[1])
+            dist.all_reduce(self.buckets[1], group=group)
+            self.comm_stream.wait_event(done)
+            dist.all_reduce(self.buckets[2], group=group)
+        cur.wait_stream(self.comm_stream)
 
     def forward(self, image, text, sid, text_cls=None):
         n_cls = self.n_cls if text_cls is not None else 0
@@ -363,14 +412,17 @@ class HostBatchPipeline:
     replay (optimizer step / all-reduce), before the next replay can overwrite them."""
 
     def __init__(self, pack: HeadParamPack, img_prototypes: torch.Tensor, batch: int, text_cls: torch.Tensor,
-                 mode: int = MODE_F32, depth: int = 2, after_step=None):
+                 mode: int = MODE_F32, depth: int = 2, after_step=None, grad_events: bool = False,
+                 grad_buffer: Optional[torch.Tensor] = None, in_graph=None):
         capi.require_device()
         if depth < 1:
             raise ValueError("depth must be >= 1")
         dev = pack.flat[0].device
         self.dev, self.B, self.depth, self.after_step = dev, batch, depth, after_step
         self.text_cls = _f32c(text_cls, dev)
-        self.runner = HeadStepRunner(pack, img_prototypes, batch, int(self.text_cls.shape[0]), mode)
+        self.runner = HeadStepRunner(pack, img_prototypes, batch, int(self.text_cls.shape[0]), mode,
+                                     grad_events=grad_events, grad_buffer=grad_buffer)
+        self.in_graph = in_graph                 # optional callable captured right after the step (e.g. PeerAllReduce)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.compute_stream = torch.cuda.Stream(device=dev)
         mk = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=dev)
@@ -394,6 +446,8 @@ class HostBatchPipeline:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.compute_stream):
                 r.step(sl["image"], sl["text"], sl["state"], self.text_cls, sl["cots"])
+                if self.in_graph is not None:
+                    self.in_graph()
         sl["graph"] = g
 
     def submit(self, image: torch.Tensor, text: torch.Tensor, state_ids: torch.Tensor, cotangents: Sequence[torch.Tensor]):

@@ -173,3 +173,47 @@ def test_host_batch_pipeline_matches_direct_step():
     torch.cuda.synchronize()
     for g, w in zip(seen_grads, want_grad):
         assert torch.equal(g.cpu(), w)          # same kernels, same order: bit-identical
+
+
+def test_grad_ready_events_inside_a_captured_step():
+    """team_head_grads.ev_*: the events recorded in the middle of a CAPTURED backward (external record nodes)
+    release a side stream that reads the finished gradient buckets while the rest of the graph still runs."""
+    from team_b200 import head
+    dev = torch.device("cuda")
+    T, B = 2, 48
+    C = 2 * T
+    params = synth.make_params(T, seed=9)
+    pack = head.HeadParamPack.from_state_dict({k: v.to(dev) for k, v in params.items()})
+    protos = synth.make_prototypes(C, seed=4).to(dev)
+    text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
+    b = synth.make_batch(B, C, step=1)
+    args = (b["image"].to(dev), b["text"].to(dev), b["state"].to(dev), text_cls,
+            [c.reshape(B, 512).to(dev) for c in synth.make_cotangents(B, step=1)])
+    plain = head.HeadStepRunner(pack, protos, B, C, head.MODE_F32)
+    plain.step(*args)
+    torch.cuda.synchronize()
+    want = plain.flat_grads.clone()
+    r = head.HeadStepRunner(pack, protos, B, C, head.MODE_F32, grad_events=True)
+    assert sum(x.numel() for x in r.buckets) == r.flat_grads.numel()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        r.step(*args)                       # eager: plain event records
+        st.synchronize()
+        assert torch.equal(r.flat_grads, want)
+        r.flat_grads.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            r.step(*args)
+        r.flat_grads.zero_()
+        st.synchronize()
+        g.replay()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        side.wait_event(r.ready_events[0])
+        got0 = r.buckets[0].clone()
+        side.wait_event(r.ready_events[1])
+        got1 = r.buckets[1].clone()
+    torch.cuda.synchronize()
+    d2 = 512 * 512
+    assert torch.equal(got0, want[:d2]) and torch.equal(got1, want[d2:4 * d2])
+    assert torch.equal(r.flat_grads, want)

@@ -129,3 +129,21 @@ def test_cosine_logits_vs_oracle(n, C, dtype):
     assert int(safe.sum()) >= int(0.99 * n)
     am_only = ops.cosine_logits(xq.cuda(), w.cuda(), sig, want_logits=False, want_argmax=True)
     assert torch.equal(am_only, am)
+
+
+def test_peer_allreduce_single_rank_and_argument_checks():
+    """team_peer_allreduce_f32: world = 1 is a no-op; bad arguments are rejected before any launch.  (The W > 1
+    path needs one GPU per rank: tools/peer_allreduce_check.py under torchrun, profiles/r1g_peer_allreduce_check.txt.)"""
+    import ctypes as C
+    from team_b200 import capi
+    L = capi.lib()
+    x = torch.arange(16, dtype=torch.float32, device="cuda")
+    flags = torch.zeros(L.team_peer_allreduce_flag_bytes() // 4, dtype=torch.int32, device="cuda")
+    bufs, flgs = (C.c_void_p * 1)(x.data_ptr()), (C.c_void_p * 1)(flags.data_ptr())
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.team_peer_allreduce_f32(bufs, flgs, None, 0, 1, 16, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(x.cpu(), torch.arange(16, dtype=torch.float32))
+    assert L.team_peer_allreduce_f32(bufs, flgs, None, 0, 1, 15, st) != 0        # n % 4
+    assert L.team_peer_allreduce_f32(bufs, flgs, None, 3, 2, 16, st) != 0        # rank >= world
+    assert L.team_peer_allreduce_f32(bufs, flgs, None, 0, 9, 16, st) != 0        # more than one box
