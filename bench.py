@@ -205,11 +205,18 @@ def run_team(a):
     text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
     # N > 1: the gradient buffer lives in symmetric memory and is summed over the ranks by ONE kernel over NVLink
     # peer memory, captured at the end of the step's graph (--comm nccl: torch.distributed all-reduce after the replay)
-    peer = None
+    peer, comm = None, (a.comm if world > 1 else None)
     if world > 1 and a.comm == "peer":
         from team_b200 import parallel
-        peer = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev)
-    runner = head.HeadStepRunner(pack, protos, B, C, mode, grad_events=world > 1 and a.comm == "nccl-buckets",
+        try:
+            peer = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev)
+        except Exception as e:                    # no symmetric memory on this box: every rank falls back together
+            print(f"[bench] rank {rank}: peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr, flush=True)
+        ok = torch.tensor([0 if peer is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer, comm = None, "nccl (peer-memory all-reduce unavailable)"
+    runner = head.HeadStepRunner(pack, protos, B, C, mode, grad_events=comm == "nccl-buckets",
                                  grad_buffer=peer.buffer if peer is not None else None)
     stream = torch.cuda.Stream(device=dev)
 
@@ -342,7 +349,7 @@ def run_team(a):
         after = (lambda r: r.allreduce_grads()) if world > 1 and peer is None else None
         peer2 = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev) if peer is not None else None
         pipe = head.HostBatchPipeline(pack, protos, B, text_cls, mode=mode, depth=2, after_step=after,
-                                      grad_events=world > 1 and a.comm == "nccl-buckets",
+                                      grad_events=comm == "nccl-buckets",
                                       grad_buffer=peer2.buffer if peer2 is not None else None, in_graph=peer2)
         correct = [0]
 
@@ -384,7 +391,7 @@ def run_team(a):
                 "dtype": a.mode, "data": "synthetic",
                 "config": {"workload": f"TEAM/PROOF head fwd+bwd (BASELINE configs[2]): T={T} tasks, C={C} classes, "
                                        f"P={10 * T} prompts, L={3 + 12 * T} tokens, batch {B} per GPU",
-                           "tasks": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_exchange": (a.comm if world > 1 else None),
+                           "tasks": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_exchange": comm,
                            "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2",
                            "cuda_graphs": graphs is not None,
                            "alg_flops_per_sample_survey": 55.07e6},

@@ -53,6 +53,8 @@ long long team_launch_count(void);
  * team_prof_collect synchronises, sums and clears.  Not for use under stream capture. */
 int team_prof_enable(int on);
 int team_prof_collect(int kind, double* total_ms, double* total_flops, double* total_bytes, long long* launches);
+/* per-launch records in launch order (ms, flops, kind) for up to cap launches; returns the count; clears. */
+long long team_prof_dump(double* ms, double* flops, int* kind, long long cap);
 
 /* ------------------------------------------------------------------ prototype build
  * Deterministic, atomic-free keyed segmented sum (K9/K17).

@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "prof.cuh"
 
@@ -424,6 +425,367 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     }
 }
 
+// =========================================================================================================
+// Persistent variant for LARGE launches (many more tiles than SMs): one CTA per SM walks a static list of work
+// items (problem, 128 x BN tile, K split), BN up to 256.
+//   warp 0     : TMA producer - keeps a 3-stage ring of {A 128x64, B BNx64} k-blocks full ACROSS tiles
+//   warp 1     : MMA issuer   - tcgen05.mma into one of TWO tensor-memory accumulators (2 x 256 columns)
+//   warps 2..9 : epilogue     - tcgen05.ld of accumulator i while the tensor pipe already fills accumulator i+1;
+//                warp (q, half) owns 32 accumulator rows and every other 32-column chunk, stages a chunk through
+//                its own padded shared-memory patch (the next chunk's TMEM load already in flight) and stores
+//                row-contiguous 128-byte segments (fp32) / 64-byte (bf16)
+// so neither the prologue (barriers, TMEM allocation, tensor-map fetch) nor the epilogue of a tile is exposed,
+// and a 128 x 256 tile needs 25 % less L2 -> SM operand traffic per flop than 128 x 128 (these K = 512 products
+// are bound by that traffic, not by the tensor pipe).
+//   split-K : long-K / few-tile problems (weight gradients, K = 2B) are cut into items of equal k-range; every
+//             item stores its fp32 partial tile to the workspace and a small second kernel (pk_fixup_kernel, all SMs)
+//             sums the partials in split order (deterministic) and runs the epilogue.  (A "last arriver reduces"
+//             ticket scheme was measured first: one CTA pulling 16 x 128 KB of partials takes ~100 us and stalls
+//             its remaining items.)
+constexpr int PK_BN_MAX = 256;
+constexpr int PK_STAGES = 3;
+constexpr int PK_A_BYTES = TC_BM * TC_BK * 2;                 // 16 KB
+constexpr int PK_B_BYTES = PK_BN_MAX * TC_BK * 2;             // 32 KB
+constexpr int PK_STAGE_BYTES = PK_A_BYTES + PK_B_BYTES;       // 48 KB
+constexpr int PK_EPI_LD = 36;                                 // floats per staged row: 32 + 4 (conflict-free both ways)
+constexpr int PK_EPI_BYTES = 8 * 32 * PK_EPI_LD * 4;          // 8 epilogue warps x 32 rows
+constexpr int PK_THREADS = 320;                               // producer warp, MMA warp, 8 epilogue warps
+constexpr int PK_SMEM_BYTES = PK_STAGES * PK_STAGE_BYTES + PK_EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(PK_SMEM_BYTES <= 227 * 1024, "persistent GEMM: shared memory budget");
+
+struct alignas(64) PkProb {
+    TcSegDev s[2];
+    float* C;
+    __nv_bfloat16* Cb;
+    const float* bias;
+    long long ldc, ldcb;
+    float alpha, beta;
+    int M, N;
+    int bn, tiles_n, n_tiles, item_begin, splits, kb_per_split;
+    float* partials;              // [n_tiles][splits][128][bn] fp32 (splits > 1): summed by pk_fixup_kernel
+};
+struct PkGroup {
+    PkProb p[TC_MAXP];
+    int n;
+    int total_items;
+    unsigned long long* dbg;      // optional [cta < 148][item < 8][8] globaltimer stamps (tools/pk_stamps.py), else null
+};
+#define PK_STAMP(n_it, slot) do { if (g.dbg != nullptr && (n_it) < 8) g.dbg[((size_t)blockIdx.x * 8 + (n_it)) * 8 + (slot)] = gtime(); } while (0)
+struct PkItem {
+    int pi, tile, split, m0, n0, bn, kb_begin, kb_end, nkb0;
+};
+__device__ __forceinline__ PkItem pk_decode(const PkGroup& g, int item) {
+    PkItem it;
+    int pi = 0;
+    for (int i = 1; i < g.n; ++i)
+        if (item >= g.p[i].item_begin) pi = i;
+    const PkProb& P = g.p[pi];
+    const int local = item - P.item_begin;
+    it.pi = pi;
+    it.split = local % P.splits;
+    it.tile = local / P.splits;
+    it.bn = P.bn;
+    it.m0 = (it.tile / P.tiles_n) * TC_BM;
+    it.n0 = (it.tile % P.tiles_n) * P.bn;
+    it.nkb0 = P.s[0].nkb;
+    const int nkb = P.s[0].nkb + P.s[1].nkb;
+    it.kb_begin = it.split * P.kb_per_split;
+    it.kb_end = min(nkb, it.kb_begin + P.kb_per_split);
+    return it;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(PK_THREADS, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ PkGroup g) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    float* epi_all = reinterpret_cast<float*>(smem + PK_STAGES * PK_STAGE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PK_STAGES * PK_STAGE_BYTES + PK_EPI_BYTES);
+    uint64_t* empty_bar = full_bar + PK_STAGES;
+    uint64_t* acc_full = empty_bar + PK_STAGES;        // [2]
+    uint64_t* acc_empty = acc_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PK_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < g.n; ++i) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&g.p[i].s[0].ma)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&g.p[i].s[0].mb)) : "memory");
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            int n_it = 0;
+            for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++n_it) {
+                const PkItem it = pk_decode(g, item);
+                const PkProb& P = g.p[it.pi];
+                const uint32_t tx_bytes = (uint32_t)(PK_A_BYTES + it.bn * TC_BK * 2);
+                PK_STAMP(n_it, 0);
+                for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * PK_STAGE_BYTES;
+                    unsigned char* sb = sa + PK_A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    const TcSegDev& sg = P.s[kb >= it.nkb0 ? 1 : 0];
+                    const int k0 = (kb >= it.nkb0 ? kb - it.nkb0 : kb) * TC_BK;
+                    if (!sg.a_mn) {
+                        tma_load_2d(sa, &sg.ma, &full_bar[stage], k0, it.m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < TC_BM / 64; ++c)
+                            tma_load_2d(sa + c * (TC_BK * 128), &sg.ma, &full_bar[stage], it.m0 + 64 * c, k0);
+                    }
+                    if (!sg.b_mn) {
+                        tma_load_2d(sb, &sg.mb, &full_bar[stage], k0, it.n0);
+                    } else {
+                        for (int c = 0; c < it.bn / 64; ++c)
+                            tma_load_2d(sb + c * (TC_BK * 128), &sg.mb, &full_bar[stage], it.n0 + 64 * c, k0);
+                    }
+                    if (++stage == PK_STAGES) { stage = 0; phase ^= 1; }
+                }
+                PK_STAMP(n_it, 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            int stage = 0; uint32_t phase = 0;
+            int n_it = 0;
+            for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++n_it) {
+                const PkItem it = pk_decode(g, item);
+                const PkProb& P = g.p[it.pi];
+                const int buf = n_it & 1;
+                const uint32_t accph = (uint32_t)(n_it >> 1) & 1u;
+                mbar_wait(&acc_empty[buf], accph ^ 1);              // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * PK_BN_MAX);
+                const uint32_t idesc0 = umma_idesc(TC_BM, it.bn, P.s[0].a_mn, P.s[0].b_mn);
+                const uint32_t idesc1 = umma_idesc(TC_BM, it.bn, P.s[1].a_mn, P.s[1].b_mn);
+                for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
+                    const int si = kb >= it.nkb0 ? 1 : 0;
+                    const int a_mn = P.s[si].a_mn, b_mn = P.s[si].b_mn;
+                    const uint32_t idesc = si ? idesc1 : idesc0;
+                    mbar_wait(&full_bar[stage], phase);
+                    if (kb == it.kb_begin) PK_STAMP(n_it, 2);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + stage * PK_STAGE_BYTES);
+                    const uint32_t sb = sa + PK_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+                        const uint64_t ad = a_mn ? umma_desc(sa + k * 2048, TC_BK * 128, 1024) : umma_desc(sa + k * 32, 0, 1024);
+                        const uint64_t bd = b_mn ? umma_desc(sb + k * 2048, TC_BK * 128, 1024) : umma_desc(sb + k * 32, 0, 1024);
+                        tcgen05_mma_f16(d_tmem, ad, bd, idesc, (kb > it.kb_begin || k > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(&empty_bar[stage]);
+                    if (++stage == PK_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&acc_full[buf]);
+                PK_STAMP(n_it, 3);
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps = 4 TMEM lane groups (q = warp % 4) x 2 column halves =====================
+        // warp (q, half) owns accumulator rows 32q..32q+31 and the 32-column chunks ci with (ci & 1) == half.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        float* epi = epi_all + (size_t)(warp - 2) * 32 * PK_EPI_LD;
+        int n_it = 0;
+        for (int item = blockIdx.x; item < g.total_items; item += gridDim.x, ++n_it) {
+            const PkItem it = pk_decode(g, item);
+            const PkProb& P = g.p[it.pi];
+            const int buf = n_it & 1;
+            const uint32_t accph = (uint32_t)(n_it >> 1) & 1u;
+            const int bn = it.bn, M = P.M, N = P.N, splits = P.splits;
+            const float alpha = P.alpha, beta = P.beta;
+            float* const C = P.C;
+            __nv_bfloat16* const Cb = P.Cb;
+            const float* const bias = P.bias;
+            const long long ldc = P.ldc, ldcb = P.ldcb;
+            const bool acc_c = beta != 0.f && C != nullptr;
+            float* const part = splits > 1 ? P.partials + ((size_t)it.tile * splits + it.split) * (size_t)(TC_BM * bn) : nullptr;
+            mbar_wait(&acc_full[buf], accph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (threadIdx.x == 64) { PK_STAMP(n_it, 4); if (g.dbg != nullptr && n_it < 8) g.dbg[((size_t)blockIdx.x * 8 + n_it) * 8 + 7] = (unsigned long long)(it.kb_end - it.kb_begin) | ((unsigned long long)it.pi << 32); }
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * PK_BN_MAX);
+            const int nchunks = (bn + 31) >> 5;
+            uint32_t r[32];
+            int ci = half;
+            if (ci < nchunks) {                              // first TMEM load of this warp
+                if (bn - 32 * ci >= 32) tmem_ld32_nowait(tbase + (uint32_t)(32 * ci), r);
+                else tmem_ld16_nowait(tbase + (uint32_t)(32 * ci), r);
+            } else {                                         // nothing to read (bn <= 32 and half == 1): release at once
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+            for (; ci < nchunks; ci += 2) {
+                const int c0 = 32 * ci;
+                const int ncols = min(32, bn - c0);          // 32 or 16 (bn is a multiple of 16)
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                {
+                    float* my = epi + lane * PK_EPI_LD;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        if (i < ncols) *reinterpret_cast<float4*>(my + i) = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
+                if (ci + 2 < nchunks) {                      // next chunk's TMEM load flies under this chunk's stores
+                    if (bn - (c0 + 64) >= 32) tmem_ld32_nowait(tbase + (uint32_t)(c0 + 64), r);
+                    else tmem_ld16_nowait(tbase + (uint32_t)(c0 + 64), r);
+                } else {                                     // accumulator fully read by this warp: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                __syncwarp();
+                // row-contiguous phase: lpr lanes per row, rpi rows per instruction, lane rows r_off + j * rpi
+                const int lpr = ncols == 32 ? 8 : 4, rpi = ncols == 32 ? 4 : 8;
+                const int r_off = ncols == 32 ? (lane >> 3) : (lane >> 2), c4 = ncols == 32 ? (lane & 7) : (lane & 3);
+                const int col = it.n0 + c0 + 4 * c4;
+                if (col < N) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (bias != nullptr && part == nullptr) bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                    const int row0 = it.m0 + q * 32 + r_off;
+                    int nj = ncols == 32 ? 8 : 4;
+                    {
+                        const int left = M - row0;
+                        const int cap = left <= 0 ? 0 : (left + rpi - 1) / rpi;
+                        if (cap < nj) nj = cap;
+                    }
+                    (void)lpr;
+                    const float* sp = epi + r_off * PK_EPI_LD + 4 * c4;
+                    float4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < nj) v[j] = *reinterpret_cast<const float4*>(sp + j * rpi * PK_EPI_LD);
+                    if (part != nullptr) {
+                        float* dp = part + (size_t)(q * 32 + r_off) * bn + c0 + 4 * c4;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < nj) *reinterpret_cast<float4*>(dp + (size_t)j * rpi * bn) = v[j];
+                    } else {
+                        float* cp = C != nullptr ? C + (long long)row0 * ldc + col : nullptr;
+                        __nv_bfloat16* bp = Cb != nullptr ? Cb + (long long)row0 * ldcb + col : nullptr;
+                        const long long cstep = (long long)rpi * ldc, bstep = (long long)rpi * ldcb;
+                        if (acc_c) {                          // all C reads of the chunk in flight before the first store
+                            float4 o[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < nj) o[j] = *reinterpret_cast<const float4*>(cp + j * cstep);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < nj) { v[j].x = fmaf(alpha, v[j].x, fmaf(beta, o[j].x, bv.x)); v[j].y = fmaf(alpha, v[j].y, fmaf(beta, o[j].y, bv.y));
+                                              v[j].z = fmaf(alpha, v[j].z, fmaf(beta, o[j].z, bv.z)); v[j].w = fmaf(alpha, v[j].w, fmaf(beta, o[j].w, bv.w)); }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < nj) { v[j].x = fmaf(alpha, v[j].x, bv.x); v[j].y = fmaf(alpha, v[j].y, bv.y); v[j].z = fmaf(alpha, v[j].z, bv.z); v[j].w = fmaf(alpha, v[j].w, bv.w); }
+                        }
+                        if (cp != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < nj) *reinterpret_cast<float4*>(cp + j * cstep) = v[j];
+                        }
+                        if (bp != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j < nj) *reinterpret_cast<uint2*>(bp + j * bstep) = pack_bf16x4(v[j]);
+                        }
+                    }
+                }
+                __syncwarp();                                 // staging patch is rewritten by the next chunk
+            }
+            if (threadIdx.x == 64) PK_STAMP(n_it, 5);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Split-K fix-up of the persistent kernel: out = alpha * sum_s partial[s] (+ bias) (+ beta C), partials summed in
+// split order.  Block = 32 rows of one tile (256 threads, row-contiguous float4 accesses).
+struct PkFixProb {
+    const float* partials;
+    float* C;
+    __nv_bfloat16* Cb;
+    const float* bias;
+    long long ldc, ldcb;
+    float alpha, beta;
+    int M, N, bn, tiles_n, n_tiles, splits, blk_begin;
+};
+struct PkFix {
+    PkFixProb p[TC_MAXP];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+pk_fixup_kernel(const __grid_constant__ PkFix f) {
+    pdl_trigger();
+    pdl_wait();
+    int pi = 0;
+    for (int i = 1; i < f.n; ++i)
+        if ((int)blockIdx.x >= f.p[i].blk_begin) pi = i;
+    const PkFixProb& P = f.p[pi];
+    const int local = (int)blockIdx.x - P.blk_begin;
+    const int tile = local >> 2, rq = local & 3;
+    const int bn = P.bn, lpr = bn >> 2, splits = P.splits;
+    const int m0 = (tile / P.tiles_n) * TC_BM + rq * 32, n0 = (tile % P.tiles_n) * bn;
+    const float* tile_part = P.partials + (size_t)tile * splits * (size_t)(TC_BM * bn) + (size_t)(rq * 32) * bn;
+    const bool acc_c = P.beta != 0.f && P.C != nullptr;
+    for (int idx = threadIdx.x; idx < 32 * lpr; idx += 256) {
+        const int rr = idx / lpr, c4 = idx - rr * lpr;
+        const int row = m0 + rr, col = n0 + 4 * c4;
+        if (row >= P.M || col >= P.N) continue;
+        const float* src = tile_part + (size_t)rr * bn + 4 * c4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z0 = 0; z0 < splits; z0 += 8) {
+            float4 a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (z0 + u < splits) a[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(z0 + u) * (TC_BM * bn)));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (z0 + u < splits) { v.x += a[u].x; v.y += a[u].y; v.z += a[u].z; v.w += a[u].w; }
+        }
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+        float4 x = make_float4(fmaf(P.alpha, v.x, bv.x), fmaf(P.alpha, v.y, bv.y), fmaf(P.alpha, v.z, bv.z), fmaf(P.alpha, v.w, bv.w));
+        if (acc_c) {
+            const float4 o = *reinterpret_cast<const float4*>(P.C + (long long)row * P.ldc + col);
+            x.x = fmaf(P.beta, o.x, x.x); x.y = fmaf(P.beta, o.y, x.y); x.z = fmaf(P.beta, o.z, x.z); x.w = fmaf(P.beta, o.w, x.w);
+        }
+        if (P.C != nullptr) *reinterpret_cast<float4*>(P.C + (long long)row * P.ldc + col) = x;
+        if (P.Cb != nullptr) *reinterpret_cast<uint2*>(P.Cb + (long long)row * P.ldcb + col) = pack_bf16x4(x);
+    }
+}
+
 // fp32 -> bf16 (hi) and optional residual (lo = bf16(x - hi)); rows x cols with leading dims
 __global__ void __launch_bounds__(256)
 f32_to_bf16_kernel(const float* __restrict__ src, int64_t lds, int64_t rows, int cols,
@@ -526,13 +888,146 @@ static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double
     return TEAM_OK;
 }
 
+// ---- persistent path: planning + launch of one group (<= TC_MAXP problems).  ws = [tickets | split-K partials].
+static bool pk_eligible(const TcGemm& g) {
+    if (g.N % 4 != 0) return false;
+    if (g.C != nullptr && (g.ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(g.C) & 15) != 0)) return false;
+    if (g.Cb != nullptr && (g.ldcb % 4 != 0 || (reinterpret_cast<uintptr_t>(g.Cb) & 7) != 0)) return false;
+    if (g.bias != nullptr && (reinterpret_cast<uintptr_t>(g.bias) & 15) != 0) return false;
+    return true;
+}
+
+static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, void* ws, size_t ws_bytes) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
+        attr_set = true;
+    }
+    PkGroup grp;
+    memset(&grp, 0, sizeof(grp));
+    const bool have_ws = ws != nullptr && ws_bytes > 4096 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
+    char* part_base = have_ws ? reinterpret_cast<char*>(ws) : nullptr;
+    size_t part_cap = have_ws ? ws_bytes : 0, part_off = 0;
+    int order[TC_MAXP], bn_[TC_MAXP], tiles_n_[TC_MAXP], tiles_[TC_MAXP], nkb_[TC_MAXP], splits_[TC_MAXP], kbps_[TC_MAXP];
+    bool any_split = false;
+    for (int i = 0; i < np; ++i) {
+        const TcGemm& g = *sel[i];
+        bool any_b_mn = false;
+        int nkb = 0;
+        for (int q = 0; q < g.nseg; ++q) { any_b_mn = any_b_mn || g.s[q].b_mn; nkb += (int)((g.s[q].K + TC_BK - 1) / TC_BK); }
+        int bn;
+        if (g.N >= PK_BN_MAX) bn = PK_BN_MAX;
+        else bn = any_b_mn ? (int)((g.N + 63) / 64 * 64) : (int)((g.N + 15) / 16 * 16);
+        const int tiles_n = (int)((g.N + bn - 1) / bn), tiles = (int)((g.M + TC_BM - 1) / TC_BM) * tiles_n;
+        int splits = 1;
+        if (have_ws && tiles < NUM_SMS / 2 && nkb >= 64) {
+            // a partial tile costs 2 x 128 x bn x 4 bytes of extra traffic: keep >= 32 k-blocks (1.5 MB of operands) per item
+            splits = (NUM_SMS + tiles - 1) / tiles;
+            if (splits > nkb / 32) splits = nkb / 32;
+            if (splits > 32) splits = 32;
+            while (splits > 1 && part_off + (size_t)tiles * splits * TC_BM * bn * 4 > part_cap) splits /= 2;
+            if (splits < 1) splits = 1;
+        }
+        int kbps = (nkb + splits - 1) / splits;
+        splits = (nkb + kbps - 1) / kbps;                 // every split owns at least one k-block
+        bn_[i] = bn; tiles_n_[i] = tiles_n; tiles_[i] = tiles; nkb_[i] = nkb; splits_[i] = splits; kbps_[i] = kbps;
+        order[i] = i;
+        if (splits > 1) {
+            any_split = true;
+            PkProb& p = grp.p[i];
+            p.partials = reinterpret_cast<float*>(part_base + part_off);
+            part_off += align_up((size_t)tiles * splits * TC_BM * bn * 4, 256);
+        }
+    }
+    // longest items first: the static round-robin over CTAs then balances to within one short item
+    for (int a = 0; a < np; ++a)
+        for (int b = a + 1; b < np; ++b)
+            if (kbps_[order[b]] > kbps_[order[a]]) { const int t = order[a]; order[a] = order[b]; order[b] = t; }
+    PkGroup out;
+    memset(&out, 0, sizeof(out));
+    int item = 0, rc;
+    double flops = 0, bytes = 0;
+    for (int o = 0; o < np; ++o) {
+        const int i = order[o];
+        const TcGemm& g = *sel[i];
+        PkProb& p = out.p[o];
+        p.partials = grp.p[i].partials;
+        p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias;
+        p.alpha = g.alpha; p.beta = g.beta; p.M = (int)g.M; p.N = (int)g.N;
+        p.bn = bn_[i]; p.tiles_n = tiles_n_[i]; p.n_tiles = tiles_[i]; p.splits = splits_[i]; p.kb_per_split = kbps_[i];
+        p.item_begin = item;
+        item += tiles_[i] * splits_[i];
+        double ksum = 0;
+        for (int q = 0; q < g.nseg; ++q) {
+            const TcSeg& sg = g.s[q];
+            TcSegDev& sd = p.s[q];
+            sd.K = (int)sg.K; sd.a_mn = sg.a_mn ? 1 : 0; sd.b_mn = sg.b_mn ? 1 : 0;
+            sd.nkb = (int)((sg.K + TC_BK - 1) / TC_BK);
+            if (!sg.a_mn) rc = make_map(&sd.ma, sg.A, sg.K, g.M, sg.lda, TC_BK, TC_BM); else rc = make_map(&sd.ma, sg.A, g.M, sg.K, sg.lda, 64, TC_BK);
+            if (rc) return rc;
+            if (!sg.b_mn) rc = make_map(&sd.mb, sg.B, sg.K, g.N, sg.ldb, TC_BK, p.bn); else rc = make_map(&sd.mb, sg.B, g.N, sg.K, sg.ldb, 64, TC_BK);
+            if (rc) return rc;
+            ksum += (double)sg.K;
+        }
+        if (g.nseg == 1) { out.p[o].s[1] = out.p[o].s[0]; out.p[o].s[1].nkb = 0; out.p[o].s[1].K = 0; }   // valid (unused) maps
+        flops += 2.0 * p.M * p.N * ksum;
+        bytes += 2.0 * ((double)p.M + (double)p.N) * ksum + (p.C ? 4.0 : 0.0) * p.M * p.N + (p.Cb ? 2.0 : 0.0) * p.M * p.N;
+    }
+    out.n = np;
+    out.total_items = item;
+    out.dbg = g_dbg != nullptr ? g_dbg + (size_t)(g_dbg_launch++ % 32) * 1024 * 16 : nullptr;
+    const int pslot = prof_enabled() ? prof_begin(st, 1, flops, bytes) : -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(item < NUM_SMS ? item : NUM_SMS), 1, 1);
+    cfg.blockDim = dim3(PK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = PK_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_persistent_kernel, out);
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "gemm_bf16_persistent_kernel");
+    struct ProfEnd {                     // the fix-up kernel is part of the timed GEMM
+        cudaStream_t st; int slot;
+        ~ProfEnd() { if (slot >= 0) prof_end(st, slot); }
+    } prof_guard{st, pslot};
+    if (any_split) {
+        PkFix fx;
+        memset(&fx, 0, sizeof(fx));
+        int blocks = 0;
+        for (int o = 0; o < np; ++o) {
+            const PkProb& p = out.p[o];
+            if (p.splits <= 1) continue;
+            PkFixProb& q = fx.p[fx.n++];
+            q.partials = p.partials; q.C = p.C; q.Cb = p.Cb; q.bias = p.bias; q.ldc = p.ldc; q.ldcb = p.ldcb;
+            q.alpha = p.alpha; q.beta = p.beta; q.M = p.M; q.N = p.N; q.bn = p.bn; q.tiles_n = p.tiles_n;
+            q.n_tiles = p.n_tiles; q.splits = p.splits; q.blk_begin = blocks;
+            blocks += 4 * p.n_tiles;
+        }
+        TEAM_LAUNCH(pk_fixup_kernel, blocks, 256, 0, st, fx);
+    }
+    return TEAM_OK;
+}
+
+static int pk_min_tiles() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TEAM_GEMM_PERSIST_MIN_TILES");
+        v = e != nullptr ? atoi(e) : 2 * NUM_SMS;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
+
 // Plans tiles / splits for ops[0..n) and launches them in chunks of TC_MAXP problems.
 //   * N tile: 128 wide unless the whole launch would leave most SMs without a tile, then 64;
 //   * split-K: while the launch stays within two CTAs per SM, the problem with the most k-blocks per CTA is
 //     split further (2 / 4 / 8 ways), so that a [512,512] weight gradient over K = 2B rows does not run as 16 long CTAs
 //     next to hundreds of short ones.  The largest split count is the cluster size of the launch.
 int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t ws_bytes) {
-    (void)ws; (void)ws_bytes;
     int rc = get_encode();
     if (rc) return rc;
     for (int base = 0; base < n; base += TC_MAXP) {
@@ -555,6 +1050,14 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
             tiles128 += (int)((g.M + TC_BM - 1) / TC_BM) * (int)((g.N + TC_MAX_BN - 1) / TC_MAX_BN);
         }
         if (np == 0) continue;
+        {   // large launches: persistent kernel (128 x 256 tiles, overlapped epilogue)
+            bool ok = tiles128 >= pk_min_tiles();
+            for (int i = 0; i < np && ok; ++i) ok = pk_eligible(*sel[i]);
+            if (ok) {
+                if ((rc = pk_launch_group(st, sel, np, ws, ws_bytes))) return rc;
+                continue;
+            }
+        }
         const bool narrow = tiles128 < NUM_SMS;
         int tiles[TC_MAXP], nkbs[TC_MAXP];
         double kflops[TC_MAXP];

@@ -60,3 +60,24 @@ extern "C" int team_prof_collect(int kind, double* total_ms, double* total_flops
     if (launches) *launches = n;
     return TEAM_OK;
 }
+
+// Per-launch records (in launch order) instead of sums: ms[i], flops[i], kind[i] for up to `cap` launches;
+// returns the number written (or a negative error); clears the records.  Synchronises the device.
+extern "C" long long team_prof_dump(double* ms, double* flops, int* kind, long long cap) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return TEAM_ECUDA;
+    std::lock_guard<std::mutex> lk(g_mu);
+    long long n = 0;
+    for (auto& r : g_recs) {
+        float t = 0.f;
+        if (n < cap && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            if (ms) ms[n] = t;
+            if (flops) flops[n] = r.flops;
+            if (kind) kind[n] = r.kind;
+            ++n;
+        }
+        g_pool.push_back(r.a);
+        g_pool.push_back(r.b);
+    }
+    g_recs.clear();
+    return n;
+}

@@ -59,7 +59,7 @@ def test_gemm_bf16_tcgen05(a_mn, b_mn, M, N, K):
                                          B.stride(0), 0.0, out.data_ptr(), N, None, ws.data_ptr(), ws.numel(), _st()),
                "team_gemm_bf16")
     torch.cuda.synchronize()
-    assert rel(out, ref) < 2e-6, rel(out, ref)
+    assert rel(out, ref) < 3e-6, rel(out, ref)          # fp32 accumulation over up to 2048 products
 
 
 def test_gemm_bf16_epilogue_and_split():
@@ -178,3 +178,71 @@ def test_gemm_bf16_two_segments(maj):
     torch.cuda.synchronize()
     for i in range(len(cases)):
         assert rel(outs[i], refs[i]) < 3e-6, (i, rel(outs[i], refs[i]))
+
+
+@pytest.mark.parametrize("two_seg", [False, True])
+def test_gemm_bf16_persistent_group(two_seg):
+    """Large grouped launch -> the persistent kernel (128 x 256 tiles, double-buffered accumulator, ticketed
+    split-K for the long-K weight-gradient shapes): mixed majors, ragged M / N, dual outputs, alpha/beta/bias,
+    two K-segments; twice, so the tickets must have reset themselves; results bit-identical between the runs."""
+    from team_b200 import capi
+    capi.require_device()
+    g = torch.Generator().manual_seed(23)
+    pad = lambda n: (n + 7) // 8 * 8
+    specs = [  # a_mn, b_mn, M, N, K, alpha, beta, bias, out
+        (0, 0, 8192, 1536, 512, 1.0, 0.0, False, "b"), (0, 0, 8000, 512, 512, 1.0, 0.0, True, "fb"),
+        (0, 0, 8192, 144, 512, 0.5, 0.0, False, "f"), (1, 1, 512, 512, 8192 + 144, 1.0, 0.0, False, "f"),
+        (1, 1, 144, 512, 8192, 1.0, 1.0, False, "fb"), (0, 1, 8192, 512, 144, 1.0, 1.0, False, "f"),
+        (0, 1, 4100, 512, 1536, 1.0, 1.0, False, "f"), (1, 0, 256, 148, 4096, 2.0, 0.0, True, "f")]
+    descs = (capi.GemmDesc * len(specs))()
+    keep, checks = [], []
+    for i, (a_mn, b_mn, M, N, K, alpha, beta, use_bias, out) in enumerate(specs):
+        A = (0.25 * torch.randn((K, pad(M)) if a_mn else (M, pad(K)), generator=g)).to(torch.bfloat16).cuda()
+        B = (0.25 * torch.randn((K, pad(N)) if b_mn else (N, pad(K)), generator=g)).to(torch.bfloat16).cuda()
+        Av = A[:, :M] if a_mn else A[:, :K]
+        Bv = B[:, :N] if b_mn else B[:, :K]
+        C0 = torch.randn((M, N), generator=g).cuda()
+        bias = torch.randn((N,), generator=g).cuda() if use_bias else None
+        ref = alpha * ((Av.double().t() if a_mn else Av.double()) @ (Bv.double() if b_mn else Bv.double().t()))
+        d = descs[i]
+        if two_seg and i in (3, 6):            # second K-segment with the other operand majors
+            K2 = 200
+            A2 = (0.25 * torch.randn((M, pad(K2)) if a_mn else (K2, pad(M)), generator=g)).to(torch.bfloat16).cuda()
+            B2 = (0.25 * torch.randn((N, pad(K2)) if b_mn else (K2, pad(N)), generator=g)).to(torch.bfloat16).cuda()
+            A2v = A2[:, :K2] if a_mn else A2[:, :M]
+            B2v = B2[:, :K2] if b_mn else B2[:, :N]
+            ref = ref + alpha * ((A2v.double() if a_mn else A2v.double().t()) @ (B2v.double().t() if b_mn else B2v.double()))
+            d.a_mn2, d.b_mn2, d.K2 = 1 - a_mn, 1 - b_mn, K2
+            d.A2, d.lda2, d.B2, d.ldb2 = A2.data_ptr(), A2.stride(0), B2.data_ptr(), B2.stride(0)
+            keep += [A2, B2]
+        if use_bias:
+            ref = ref + bias.double()
+        if beta != 0.0:
+            ref = ref + beta * C0.double()
+        Cf = C0.clone() if "f" in out or beta != 0.0 else None
+        Cb = torch.zeros((M, pad(N)), dtype=torch.bfloat16, device="cuda") if "b" in out else None
+        d.a_mn, d.b_mn, d.M, d.N, d.K, d.alpha, d.beta = a_mn, b_mn, M, N, K, alpha, beta
+        d.A, d.lda, d.B, d.ldb = A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0)
+        d.C, d.ldc = (Cf.data_ptr(), N) if Cf is not None else (None, 0)
+        d.C_bf16, d.ldc_bf16 = (Cb.data_ptr(), Cb.stride(0)) if Cb is not None else (None, 0)
+        d.bias = bias.data_ptr() if use_bias else None
+        keep += [A, B, bias]
+        checks.append((Cf, Cb, ref, N, C0))
+    ws = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    first = None
+    for rep in range(2):
+        for Cf, Cb, ref, N, C0 in checks:
+            if Cf is not None:
+                Cf.copy_(C0)
+        capi.check(capi.lib().team_gemm_bf16_group(descs, len(specs), ws.data_ptr(), ws.numel(), _st()), "team_gemm_bf16_group")
+        torch.cuda.synchronize()
+        for i, (Cf, Cb, ref, N, C0) in enumerate(checks):
+            if Cf is not None:
+                assert rel(Cf, ref) < 3e-6, (rep, i, rel(Cf, ref))
+            if Cb is not None:
+                assert rel(Cb[:, :N].float(), ref) < 4e-3, (rep, i)
+        snap = [x.clone() for c in checks for x in c[:2] if x is not None]
+        if first is None:
+            first = snap
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(first, snap))
