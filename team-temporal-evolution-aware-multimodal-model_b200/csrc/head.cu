@@ -1,7 +1,9 @@
 // Host orchestration + C ABI of the fusion head: team_head_tri_fwd / team_head_tri_bwd /
 // team_head_encode (include/team_b200.h).  Every launch goes to the caller's stream, there is
 // no synchronisation and no allocation, so a whole step can be captured into a CUDA graph.
+#include <stdlib.h>
 #include "head_proof_kernels.cuh"
+#include "head_table_kernels.cuh"
 #include "gemm_tc.cuh"
 
 namespace team {
@@ -244,6 +246,13 @@ static int record_ready(cudaStream_t st, void* ev) {
     return TEAM_OK;
 }
 
+// second-generation table-row kernels unless the head is too large for them or TEAM_TABLE_V1 is set (A/B runs)
+static bool use_table2(const HeadDims& d) {
+    static int v1 = -1;
+    if (v1 < 0) v1 = getenv("TEAM_TABLE_V1") != nullptr ? 1 : 0;
+    return v1 == 0 && table2_supported(d) && table2_bwd_smem_floats(d) * sizeof(float) <= 227 * 1024;
+}
+
 static void norm_add(NormList& nl, int& blocks, const float* Z, float* X, __nv_bfloat16* Xh, float* inv, int64_t rows) {
     if (rows <= 0) return;
     NormSeg& s = nl.s[nl.n++];
@@ -331,8 +340,15 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
     RUN(wv);
     TEAM_LAUNCH(ln_own_fwd_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
-    const int tgrid = d.B < 6 * NUM_SMS ? d.B : 6 * NUM_SMS;
-    TEAM_LAUNCH(table_rows_fwd_kernel, tgrid, TQ_WARPS * 32, 0, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
+    if (use_table2(d)) {          // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
+        const int groups = (d.B + TW - 1) / TW;
+        const size_t tsm = table2_fwd_smem_floats(d) * sizeof(float);
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        TEAM_LAUNCH(table_rows_fwd2_kernel, groups < NUM_SMS ? groups : NUM_SMS, TW * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
+    } else {
+        const int tgrid = d.B < 6 * NUM_SMS ? d.B : 6 * NUM_SMS;
+        TEAM_LAUNCH(table_rows_fwd_kernel, tgrid, TQ_WARPS * 32, 0, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
+    }
     if (want_cls) {
         // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
         if ((rc = cosine_logits_launch(cx.st, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
@@ -360,11 +376,20 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     const bool bf = cx.mode == TEAM_MODE_BF16;
     auto honly = [&](const Mat& m) { return bf ? Mat{nullptr, m.h, m.ld} : m; };
     // ---- table-query rows (prototype / state outputs)
-    const int tgrid = d.B < d.nctas ? d.B : d.nctas;
-    const size_t tsm = table_bwd_smem_floats(d) * sizeof(float);
-    TEAM_REQUIRE(tsm <= 200 * 1024, "head bwd: too many classes for the table-row kernel (%d)", d.C);
-    TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    TEAM_LAUNCH(table_rows_bwd_kernel, tgrid, TQ_WARPS * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
+    int tgrid;
+    if (use_table2(d)) {          // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
+        const int groups = (d.B + TW - 1) / TW;
+        tgrid = groups < NUM_SMS ? groups : NUM_SMS;
+        const size_t tsm = table2_bwd_smem_floats(d) * sizeof(float);
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        TEAM_LAUNCH(table_rows_bwd2_kernel, tgrid, TW * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
+    } else {
+        tgrid = d.B < d.nctas ? d.B : d.nctas;
+        const size_t tsm = table_bwd_smem_floats(d) * sizeof(float);
+        TEAM_REQUIRE(tsm <= 200 * 1024, "head bwd: too many classes for the table-row kernel (%d)", d.C);
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        TEAM_LAUNCH(table_rows_bwd_kernel, tgrid, TQ_WARPS * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
+    }
     // ---- own query rows
     int ogrid = (d.B + 7) / 8;
     if (ogrid > NUM_SMS) ogrid = NUM_SMS;
