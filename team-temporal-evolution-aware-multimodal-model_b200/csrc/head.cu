@@ -246,6 +246,53 @@ static int record_ready(cudaStream_t st, void* ev) {
     return TEAM_OK;
 }
 
+// ---- fork / join onto a per-thread side stream, so that independent kernels of one call run concurrently (under
+// stream capture the side stream joins the capture and the kernels become parallel branches of the graph).
+// Resources are created lazily per host thread and device; if that fails (e.g. creation refused during a capture)
+// the call simply stays on the caller's stream.  TEAM_NO_FORK=1 disables it (A/B runs).
+struct SideStream {
+    cudaStream_t st = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool tried = false;
+};
+static SideStream* side_stream() {
+    static thread_local SideStream tab[16];
+    static int off = -1;
+    if (off < 0) off = getenv("TEAM_NO_FORK") != nullptr ? 1 : 0;
+    if (off) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStream& s = tab[dev];
+    if (!s.tried) {
+        s.tried = true;
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            s.st = nullptr;
+        }
+    }
+    return s.st != nullptr ? &s : nullptr;
+}
+// returns the stream to launch the forked work on (the caller's own stream when forking is unavailable)
+static cudaStream_t fork_side(cudaStream_t main, SideStream** out) {
+    *out = nullptr;
+    SideStream* s = side_stream();
+    if (s == nullptr) return main;
+    if (cudaEventRecord(s->fork, main) != cudaSuccess || cudaStreamWaitEvent(s->st, s->fork, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return main;
+    }
+    *out = s;
+    return s->st;
+}
+static int join_side(cudaStream_t main, SideStream* s) {
+    if (s == nullptr) return TEAM_OK;
+    TEAM_CUDA_CHECK(cudaEventRecord(s->join, s->st));
+    TEAM_CUDA_CHECK(cudaStreamWaitEvent(main, s->join, 0));
+    return TEAM_OK;
+}
+
 // second-generation table-row kernels unless the head is too large for them or TEAM_TABLE_V1 is set (A/B runs)
 static bool use_table2(const HeadDims& d) {
     static int v1 = -1;
@@ -339,7 +386,14 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
     seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
     RUN(wv);
-    TEAM_LAUNCH(ln_own_fwd_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
+    // the own-row outputs and the classification logits do not depend on the table-query rows: side stream
+    SideStream* side = nullptr;
+    const cudaStream_t sst = fork_side(cx.st, &side);
+    TEAM_LAUNCH(ln_own_fwd_kernel, (d.B2 + 7) / 8, 256, 0, sst, d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
+    if (want_cls) {
+        // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
+        if ((rc = cosine_logits_launch(sst, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
+    }
     if (use_table2(d)) {          // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
         const int groups = (d.B + TW - 1) / TW;
         const size_t tsm = table2_fwd_smem_floats(d) * sizeof(float);
@@ -349,10 +403,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         const int tgrid = d.B < 6 * NUM_SMS ? d.B : 6 * NUM_SMS;
         TEAM_LAUNCH(table_rows_fwd_kernel, tgrid, TQ_WARPS * 32, 0, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
     }
-    if (want_cls) {
-        // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
-        if ((rc = cosine_logits_launch(cx.st, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
-    }
+    if ((rc = join_side(cx.st, side))) return rc;
     (void)none;
     return TEAM_OK;
 }

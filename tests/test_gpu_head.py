@@ -217,3 +217,54 @@ def test_grad_ready_events_inside_a_captured_step():
     d2 = 512 * 512
     assert torch.equal(got0, want[:d2]) and torch.equal(got1, want[d2:4 * d2])
     assert torch.equal(r.flat_grads, want)
+
+
+@pytest.mark.parametrize("mode_name,B,chunks", [("bf16", 4096, 8), ("f32", 2048, 4)])
+def test_large_batch_equals_its_chunks(mode_name, B, chunks):
+    """Full-size batches take other code paths than the small parity cases (persistent 128x256 GEMM + split-K
+    fix-up kernel, several rounds per CTA in the table-row kernels).  Size-independent properties pin them:
+      * every output row depends on its own sample only  -> one call on B samples == `chunks` calls on B/chunks,
+      * the parameter gradients are sums over samples     -> grad(B) == sum of the chunk gradients,
+      * the first 48 samples agree with the fp64 oracle run on those 48 samples alone."""
+    from team_b200 import head
+    mode = head.MODE_BF16 if mode_name == "bf16" else head.MODE_F32
+    dev = torch.device("cuda")
+    T = 10
+    C = 2 * T
+    params = synth.make_params(T, seed=77)
+    pack = head.HeadParamPack.from_state_dict({k: v.to(dev) for k, v in params.items()})
+    protos = synth.make_prototypes(C, seed=5)
+    batch = synth.make_batch(B, C, step=9, five_state=True)
+    cots = [c.reshape(B, 512) for c in synth.make_cotangents(B, step=9)]
+    text_cls = batch["text_cls"].to(dev)
+    img, txt, sid = batch["image"].to(dev), batch["text"].to(dev), batch["state"].to(dev)
+    cd = [c.to(dev) for c in cots]
+    full = head.HeadStepRunner(pack, protos.to(dev), B, C, mode)
+    full.step(img, txt, sid, text_cls, cd)
+    torch.cuda.synchronize()
+    outs_full, grad_full, am_full = full.outs.clone(), full.flat_grads.clone(), full.argmax.clone()
+    n = B // chunks
+    part = head.HeadStepRunner(pack, protos.to(dev), n, C, mode)
+    grad_sum = torch.zeros_like(grad_full, dtype=torch.float64)
+    tol_o, tol_g = (2e-3, 4e-3) if mode_name == "bf16" else (1e-5, 3e-5)
+    for c in range(chunks):
+        sl = slice(c * n, (c + 1) * n)
+        part.step(img[sl].contiguous(), txt[sl].contiguous(), sid[sl].contiguous(), text_cls, [x[sl].contiguous() for x in cd])
+        torch.cuda.synchronize()
+        for k in range(4):
+            assert rel(outs_full[k, sl], part.outs[k]) < tol_o, (c, k, rel(outs_full[k, sl], part.outs[k]))
+        assert (am_full[sl] == part.argmax).float().mean() > 0.999
+        grad_sum += part.flat_grads.double()
+    for name, view in full.grad_views.items():
+        lo = view.data_ptr() - full.flat_grads.data_ptr()
+        seg = slice(lo // 4, lo // 4 + view.numel())
+        e = rel(grad_full[seg], grad_sum[seg])
+        assert e < tol_g, (name, e)
+    # oracle on the first samples alone
+    m = 48
+    p64 = {k: v.double() for k, v in params.items()}
+    with torch.no_grad():
+        ref = O.forward_tri_modal(p64, batch["image"][:m].double(), batch["text"][:m].double(), batch["state"][:m], protos.double())
+    tol = 1e-2 if mode_name == "bf16" else 1e-5
+    for k, r in enumerate(ref[:4]):
+        assert rel(outs_full[k, :m], r.reshape(m, 512)) < tol, (k, rel(outs_full[k, :m], r.reshape(m, 512)))
