@@ -731,7 +731,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ PkGroup g) {
 }
 
 // Split-K fix-up of the persistent kernel: out = alpha * sum_s partial[s] (+ bias) (+ beta C), partials summed in
-// split order.  Block = 32 rows of one tile (256 threads, row-contiguous float4 accesses).
+// split order.  Block = 8 rows of one tile (256 threads, row-contiguous float4 accesses): 16 blocks per tile keep
+// all SMs busy even when a launch has only a handful of split tiles.
 struct PkFixProb {
     const float* partials;
     float* C;
@@ -754,12 +755,12 @@ pk_fixup_kernel(const __grid_constant__ PkFix f) {
         if ((int)blockIdx.x >= f.p[i].blk_begin) pi = i;
     const PkFixProb& P = f.p[pi];
     const int local = (int)blockIdx.x - P.blk_begin;
-    const int tile = local >> 2, rq = local & 3;
+    const int tile = local >> 4, rq = local & 15;
     const int bn = P.bn, lpr = bn >> 2, splits = P.splits;
-    const int m0 = (tile / P.tiles_n) * TC_BM + rq * 32, n0 = (tile % P.tiles_n) * bn;
-    const float* tile_part = P.partials + (size_t)tile * splits * (size_t)(TC_BM * bn) + (size_t)(rq * 32) * bn;
+    const int m0 = (tile / P.tiles_n) * TC_BM + rq * 8, n0 = (tile % P.tiles_n) * bn;
+    const float* tile_part = P.partials + (size_t)tile * splits * (size_t)(TC_BM * bn) + (size_t)(rq * 8) * bn;
     const bool acc_c = P.beta != 0.f && P.C != nullptr;
-    for (int idx = threadIdx.x; idx < 32 * lpr; idx += 256) {
+    for (int idx = threadIdx.x; idx < 8 * lpr; idx += 256) {
         const int rr = idx / lpr, c4 = idx - rr * lpr;
         const int row = m0 + rr, col = n0 + 4 * c4;
         if (row >= P.M || col >= P.N) continue;
@@ -1005,7 +1006,7 @@ static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, vo
             q.partials = p.partials; q.C = p.C; q.Cb = p.Cb; q.bias = p.bias; q.ldc = p.ldc; q.ldcb = p.ldcb;
             q.alpha = p.alpha; q.beta = p.beta; q.M = p.M; q.N = p.N; q.bn = p.bn; q.tiles_n = p.tiles_n;
             q.n_tiles = p.n_tiles; q.splits = p.splits; q.blk_begin = blocks;
-            blocks += 4 * p.n_tiles;
+            blocks += 16 * p.n_tiles;
         }
         TEAM_LAUNCH(pk_fixup_kernel, blocks, 256, 0, st, fx);
     }
