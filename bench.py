@@ -55,6 +55,23 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_dram_bytes_per_launch(kernel_prefix: str):
+    """Average DRAM bytes (read + write) per launch of a kernel from the committed `ncu --set full` summary of this
+    workload (profiles/, written by tools/ncu_summary.py); None if the file is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1h_ncu_full_B1024_T10_summary.csv")
+    if not os.path.exists(path):
+        return None, None
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    cols = [(i, scale.get(h[h.index("[") + 1:h.index("]")], None)) for i, h in enumerate(hdr) if h.startswith("dram__bytes_")]
+    vals = [sum(float(r[i]) * sc for i, sc in cols if sc) for r in rows[1:] if r[1].startswith(kernel_prefix)]
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), os.path.relpath(path, ROOT)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -327,8 +344,9 @@ def run_team(a):
     if dn > 0 and dms > 0:
         ach = dfl / (dms * 1e-3) / 1e12
         peak = pk["tensor_sustained"]
+        traffic, traffic_src = ncu_dram_bytes_per_launch("gemm_bf16_tcgen05") if dom == 1 else (None, None)
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": dby / dn,
                 "kernel": "gemm_bf16_tcgen05_kernel" if dom == 1 else "gemm_f32_kernel (fp32 FFMA; no tensor pipe)",
                 "launches_timed": dn, "avg_launch_us": dms * 1e3 / dn,
                 "share_of_step": (dms / nprof) / ms_per_step,
