@@ -196,6 +196,16 @@ int team_head_proof_fwd(const team_head_weights* w, int mode, int64_t batch, con
                         float* out_image, float* out_text, float* out_proto,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Class-text form of forward_tri_modal (utils/inc_net.py:528-580 when text has num_text != batch rows: the text
+ * rows are shared by all samples and the text output is the per-sample MEAN over them, :573-574).
+ * image_feat [B,512], text_feat [num_text,512], state_ids [B] int64; outputs [B,512] each.  Forward only (the learner
+ * always passes one text per sample, models/proof.py:421-425).
+ * workspace: team_head_workspace_bytes(batch, num_text + C, P, num_text, mode). */
+int team_head_tri_classtext_fwd(const team_head_weights* w, int mode, int64_t batch, const float* image_feat,
+                                const float* text_feat, int64_t num_text, const int64_t* state_ids,
+                                float* out_image, float* out_text, float* out_state, float* out_proto,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ gradient all-reduce over NVLink peer memory
  * The reference has no working multi-GPU path (its nn.DataParallel wrap crashes, models/proof.py:312-313 vs :248);
  * this is the exchange step of the data-parallel training step (the sum autograd would produce on one big batch,

@@ -129,6 +129,8 @@ def _declare(lib):
         lib.team_peer_allreduce_flag_bytes.argtypes = []
         lib.team_peer_allreduce_f32.restype = i32
         lib.team_peer_allreduce_f32.argtypes = [C.POINTER(vp), C.POINTER(vp), vp, i32, i32, i64, vp]
+        lib.team_head_tri_classtext_fwd.restype = i32
+        lib.team_head_tri_classtext_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]
         lib.team_head_proof_fwd.restype = i32
         lib.team_head_proof_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, i32, vp, vp, vp, vp, sz, vp]
         lib.team_head_encode_bwd.restype = i32

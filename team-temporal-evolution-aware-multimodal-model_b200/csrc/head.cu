@@ -633,6 +633,78 @@ extern "C" int team_head_proof_fwd(const team_head_weights* hw, int mode, int64_
     return TEAM_OK;
 }
 
+// Class-text form of forward_tri_modal (utils/inc_net.py:528-580 with num_text != batch): forward only.
+// workspace: team_head_workspace_bytes(batch, num_text + C, P, num_text, mode).
+extern "C" int team_head_tri_classtext_fwd(const team_head_weights* hw, int mode, int64_t batch, const float* image_feat,
+                                           const float* text_feat, int64_t num_text, const int64_t* state_ids,
+                                           float* out_image, float* out_text, float* out_state, float* out_proto,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+    HeadCtx cx;
+    int rc = validate(hw, mode, batch);
+    if (rc) return rc;
+    TEAM_REQUIRE(image_feat && text_feat && state_ids && out_image && out_text && out_state && out_proto, "head classtext fwd: null pointer");
+    TEAM_REQUIRE(num_text >= 1 && num_text <= 2048, "head classtext fwd: num_text %lld out of range", (long long)num_text);
+    TEAM_REQUIRE(hw->w_q && hw->w_k && hw->w_v && hw->w_fc && hw->b_fc && hw->ln_g && hw->ln_b && hw->prototypes && hw->state_emb, "head classtext fwd: null weight");
+    const int Tn = (int)num_text, C = hw->num_classes, P = hw->num_tasks * hw->prompts_per_task;
+    const int R = Tn + C;
+    cx.st = (cudaStream_t)stream;
+    cx.mode = mode;
+    cx.d = head_dims(batch, R, P, Tn);           // step rows: [Tn text | C prototypes | P prompts | 10 state-table rows]
+    head_plan(cx.d, mode, workspace, &cx.w);
+    if (workspace == nullptr || workspace_bytes < cx.w.total_bytes) {
+        set_error("head classtext fwd: workspace %zu < %zu bytes", workspace_bytes, cx.w.total_bytes);
+        return TEAM_EWORKSPACE;
+    }
+    TEAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "head: workspace must be 256-byte aligned");
+    const HeadDims& d = cx.d;
+    HeadWS& w = cx.w;
+    const int M = d.M, B = d.B;
+    bind_inputs(cx, hw, image_feat, nullptr, text_feat);
+    if ((rc = prologue(cx, hw, 3, image_feat, nullptr, text_feat, batch))) return rc;
+    const int fill_rows = P + (d.Nsp - d.Ns);
+    if (fill_rows > 0) {
+        TEAM_LAUNCH(fill_prompt_rows_kernel, fill_rows, 128, 0, cx.st, plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, R, d.Ns, d.Nsp, w.S.f, w.S.h);
+    }
+    Wave wv;
+    auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
+    auto honly = [&](const Mat& m) { return cx.mode == TEAM_MODE_BF16 ? Mat{nullptr, m.h, m.ld} : m; };
+    // ---- wave 1: projections (class-text rows, prototype rows, state table, image rows)
+    seg(wv.add(Tn, D, 0.f, fonly(w.Ztab, D), w.bsum[1]), false, w.tcls, false, w.Wsum[1], D);
+    seg(wv.add(C, D, 0.f, fonly(w.Ztab + (size_t)Tn * D, D), w.bsum[0]), false, w.protos, false, w.Wsum[0], D);
+    seg(wv.add(10, D, 0.f, fonly(w.Ztab + (size_t)R * D, D), w.bsum[2]), false, w.E, false, w.Wsum[2], D);
+    seg(wv.add(B, D, 0.f, fonly(w.Xo.f, D), w.bsum[0]), false, w.img, false, w.Wsum[0], D);
+    RUN(wv);
+    {
+        NormList nl;
+        memset(&nl, 0, sizeof(nl));
+        nl.do_normalize = 1;
+        int blocks = 0;
+        norm_add(nl, blocks, w.Ztab, w.S.f, w.S.h, w.invS, R);
+        norm_add(nl, blocks, w.Ztab + (size_t)R * D, w.S.f + (size_t)M * D, w.S.h ? w.S.h + (size_t)M * D : nullptr, w.invS + M, 10);
+        norm_add(nl, blocks, w.Xo.f, w.Xo.f, w.Xo.h, w.invo, B);
+        TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
+    }
+    seg(wv.add(d.Nsp, 3 * D, 0.f, honly(w.QKVs)), false, w.S, false, w.Wqkv, D);
+    seg(wv.add(B, 3 * D, 0.f, honly(w.QKVo)), false, w.Xo, false, w.Wqkv, D);
+    RUN(wv);
+    const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
+    const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
+    seg(wv.add(d.Nsp, D, 0.f, w.VFs), false, Vs, false, w.Wfc, D);
+    seg(wv.add(B, D, 0.f, fonly(w.VFo.f, D)), false, Vo, false, w.Wfc, D);
+    seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.TT, d.Nsp)), false, Qs, false, Ks, D);
+    seg(wv.add(B, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
+    seg(wv.add(B, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
+    RUN(wv);
+    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+    TEAM_LAUNCH(ct_attn_own_kernel, (B + 7) / 8, 256, 0, cx.st, B, M, d.Nsp, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, state_ids, w.Aext.f, w.Aext.h, w.aown);
+    seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
+    seg(wv.add(B, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
+    RUN(wv);
+    TEAM_LAUNCH(proof_ln_own_fwd_kernel, (B + 7) / 8, 256, 0, cx.st, B, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image);
+    TEAM_LAUNCH(ct_table_rows_fwd_kernel, (B + 7) / 8, 256, 0, cx.st, B, Tn, C, M, d.Nsp, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_text, out_state, out_proto);
+    return TEAM_OK;
+}
+
 // workspace: team_head_workspace_bytes(which <= 1 ? n_rows : 1, C, P, 0, mode)
 extern "C" int team_head_encode(const team_head_weights* hw, int mode, int which, const void* x, int64_t n_rows,
                                 int normalize, float* out, void* workspace, size_t workspace_bytes, void* stream) {

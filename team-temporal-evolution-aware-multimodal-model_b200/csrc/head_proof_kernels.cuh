@@ -135,4 +135,101 @@ proof_finalize_kernel(const float* __restrict__ partials, int nparts, int R, int
     }
 }
 
+// ------------------------------------------------------------------ class-text form of forward_tri_modal
+// (utils/inc_net.py:528-580 with text rows != batch): tokens of sample b = [image_b | Tn class-text rows | state_b |
+// C prototype rows | P prompt rows].  Own row: the image.  Shared keys: the M = Tn + C + P text / prototype / prompt
+// rows; per-sample keys: the own image key and the state-table row of the sample (column M + sid).  Returned:
+// image row, MEAN over the Tn text rows, state row, MEAN over the C prototype rows - all per sample.
+
+// softmax of the own (image) query over the M shared keys, the sample's state key and its own key
+__global__ void __launch_bounds__(256)
+ct_attn_own_kernel(int B, int M, int Nsp, const float* __restrict__ SQ, const float* __restrict__ QKVo,
+                   const __nv_bfloat16* __restrict__ QKVoh, const int64_t* __restrict__ state_ids,
+                   float* __restrict__ Aext, __nv_bfloat16* __restrict__ Aexth, float* __restrict__ aown) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const int scol = M + clamp_state(state_ids[row]);
+    float4 q[4], k[4];
+    const bool hq = QKVoh != nullptr;
+    ld_row_any(QKVo + (size_t)row * 3 * D, hq ? QKVoh + (size_t)row * 3 * D : nullptr, lane, q);
+    ld_row_any(QKVo + (size_t)row * 3 * D + D, hq ? QKVoh + (size_t)row * 3 * D + D : nullptr, lane, k);
+    const float s_own = warp_sum(dot_part(q, k)) * INV_TAU;
+    float mx = s_own;
+    for (int j = lane; j < Nsp; j += 32)
+        if (j < M || j == scol) mx = fmaxf(mx, SQ[(size_t)row * Nsp + j] * INV_TAU);
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < Nsp; j += 32) {
+        float p = 0.f;
+        if (j < M || j == scol) { p = expf(SQ[(size_t)row * Nsp + j] * INV_TAU - mx); z += p; }
+        Aext[(size_t)row * Nsp + j] = p;
+    }
+    const float p_own = expf(s_own - mx);
+    z = warp_sum(z) + p_own;
+    const float iz = 1.0f / z;
+    for (int j = lane; j < Nsp; j += 32) {
+        const float a = Aext[(size_t)row * Nsp + j] * iz;
+        Aext[(size_t)row * Nsp + j] = a;
+        if (Aexth != nullptr) Aexth[(size_t)row * Nsp + j] = __float2bfloat16_rn(a);
+    }
+    if (lane == 0) aown[row] = p_own * iz;
+}
+
+// table-query rows of one sample (warp per sample): Tn text rows, C prototype rows, the state row.
+// row r (step-row id): u = c_w NF_r + a_i VF_b + a_s VFs_srow + S_r + bfc -> LayerNorm; softmax over
+// {M shared keys (partial m_r, Z_r), own image key SK[b][r], state key TT[r][srow]}.
+__global__ void __launch_bounds__(256)
+ct_table_rows_fwd_kernel(int B, int Tn, int C, int M, int Nsp, const float* __restrict__ SK,
+                         const float* __restrict__ TT, const float* __restrict__ mt, const float* __restrict__ Zt,
+                         const float* __restrict__ NFt, const float* __restrict__ VFo, const float* __restrict__ VFs,
+                         const float* __restrict__ S, const float* __restrict__ bfc, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const int64_t* __restrict__ state_ids,
+                         float* __restrict__ out_text, float* __restrict__ out_state, float* __restrict__ out_proto) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int srow = M + clamp_state(state_ids[b]);
+    float4 vi[4], vs[4], bf[4], g[4], be[4], acc_t[4], acc_p[4];
+    ld_row(VFo + (size_t)b * D, lane, vi);
+    ld_row(VFs + (size_t)srow * D, lane, vs);
+    ld_row(bfc, lane, bf); ld_row(gamma, lane, g); ld_row(beta, lane, be);
+    zero_row(acc_t); zero_row(acc_p);
+    const int R = Tn + C;
+    for (int j = 0; j <= R; ++j) {
+        const int r = j < R ? j : srow;
+        const float s_i = SK[(size_t)b * Nsp + r] * INV_TAU;
+        const float s_s = TT[(size_t)r * Nsp + srow] * INV_TAU;
+        const float mr = mt[r];
+        const float m2 = fmaxf(mr, fmaxf(s_i, s_s));
+        const float c = expf(mr - m2), p_i = expf(s_i - m2), p_s = expf(s_s - m2);
+        const float w = 1.0f / (c * Zt[r] + p_i + p_s);
+        float4 u[4], t[4];
+        ld_row(NFt + (size_t)r * D, lane, u);
+        ld_row(S + (size_t)r * D, lane, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = fma4s(c * w, u[i], fma4s(p_i * w, vi[i], fma4s(p_s * w, vs[i], add4(t[i], bf[i]))));
+        const float mean = warp_sum(sum_part(u)) * (1.0f / D);
+        shift_row(u, -mean);
+        const float var = warp_sum(dot_part(u, u)) * (1.0f / D);
+        const float rstd = 1.0f / sqrtf(var + LN_EPS);
+        if (j < Tn) axpy_row(acc_t, rstd, u);
+        else if (j < R) axpy_row(acc_p, rstd, u);
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = fma4(mul4s(rstd, u[i]), g[i], be[i]);
+            st_row(out_state + (size_t)b * D, lane, u);
+        }
+    }
+    const float it = 1.0f / (float)Tn, ip = 1.0f / (float)C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc_t[i] = fma4(mul4s(it, acc_t[i]), g[i], be[i]); acc_p[i] = fma4(mul4s(ip, acc_p[i]), g[i], be[i]); }
+    st_row(out_text + (size_t)b * D, lane, acc_t);
+    st_row(out_proto + (size_t)b * D, lane, acc_p);
+}
+
 }  // namespace team

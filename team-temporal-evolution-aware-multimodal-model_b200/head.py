@@ -209,6 +209,32 @@ def forward_proof(pack: HeadParamPack, image: torch.Tensor, text: torch.Tensor, 
     return o_img, o_txt, o_pro
 
 
+def forward_tri_modal_class_text(pack: HeadParamPack, image: torch.Tensor, text: torch.Tensor, state_ids: torch.Tensor,
+                                 img_prototypes: torch.Tensor, *, mode: int = MODE_F32):
+    """``forward_tri_modal`` when ``text`` holds class texts ([Tn,512], Tn != batch; utils/inc_net.py:544-547,
+    :573-574): (image [B,512], text [B,512] = mean over the Tn text rows, state [B,512], proto [B,512]).  No autograd."""
+    capi.require_device()
+    if not image.is_cuda:
+        raise capi.TeamB200Error("forward_tri_modal needs CUDA tensors (no CPU fallback)")
+    dev = image.device
+    image, text, protos = _f32c(image, dev), _f32c(text, dev), _f32c(img_prototypes, dev)
+    sid = state_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    B, Tn = image.shape[0], text.shape[0]
+    if image.shape != (B, capi.D) or text.shape != (Tn, capi.D) or sid.shape != (B,) or B < 1 or Tn < 1:
+        raise ValueError("image must be [B,512], text [num_text,512], state_ids [B]")
+    flat = [_f32c(p, dev) for p in pack.flat]
+    hw = _fill_weights(pack.T, pack.ppt, flat, protos)
+    L = capi.lib()
+    nbytes = L.team_head_workspace_bytes(B, Tn + hw.num_classes, pack.T * pack.ppt, Tn, mode)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    outs = torch.empty((4, B, capi.D), dtype=torch.float32, device=dev)
+    capi.check(L.team_head_tri_classtext_fwd(C.byref(hw), mode, B, image.data_ptr(), text.data_ptr(), Tn, sid.data_ptr(),
+                                             outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+                                             ws.data_ptr(), nbytes, _stream_ptr()), "team_head_tri_classtext_fwd")
+    # a single text row is not averaged away by the reference: it comes back as [B,1,512] (utils/inc_net.py:573-574)
+    return outs[0], (outs[1].view(B, 1, capi.D) if Tn == 1 else outs[1]), outs[2], outs[3]
+
+
 class _EncodeFn(torch.autograd.Function):
     """encode_image / encode_text with autograd to the projections (the ClipLoss branch of the training
     step, models/proof.py:428-431).  No gradient flows into the (frozen-backbone) features."""

@@ -286,9 +286,11 @@ class Proof_Net(nn.Module):
             text = self.tokenizer(text)
             text = text.to(self._device) if torch.is_tensor(text) else text
         txt = self.convnet.encode_text(text)
-        if txt.shape[0] != img.shape[0]:
-            raise NotImplementedError("class-text form of forward_tri_modal (text rows != batch) has no CUDA path yet; "
-                                      "the learner always passes one text per sample")
+        if txt.shape[0] != img.shape[0]:          # class texts shared by all samples: text output = mean over them (forward only)
+            with torch.no_grad():
+                o = head.forward_tri_modal_class_text(self._pack(), img, txt, state_ids.to(self._device), self._protos(),
+                                                      mode=self.team_mode)
+            return o[0], o[1], o[2], o[3], self.convnet.logit_scale.exp()
         o = head.forward_tri_modal(self._pack(), img, txt, state_ids.to(self._device), self._protos(), mode=self.team_mode)
         return o[0], o[1], o[2], o[3], self.convnet.logit_scale.exp()
 

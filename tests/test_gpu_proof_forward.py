@@ -90,3 +90,38 @@ def test_proof_net_forward_surface(golden):
     img, txt, ls, pro = net.forward(b["image"].cuda(), b["text_cls"].cuda())
     assert rel(img, g["image"]) < 1e-5 and rel(txt, g["text"]) < 1e-5 and rel(pro, g["proto"]) < 1e-5
     assert rel(ls, g["logit_scale_exp"]) < 1e-6
+
+
+def test_tri_modal_class_text_vs_golden(golden):
+    """forward_tri_modal with class texts (text rows != batch): SURVEY 8a row a7, second input form."""
+    from team_b200 import head
+    dev = torch.device("cuda")
+    case, g = CASES["head_T2_B7_classtext"], golden("head_T2_B7_classtext")
+    ci = case_inputs(case)
+    b = ci["batch"]
+    outs = head.forward_tri_modal_class_text(_pack(ci["params"], dev), b["image"].to(dev), b["text_cls"].to(dev),
+                                             b["state"].to(dev), ci["protos"].to(dev), mode=head.MODE_F32)
+    for key, o in zip(("image", "text", "state", "proto"), outs):
+        assert tuple(o.shape) == g[key].shape, (key, o.shape, g[key].shape)
+        assert rel(o, g[key]) < 1e-5, (key, rel(o, g[key]))
+
+
+@pytest.mark.parametrize("T,B,Tn,five", [(10, 100, 20, True), (3, 33, 4, False), (2, 9, 1, False)])
+def test_tri_modal_class_text_vs_oracle(T, B, Tn, five):
+    from team_b200 import head
+    dev = torch.device("cuda")
+    C = 2 * T
+    params = synth.make_params(T, seed=400 + T)
+    protos = synth.make_prototypes(C, seed=13)
+    batch = synth.make_batch(B, C, step=50 + T, five_state=five)
+    text = synth.make_text_class_features(20)[:Tn].contiguous()
+    p64 = {k: v.double() for k, v in params.items()}
+    with torch.no_grad():
+        ref = O.forward_tri_modal(p64, batch["image"].double(), text.double(), batch["state"], protos.double())
+    pack = _pack(params, dev)
+    for mode, tol in ((head.MODE_F32, 1e-5), (head.MODE_BF16, 1e-2)):
+        outs = head.forward_tri_modal_class_text(pack, batch["image"].to(dev), text.to(dev), batch["state"].to(dev),
+                                                 protos.to(dev), mode=mode)
+        for key, o, r in zip(("image", "text", "state", "proto"), outs, ref[:4]):
+            assert tuple(o.shape) == tuple(r.shape), (key, o.shape, r.shape)
+            assert rel(o, r) < tol, (key, mode, rel(o, r))
