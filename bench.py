@@ -234,8 +234,7 @@ def run_team(a):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             peer, comm = None, "nccl (peer-memory all-reduce unavailable)"
-    runner = head.HeadStepRunner(pack, protos, B, C, mode, grad_events=comm == "nccl-buckets",
-                                 grad_buffer=peer.buffer if peer is not None else None)
+    runner = head.HeadStepRunner(pack, protos, B, C, mode, grad_events=comm == "nccl-buckets", peer=peer)
     stream = torch.cuda.Stream(device=dev)
 
     def eager_step(i):
@@ -258,9 +257,7 @@ def run_team(a):
             for j in range(rot):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
-                    runner.step(imgs[j], txts[j], sids[j], text_cls, cots[j])
-                    if peer is not None:
-                        peer()
+                    runner.step(imgs[j], txts[j], sids[j], text_cls, cots[j])      # N > 1: the exchange is inside the backward
                 graphs.append(g)
         torch.cuda.synchronize()
 
@@ -269,8 +266,6 @@ def run_team(a):
             graphs[i % rot].replay()
         else:
             eager_step(i)
-            if peer is not None:
-                peer()
         if world > 1 and peer is None:
             runner.allreduce_grads()                  # NCCL: the only per-step collective
 
@@ -369,7 +364,7 @@ def run_team(a):
         peer2 = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev) if peer is not None else None
         pipe = head.HostBatchPipeline(pack, protos, B, text_cls, mode=mode, depth=2, after_step=after,
                                       grad_events=comm == "nccl-buckets",
-                                      grad_buffer=peer2.buffer if peer2 is not None else None, in_graph=peer2)
+                                      peer=peer2)
         correct = [0]
 
         def e2e_step(i):
@@ -459,7 +454,7 @@ def run_team(a):
                            "cuda_graphs": graphs is not None,
                            "alg_flops_per_sample_survey": 55.07e6},
                 "roofline": roof, "at_scale": at_scale, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
-                "gpu_launches": (int(launches_per_step) + (1 if peer is not None else 0)) * a.steps,
+                "gpu_launches": int(launches_per_step) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
         print(json.dumps(line), flush=True)
     if world > 1:

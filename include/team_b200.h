@@ -125,6 +125,20 @@ typedef struct team_head_weights {
     int32_t reserved;
 } team_head_weights;
 
+/* Peer-memory gradient exchange folded into the backward (optional, see team_peer_allreduce_f32 for the meaning of
+ * the pointer tables): the gradient pointers of team_head_grads must then lie inside bufs[rank][0, n_total) with
+ * w_fc, w_q, w_k, w_v inside [0, split_at) and everything else at or beyond split_at.  The backward sums the early
+ * bucket over the ranks on a side stream as soon as it is final (after the q/k/v weight gradients), under its
+ * remaining kernels, and the late bucket after its last kernel. */
+typedef struct team_peer_comm {
+    void* bufs[8];
+    void* flags[8];
+    void* multicast;                         /* NVLS mapping of the buffers or NULL */
+    int32_t rank, world;
+    int64_t n_total;                         /* floats in the gradient buffer (multiple of 4) */
+    int64_t split_at;                        /* first float of the late bucket (multiple of 4) */
+} team_peer_comm;
+
 typedef struct team_head_grads {            /* all OVERWRITTEN by team_head_tri_bwd */
     float* w_img;  float* b_img;             /* newest task only (utils/inc_net.py:494-507) */
     float* w_text; float* b_text;
@@ -140,6 +154,7 @@ typedef struct team_head_grads {            /* all OVERWRITTEN by team_head_tri_
      * kernel ends).  Under stream capture they become external event-record nodes (cudaEventRecordExternal). */
     void* ev_w_fc;
     void* ev_w_qkv;
+    const team_peer_comm* comm;              /* NULL: no exchange inside the call */
 } team_head_grads;
 
 size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, int32_t num_prompts,

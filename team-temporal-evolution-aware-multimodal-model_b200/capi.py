@@ -40,10 +40,15 @@ class HeadWeights(C.Structure):
                 [("num_classes", C.c_int32), ("reserved", C.c_int32)])
 
 
+class PeerComm(C.Structure):
+    _fields_ = [("bufs", C.c_void_p * 8), ("flags", C.c_void_p * 8), ("multicast", C.c_void_p),
+                ("rank", C.c_int32), ("world", C.c_int32), ("n_total", C.c_int64), ("split_at", C.c_int64)]
+
+
 class HeadGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts", "state_emb",
-                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "ev_w_fc", "ev_w_qkv")]
+                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "ev_w_fc", "ev_w_qkv")] + [("comm", C.POINTER(PeerComm))]
 
 
 class TgcnBlock(C.Structure):

@@ -494,6 +494,21 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     }
     RUN(wv);
     if ((rc = record_ready(cx.st, gr->ev_w_qkv))) return rc;
+    // data-parallel: the early gradient bucket (w_fc, w_q, w_k, w_v) is final - sum it over the ranks on the side
+    // stream, under the remaining kernels of this call
+    SideStream* comm_side = nullptr;
+    const team_peer_comm* comm = gr->comm != nullptr && gr->comm->world > 1 ? gr->comm : nullptr;
+    if (comm != nullptr) {
+        const float* base = reinterpret_cast<const float*>(comm->bufs[comm->rank]);
+        auto inside = [&](const float* p, int64_t lo, int64_t hi) { return p >= base + lo && p + 1 <= base + hi; };
+        TEAM_REQUIRE(inside(gr->w_fc, 0, comm->split_at) && inside(gr->w_q, 0, comm->split_at) && inside(gr->w_k, 0, comm->split_at) &&
+                     inside(gr->w_v, 0, comm->split_at) && inside(gr->w_img, comm->split_at, comm->n_total) &&
+                     inside(gr->w_text, comm->split_at, comm->n_total) && inside(gr->w_state, comm->split_at, comm->n_total) &&
+                     inside(gr->state_emb, comm->split_at, comm->n_total) && inside(gr->b_fc, comm->split_at, comm->n_total),
+                     "head bwd: gradient pointers do not match the peer-comm buckets");
+        const cudaStream_t cst = fork_side(cx.st, &comm_side);
+        if (comm_side != nullptr && (rc = peer_allreduce_range(cst, comm, 0, comm->split_at))) return rc;
+    }
     // ---- normalisation backward of own rows, prototype rows and state-table rows (+ bias-gradient partials)
     NrmList nl;
     memset(&nl, 0, sizeof(nl));
@@ -533,6 +548,14 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
         fa.dbfc_parts = w.dbfc_parts; fa.dbfc = gr->b_fc;
         TEAM_LAUNCH(finish_bwd_kernel, 4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st, fa);
+    }
+    if (comm != nullptr) {
+        if (comm_side != nullptr) {
+            if ((rc = join_side(cx.st, comm_side))) return rc;
+        } else if ((rc = peer_allreduce_range(cx.st, comm, 0, comm->split_at))) {      // no side stream: both at the end
+            return rc;
+        }
+        if ((rc = peer_allreduce_range(cx.st, comm, comm->split_at, comm->n_total - comm->split_at))) return rc;
     }
     return TEAM_OK;
 }

@@ -127,6 +127,24 @@ peer_allreduce_f32_kernel(const __grid_constant__ ArArgs a) {
     ar_barrier(a, 1, epoch, true);
 }
 
+// all-reduce of floats [offset, offset + n) of the buffers described by `c` (both multiples of 4)
+int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offset, int64_t n) {
+    TEAM_REQUIRE(c != nullptr && c->world >= 1 && c->world <= AR_MAX_RANKS && c->rank >= 0 && c->rank < c->world, "peer_allreduce: bad comm");
+    TEAM_REQUIRE(offset >= 0 && n >= 0 && offset % 4 == 0 && n % 4 == 0 && offset + n <= c->n_total, "peer_allreduce: range [%lld, +%lld) of %lld", (long long)offset, (long long)n, (long long)c->n_total);
+    if (n == 0 || c->world == 1) return TEAM_OK;
+    ArArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < c->world; ++r) {
+        TEAM_REQUIRE(c->bufs[r] != nullptr && c->flags[r] != nullptr && (reinterpret_cast<uintptr_t>(c->bufs[r]) & 15) == 0, "peer_allreduce: bad pointer of rank %d", r);
+        a.buf[r] = reinterpret_cast<float*>(c->bufs[r]) + offset;
+        a.flag[r] = reinterpret_cast<uint32_t*>(c->flags[r]);
+    }
+    a.mc = c->multicast != nullptr ? reinterpret_cast<float*>(c->multicast) + offset : nullptr;
+    a.rank = c->rank; a.world = c->world; a.n4 = n / 4;
+    TEAM_LAUNCH(peer_allreduce_f32_kernel, AR_BLOCKS, AR_THREADS, 0, st, a);
+    return TEAM_OK;
+}
+
 }  // namespace team
 
 using namespace team;

@@ -332,10 +332,15 @@ class HeadStepRunner:
     parallelism)."""
 
     def __init__(self, pack: HeadParamPack, img_prototypes: torch.Tensor, batch: int, num_text_cls: int,
-                 mode: int = MODE_F32, grad_events: bool = False, grad_buffer: Optional[torch.Tensor] = None):
+                 mode: int = MODE_F32, grad_events: bool = False, grad_buffer: Optional[torch.Tensor] = None,
+                 peer=None):
+        """``peer``: a ``parallel.PeerAllReduce`` whose ``buffer`` becomes the gradient buffer; the backward then
+        sums the gradients over the ranks itself (early bucket under its last kernels, late bucket at its end)."""
         capi.require_device()
         dev = pack.flat[0].device
         self.dev, self.B, self.mode, self.n_cls = dev, batch, mode, num_text_cls
+        if peer is not None:
+            grad_buffer = peer.buffer
         self.pack = pack
         self.flat = [_f32c(p, dev) for p in pack.flat]
         self.protos = _f32c(img_prototypes, dev)
@@ -362,6 +367,10 @@ class HeadStepRunner:
             self.grad_views[name] = v
             setattr(self.hg, name, v.data_ptr())
             off += sz
+        self._comm = None
+        if peer is not None:
+            self._comm = peer.comm_struct(4 * capi.D * capi.D)       # early bucket = w_fc, w_q, w_k, w_v
+            self.hg.comm = C.pointer(self._comm)
         # all-reduce buckets in the order the backward completes them (see team_head_grads.ev_*)
         d2 = capi.D * capi.D
         self.buckets = (self.flat_grads[:d2], self.flat_grads[d2:4 * d2], self.flat_grads[4 * d2:])
@@ -439,7 +448,7 @@ class HostBatchPipeline:
 
     def __init__(self, pack: HeadParamPack, img_prototypes: torch.Tensor, batch: int, text_cls: torch.Tensor,
                  mode: int = MODE_F32, depth: int = 2, after_step=None, grad_events: bool = False,
-                 grad_buffer: Optional[torch.Tensor] = None, in_graph=None):
+                 grad_buffer: Optional[torch.Tensor] = None, in_graph=None, peer=None):
         capi.require_device()
         if depth < 1:
             raise ValueError("depth must be >= 1")
@@ -447,7 +456,7 @@ class HostBatchPipeline:
         self.dev, self.B, self.depth, self.after_step = dev, batch, depth, after_step
         self.text_cls = _f32c(text_cls, dev)
         self.runner = HeadStepRunner(pack, img_prototypes, batch, int(self.text_cls.shape[0]), mode,
-                                     grad_events=grad_events, grad_buffer=grad_buffer)
+                                     grad_events=grad_events, grad_buffer=grad_buffer, peer=peer)
         self.in_graph = in_graph                 # optional callable captured right after the step (e.g. PeerAllReduce)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.compute_stream = torch.cuda.Stream(device=dev)

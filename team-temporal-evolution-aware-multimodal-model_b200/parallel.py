@@ -129,6 +129,18 @@ class PeerAllReduce:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks take the same path
         self.multicast_ptr = mc if int(ok.item()) else 0
 
+    def comm_struct(self, split_at: int):
+        """ctypes ``team_peer_comm`` for ``team_head_grads.comm``: the backward then sums ``buffer[:split_at]`` over the
+        ranks on a side stream as soon as it is final and ``buffer[split_at:]`` after its last kernel."""
+        from . import capi
+        c = capi.PeerComm()
+        for r in range(self.world):
+            c.bufs[r] = int(self._hb.buffer_ptrs[r])
+            c.flags[r] = int(self._hf.buffer_ptrs[r])
+        c.multicast = self.multicast_ptr or None
+        c.rank, c.world, c.n_total, c.split_at = self.rank, self.world, self.numel, int(split_at)
+        return c
+
     def __call__(self, stream=None):
         """Enqueue the all-reduce of ``buffer`` on ``stream`` (default: the current stream); capturable."""
         from . import capi
