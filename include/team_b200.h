@@ -221,6 +221,24 @@ int team_head_tri_classtext_fwd(const team_head_weights* w, int mode, int64_t ba
                                 float* out_image, float* out_text, float* out_state, float* out_proto,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ losses of the training step (SURVEY 8f "next")
+ * Replaces: unicl_loss (evolution_features = None)        models/proof.py:21-191, called at :434-441
+ *           ClipLoss.forward (world_size 1)               utils/toolkit.py:128-141, called at :431
+ * Both return the loss value(s) on the device AND the gradient w.r.t. their feature inputs times grad_scale (the
+ * learner's weights: total = ce + clip + 0.3 unicl, models/proof.py:442), i.e. the cotangents of team_head_tri_bwd /
+ * team_head_encode_bwd - loss forward and backward are one call.  batch <= 16384 (B x B similarities).
+ * team_unicl_loss: image/text/state [B,512] fp32 as returned by forward_tri_modal (un-normalised), labels [B] int64,
+ *   temperature = the dynamic temperature of :111-116 (host scalar); losses[3] = {total, instance, category}.
+ * team_clip_loss: image/text [B,512] as handed to ClipLoss (the learner normalises them first), logit_scale host scalar. */
+size_t team_loss_workspace_bytes(int64_t batch);
+int team_unicl_loss(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
+                    int64_t batch, float temperature, float grad_scale, float* losses,
+                    float* g_image, float* g_text, float* g_state,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int team_clip_loss(int mode, const float* image, const float* text, int64_t batch, float logit_scale, float grad_scale,
+                   float* loss, float* g_image, float* g_text,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ gradient all-reduce over NVLink peer memory
  * The reference has no working multi-GPU path (its nn.DataParallel wrap crashes, models/proof.py:312-313 vs :248);
  * this is the exchange step of the data-parallel training step (the sum autograd would produce on one big batch,

@@ -33,6 +33,10 @@ CASES: Dict[str, dict] = {
     "evolve_20cls": {"kind": "evolve", "T": 10, "num_classes": 20, "seed": 48, "proto_seed": 1007},
     "state_distance_forward": {"kind": "state_distance_forward", "B": 64, "seed": 4000},
     "dynamic_gcn": {"kind": "dynamic_gcn", "N": 12, "E": 30, "seed": 5000},
+    # losses of the training step: unicl_loss (evolution_features=None) and ClipLoss, values + input grads
+    "unicl_B24": {"kind": "unicl", "B": 24, "C": 6, "seed": 6000, "epoch": 3, "max_epoch": 10},
+    "unicl_B9_static_tau": {"kind": "unicl", "B": 9, "C": 20, "seed": 6001, "epoch": None, "max_epoch": None},
+    "clip_B16": {"kind": "clip", "B": 16, "seed": 6002, "logit_scale": 14.285714},
 }
 
 
@@ -76,6 +80,17 @@ def case_inputs(case: dict) -> dict:
         sid = torch.tensor([0, 1, 3, 4, 2, 4, 1, 4], dtype=torch.int64)[
             torch.randint(0, 8, (case["B"],), generator=g)]
         return {"feat": feat, "sid": sid}
+    if kind in ("unicl", "clip"):
+        g = torch.Generator(device="cpu").manual_seed(case["seed"])
+        B = case["B"]
+        base = torch.randn((B, 512), generator=g)
+        noise = 2.0 if kind == "clip" else 0.7                                          # loss values of order 1
+        feats = [base + noise * torch.randn((B, 512), generator=g) for _ in range(3)]    # correlated, un-normalised
+        if kind == "clip":
+            return {"image": F.normalize(feats[0], dim=1), "text": F.normalize(feats[1], dim=1)}
+        labels = torch.randint(0, case["C"], (B,), generator=g, dtype=torch.int64)
+        states = torch.tensor([1, 3, 4], dtype=torch.int64)[torch.randint(0, 3, (B,), generator=g)]
+        return {"image": feats[0], "text": feats[1].reshape(B, 1, 512), "state": feats[2], "labels": labels, "states": states}
     if kind == "dynamic_gcn":
         g = torch.Generator(device="cpu").manual_seed(case["seed"])
         N, E = case["N"], case["E"]

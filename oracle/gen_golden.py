@@ -219,7 +219,30 @@ def gen_dynamic_gcn(case):
     return {"out": _np(out)}
 
 
-GENERATORS = {"head": gen_head, "proof_forward": gen_proof_forward,
+def gen_unicl(case):
+    ref_loader.install_stubs()
+    from models.proof import unicl_loss
+    ci = case_inputs(case)
+    x = [ci[k].clone().requires_grad_(True) for k in ("image", "text", "state")]
+    total, info = unicl_loss(x[0], x[1], x[2], ci["labels"], ci["states"], state_distance=None,
+                             epoch=case["epoch"], max_epoch=case["max_epoch"], evolution_features=None)
+    total.backward()
+    return {"total": _np(total.detach()), "instance": np.float64(info["instance_loss"]), "category": np.float64(info["category_loss"]),
+            "temperature": np.float64(info["temperature"]), "g_image": _np(x[0].grad), "g_text": _np(x[1].grad.reshape(-1, 512)),
+            "g_state": _np(x[2].grad)}
+
+
+def gen_clip(case):
+    ref_loader.install_stubs()
+    from utils.toolkit import ClipLoss
+    ci = case_inputs(case)
+    x = [ci[k].clone().requires_grad_(True) for k in ("image", "text")]
+    loss = ClipLoss()(x[0], x[1], torch.tensor(case["logit_scale"]))
+    loss.backward()
+    return {"loss": _np(loss.detach()), "g_image": _np(x[0].grad), "g_text": _np(x[1].grad)}
+
+
+GENERATORS = {"head": gen_head, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward,
               "cosine_linear": gen_cosine_linear, "cal_prototype": gen_cal_prototype,
               "simplecil": gen_simplecil, "evolve": gen_evolve,
               "state_distance_forward": gen_state_distance_forward,
@@ -230,7 +253,10 @@ def main():
     assert ref_loader.available(), "reference not mounted; golden vectors can only be generated in the build container"
     os.makedirs(OUT_DIR, exist_ok=True)
     torch.set_num_threads(1)           # deterministic reduction order on the generating box
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         res = GENERATORS[case["kind"]](case)
         path = os.path.join(OUT_DIR, name + ".npz")
         np.savez_compressed(path, **res)

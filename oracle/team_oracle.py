@@ -160,6 +160,49 @@ def forward_proof(p: Params, image, text, img_prototypes):
     return img_o.view(B, -1), txt_o.view(nt, -1), p["convnet.logit_scale"].exp(), pr_o.view(npr, -1)
 
 
+# --------------------------------------------------------------------------- 8f: losses of the training step
+def unicl_loss(image_features, text_features, state_features, labels, temperature=0.07, epoch=None, max_epoch=None):
+    """unicl_loss with evolution_features=None: models/proof.py:21-191 (normalise :44-46, dynamic temperature
+    :111-116, instance term :126-149 incl. the exp(row_sim * mask) quirk (the masked self entry counts as
+    exp(0) = 1), category term :151-174, weights :177-179).  Returns (total, instance, category) as tensors."""
+    B = image_features.shape[0]
+    im = F.normalize(image_features.reshape(B, -1), dim=1)
+    tx = F.normalize(text_features.reshape(B, -1), dim=1)
+    st = F.normalize(state_features.reshape(B, -1), dim=1)
+    if epoch is not None and max_epoch is not None:
+        progress = float(epoch) / float(max_epoch)
+        tau = temperature * (0.5 + 0.5 * 0.5 * (1.0 + math.cos(math.pi * progress)))
+    else:
+        tau = temperature
+    tri = torch.stack([im, tx, st], dim=1)                       # [B,3,D]
+    sim = torch.matmul(tri, tri.transpose(1, 2)) / tau           # [B,3,3]
+    eye = torch.eye(3, dtype=sim.dtype)
+    pos = torch.exp(sim * (1 - eye)).sum(-1)                     # self entry -> exp(0)
+    allv = torch.exp(sim).sum(-1)
+    instance = -(torch.log(pos / (allv + 1e-8))).sum() / (3 * B)
+    lm = (labels.unsqueeze(1) == labels.unsqueeze(0)).to(sim.dtype)
+    sm = 1 - torch.eye(B, dtype=sim.dtype)
+    lm = lm * sm
+    ii = im @ im.t() / tau
+    ex = torch.exp(ii - ii.max(dim=1, keepdim=True).values)
+    p = (ex * lm).sum(1)
+    a = (ex * sm).sum(1)
+    valid = (p > 0) & (a > 0)
+    if bool(valid.any()):
+        category = -(torch.log(p[valid] / (a[valid] + 1e-8))).sum() / int(valid.sum())
+    else:
+        category = torch.zeros((), dtype=sim.dtype)
+    return instance + 0.5 * category, instance, category
+
+
+def clip_loss(image_features, text_features, logit_scale):
+    """ClipLoss.forward, world_size 1: utils/toolkit.py:110-141."""
+    li = logit_scale * image_features @ text_features.t()
+    lt = logit_scale * text_features @ image_features.t()
+    y = torch.arange(li.shape[0])
+    return (F.cross_entropy(li, y) + F.cross_entropy(lt, y)) / 2
+
+
 # --------------------------------------------------------------------------- a9/a10
 def forward_for_classification(p: Params, image, text_cls):
     """Learner.forward_for_classification: models/proof.py:519-536."""

@@ -134,6 +134,12 @@ def _declare(lib):
         lib.team_peer_allreduce_flag_bytes.argtypes = []
         lib.team_peer_allreduce_f32.restype = i32
         lib.team_peer_allreduce_f32.argtypes = [C.POINTER(vp), C.POINTER(vp), vp, i32, i32, i64, vp]
+        lib.team_loss_workspace_bytes.restype = sz
+        lib.team_loss_workspace_bytes.argtypes = [i64]
+        lib.team_unicl_loss.restype = i32
+        lib.team_unicl_loss.argtypes = [i32, vp, vp, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, sz, vp]
+        lib.team_clip_loss.restype = i32
+        lib.team_clip_loss.argtypes = [i32, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp]
         lib.team_head_tri_classtext_fwd.restype = i32
         lib.team_head_tri_classtext_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]
         lib.team_head_proof_fwd.restype = i32

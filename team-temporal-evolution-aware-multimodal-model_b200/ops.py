@@ -107,3 +107,56 @@ def cosine_logits(x: torch.Tensor, weight: torch.Tensor, sigma: Optional[torch.T
     if want_logits and want_argmax:
         return logits, amax
     return logits if want_logits else amax
+
+
+def dynamic_temperature(temperature: float = 0.07, epoch=None, max_epoch=None) -> float:
+    """models/proof.py:111-116."""
+    import math
+    if epoch is None or max_epoch is None:
+        return float(temperature)
+    progress = float(epoch) / float(max_epoch)
+    return float(temperature * (0.5 + 0.5 * 0.5 * (1.0 + math.cos(math.pi * progress))))
+
+
+def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, labels: torch.Tensor, *,
+               temperature: float = 0.07, epoch=None, max_epoch=None, grad_scale: float = 1.0, mode: int = capi.MODE_F32):
+    """unicl_loss (models/proof.py:21-191, evolution_features=None) forward + gradient in one call.
+    Returns (losses [3] = total / instance / category on the device, (g_image, g_text, g_state) [B,512] =
+    grad_scale * d total / d input) - the gradients are the cotangents of the head's backward."""
+    capi.require_device()
+    B = image.shape[0]
+    xs = [_chk_rows(t.detach().reshape(B, -1).float(), n) for t, n in ((image, "image"), (text, "text"), (state, "state"))]
+    y = labels.detach().to(device=xs[0].device, dtype=torch.int64).contiguous()
+    L = capi.lib()
+    nbytes = L.team_loss_workspace_bytes(B)
+    if nbytes == 0:
+        raise ValueError(f"unicl_loss: batch {B} out of range")
+    dev = xs[0].device
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    losses = torch.empty((3,), dtype=torch.float32, device=dev)
+    grads = torch.empty((3, B, capi.D), dtype=torch.float32, device=dev)
+    capi.check(L.team_unicl_loss(mode, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), y.data_ptr(), B,
+                                 dynamic_temperature(temperature, epoch, max_epoch), float(grad_scale), losses.data_ptr(),
+                                 grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ws.data_ptr(), nbytes,
+                                 _stream_ptr()), "team_unicl_loss")
+    return losses, (grads[0], grads[1], grads[2])
+
+
+def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, grad_scale: float = 1.0,
+              mode: int = capi.MODE_F32):
+    """ClipLoss.forward (utils/toolkit.py:128-141, world_size 1) forward + gradient: (loss [1], (g_image, g_text))."""
+    capi.require_device()
+    B = image.shape[0]
+    xi, xt = _chk_rows(image.detach().float(), "image"), _chk_rows(text.detach().float(), "text")
+    L = capi.lib()
+    nbytes = L.team_loss_workspace_bytes(B)
+    if nbytes == 0:
+        raise ValueError(f"clip_loss: batch {B} out of range")
+    dev = xi.device
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    grads = torch.empty((2, B, capi.D), dtype=torch.float32, device=dev)
+    capi.check(L.team_clip_loss(mode, xi.data_ptr(), xt.data_ptr(), B, float(logit_scale), float(grad_scale),
+                                loss.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(), ws.data_ptr(), nbytes,
+                                _stream_ptr()), "team_clip_loss")
+    return loss, (grads[0], grads[1])

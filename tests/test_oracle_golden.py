@@ -179,3 +179,27 @@ def test_known_answer_constants():
     assert list(zip([e[0] for e in edges], [e[1] for e in edges], w)) == [
         (0, 1, 0.0), (2, 3, 0.0), (4, 5, .5), (4, 6, 0.0), (5, 6, .5), (0, 4, .5), (1, 6, .5),
         (4, 0, .5), (6, 1, .5)]
+
+
+@pytest.mark.parametrize("name", ["unicl_B24", "unicl_B9_static_tau"])
+def test_unicl_loss(name, golden):
+    """unicl_loss (models/proof.py:21-191, evolution_features=None): values and input gradients of the REAL reference."""
+    case, g = CASES[name], golden(name)
+    ci = case_inputs(case)
+    x = [ci[k].clone().double().requires_grad_(True) for k in ("image", "text", "state")]
+    total, inst, cat = O.unicl_loss(x[0], x[1], x[2], ci["labels"], epoch=case["epoch"], max_epoch=case["max_epoch"])
+    total.backward()
+    assert rel_err(total.detach(), g["total"]) < 1e-6
+    assert abs(float(inst) - float(g["instance"])) < 1e-6 and abs(float(cat) - float(g["category"])) < 1e-6
+    for k, t in zip(("g_image", "g_text", "g_state"), x):
+        assert rel_err(t.grad.reshape(-1, 512), g[k]) < 2e-6, k
+
+
+def test_clip_loss(golden):
+    case, g = CASES["clip_B16"], golden("clip_B16")
+    ci = case_inputs(case)
+    x = [ci[k].clone().double().requires_grad_(True) for k in ("image", "text")]
+    loss = O.clip_loss(x[0], x[1], case["logit_scale"])
+    loss.backward()
+    assert rel_err(loss.detach(), g["loss"]) < 1e-6
+    assert rel_err(x[0].grad, g["g_image"]) < 2e-6 and rel_err(x[1].grad, g["g_text"]) < 2e-6
