@@ -250,34 +250,43 @@ static int record_ready(cudaStream_t st, void* ev) {
 // stream capture the side stream joins the capture and the kernels become parallel branches of the graph).
 // Resources are created lazily per host thread and device; if that fails (e.g. creation refused during a capture)
 // the call simply stays on the caller's stream.  TEAM_NO_FORK=1 disables it (A/B runs).
-struct SideStream {
+struct SideStream {                 // one lane: a stream and its fork / join events
     cudaStream_t st = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
-    bool tried = false;
 };
-static SideStream* side_stream() {
-    static thread_local SideStream tab[16];
+struct SideLanes {
+    SideStream lane[2];             // 0: independent compute kernels, 1: the gradient exchange
+    bool tried = false, ok = false;
+};
+static SideStream* side_stream(int lane) {
+    static thread_local SideLanes tab[16];
     static int off = -1;
     if (off < 0) off = getenv("TEAM_NO_FORK") != nullptr ? 1 : 0;
     if (off) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    SideStream& s = tab[dev];
-    if (!s.tried) {
-        s.tried = true;
-        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            s.st = nullptr;
+    SideLanes& t = tab[dev];
+    if (!t.tried) {
+        t.tried = true;
+        t.ok = true;
+        for (int i = 0; i < 2; ++i) {
+            SideStream& s = t.lane[i];
+            if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+                cudaGetLastError();
+                t.ok = false;
+            }
         }
     }
-    return s.st != nullptr ? &s : nullptr;
+    return t.ok ? &t.lane[lane] : nullptr;
 }
-// returns the stream to launch the forked work on (the caller's own stream when forking is unavailable)
-static cudaStream_t fork_side(cudaStream_t main, SideStream** out) {
+// make the lane wait for everything enqueued on `main` so far; returns the stream to launch the forked work on
+// (the caller's own stream when forking is unavailable).  May be called again on an already forked lane to add a
+// later dependency (the second gradient bucket).
+static cudaStream_t fork_side(cudaStream_t main, SideStream** out, int lane = 0) {
     *out = nullptr;
-    SideStream* s = side_stream();
+    SideStream* s = side_stream(lane);
     if (s == nullptr) return main;
     if (cudaEventRecord(s->fork, main) != cudaSuccess || cudaStreamWaitEvent(s->st, s->fork, 0) != cudaSuccess) {
         cudaGetLastError();
@@ -340,11 +349,14 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     HeadWS& w = cx.w;
     const bool want_cls = d.Tc > 0 && (cls_logits != nullptr || cls_argmax != nullptr);
     bind_inputs(cx, hw, image_feat, text_feat, text_cls);
-    if ((rc = prologue(cx, hw, 3, image_feat, text_feat, want_cls ? text_cls : nullptr, batch))) return rc;
+    SideStream* side = nullptr;
     const int fill_rows = d.P + (d.Nsp - d.Ns);
-    if (fill_rows > 0) {
-        TEAM_LAUNCH(fill_prompt_rows_kernel, fill_rows, 128, 0, cx.st, plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S.f, w.S.h);
+    if (fill_rows > 0) {          // prompt rows of S: independent of the prologue -> side lane
+        const cudaStream_t fst = fork_side(cx.st, &side);
+        TEAM_LAUNCH(fill_prompt_rows_kernel, fill_rows, 128, 0, fst, plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S.f, w.S.h);
     }
+    if ((rc = prologue(cx, hw, 3, image_feat, text_feat, want_cls ? text_cls : nullptr, batch))) return rc;
+    if ((rc = join_side(cx.st, side))) return rc;
     Wave wv;
     const Mat none{nullptr, nullptr, 0};
     auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
@@ -380,14 +392,17 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
     RUN(wv);
-    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
-    TEAM_LAUNCH(attn_own_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, state_ids, w.Aext.f, w.Aext.h, w.aown);
+    {   // the two softmax kernels (step-row table, own rows) are independent
+        const cudaStream_t tst = fork_side(cx.st, &side);
+        TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, tst, w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+        TEAM_LAUNCH(attn_own_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, state_ids, w.Aext.f, w.Aext.h, w.aown);
+        if ((rc = join_side(cx.st, side))) return rc;
+    }
     // ---- wave 4: probabilities x (fc-space) values
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
     seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
     RUN(wv);
     // the own-row outputs and the classification logits do not depend on the table-query rows: side stream
-    SideStream* side = nullptr;
     const cudaStream_t sst = fork_side(cx.st, &side);
     TEAM_LAUNCH(ln_own_fwd_kernel, (d.B2 + 7) / 8, 256, 0, sst, d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
     if (want_cls) {
@@ -470,8 +485,11 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     RUN(wv);
     {   // dS = Aext .* (dA - rowdot) / tau (in place);  dTT += Pt .* (G VFs^T - h) / tau
         const int64_t n4 = (int64_t)d.B2 * d.Nsp / 4;
+        SideStream* sd = nullptr;
+        const cudaStream_t dst = fork_side(cx.st, &sd);
+        TEAM_LAUNCH(dtt_kernel, (d.Nsp * d.Nsp + 255) / 256, 256, 0, dst, d.Nsp, d.M, w.Pt.f, w.tmpNN, w.hfull, w.dTT.f, w.dTT.h);
         TEAM_LAUNCH(ds_kernel, (unsigned)((n4 + 255) / 256), 256, 0, cx.st, n4, d.Nsp / 4, w.Aext.f, w.rowdot, w.SQ.f, w.SQ.h, bf ? 0 : 1);
-        TEAM_LAUNCH(dtt_kernel, (d.Nsp * d.Nsp + 255) / 256, 256, 0, cx.st, d.Nsp, d.M, w.Pt.f, w.tmpNN, w.hfull, w.dTT.f, w.dTT.h);
+        if ((rc = join_side(cx.st, sd))) return rc;
     }
     const Mat& dS = w.SQ;
     // ---- wave 7: score gradients -> dQ/dK, fc folded into V, dWfc
@@ -483,6 +501,22 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     seg(seg(wv.add(D, D, 0.f, fonly(gr->w_fc, D)), true, w.dVFo, true, Vo, d.B2), true, w.dVFs, true, Vs, d.Nsp);  // dWfc = dVFo^T Vo + dVFs^T Vs
     RUN(wv);
     if ((rc = record_ready(cx.st, gr->ev_w_fc))) return rc;
+    // data-parallel: gradient buckets are summed over the ranks on the comm lane as soon as they are final, under
+    // the remaining kernels of this call: w_fc now, w_q / w_k / w_v after wave 8, everything else at the end
+    SideStream* comm_side = nullptr;
+    const team_peer_comm* comm = gr->comm != nullptr && gr->comm->world > 1 ? gr->comm : nullptr;
+    const int64_t DD = (int64_t)D * D;
+    if (comm != nullptr) {
+        const float* base = reinterpret_cast<const float*>(comm->bufs[comm->rank]);
+        auto inside = [&](const float* p, int64_t lo, int64_t hi) { return p >= base + lo && p + 1 <= base + hi; };
+        TEAM_REQUIRE(comm->split_at >= DD && gr->w_fc == base && inside(gr->w_q, DD, comm->split_at) && inside(gr->w_k, DD, comm->split_at) &&
+                     inside(gr->w_v, DD, comm->split_at) && inside(gr->w_img, comm->split_at, comm->n_total) &&
+                     inside(gr->w_text, comm->split_at, comm->n_total) && inside(gr->w_state, comm->split_at, comm->n_total) &&
+                     inside(gr->state_emb, comm->split_at, comm->n_total) && inside(gr->b_fc, comm->split_at, comm->n_total),
+                     "head bwd: gradient pointers do not match the peer-comm buckets");
+        const cudaStream_t cst = fork_side(cx.st, &comm_side, 1);
+        if (comm_side != nullptr && (rc = peer_allreduce_range(cst, comm, 0, DD))) return rc;
+    }
     TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, cx.st, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, w.dQKVo.h);
     // ---- wave 8: through the packed q/k/v projection
     seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
@@ -494,20 +528,14 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     }
     RUN(wv);
     if ((rc = record_ready(cx.st, gr->ev_w_qkv))) return rc;
-    // data-parallel: the early gradient bucket (w_fc, w_q, w_k, w_v) is final - sum it over the ranks on the side
-    // stream, under the remaining kernels of this call
-    SideStream* comm_side = nullptr;
-    const team_peer_comm* comm = gr->comm != nullptr && gr->comm->world > 1 ? gr->comm : nullptr;
-    if (comm != nullptr) {
-        const float* base = reinterpret_cast<const float*>(comm->bufs[comm->rank]);
-        auto inside = [&](const float* p, int64_t lo, int64_t hi) { return p >= base + lo && p + 1 <= base + hi; };
-        TEAM_REQUIRE(inside(gr->w_fc, 0, comm->split_at) && inside(gr->w_q, 0, comm->split_at) && inside(gr->w_k, 0, comm->split_at) &&
-                     inside(gr->w_v, 0, comm->split_at) && inside(gr->w_img, comm->split_at, comm->n_total) &&
-                     inside(gr->w_text, comm->split_at, comm->n_total) && inside(gr->w_state, comm->split_at, comm->n_total) &&
-                     inside(gr->state_emb, comm->split_at, comm->n_total) && inside(gr->b_fc, comm->split_at, comm->n_total),
-                     "head bwd: gradient pointers do not match the peer-comm buckets");
-        const cudaStream_t cst = fork_side(cx.st, &comm_side);
-        if (comm_side != nullptr && (rc = peer_allreduce_range(cst, comm, 0, comm->split_at))) return rc;
+    if (comm != nullptr && comm_side != nullptr) {
+        SideStream* again = nullptr;
+        const cudaStream_t cst = fork_side(cx.st, &again, 1);            // second dependency of the same lane
+        if (again != nullptr) {
+            if ((rc = peer_allreduce_range(cst, comm, DD, comm->split_at - DD))) return rc;
+        } else {
+            comm_side = nullptr;      // cannot happen once the lane exists; keep the end-of-call fallback consistent
+        }
     }
     // ---- normalisation backward of own rows, prototype rows and state-table rows (+ bias-gradient partials)
     NrmList nl;
@@ -533,6 +561,18 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         add(w.Rfull, w.S.f, w.invS, w.dZtab.f + (size_t)d.C * D, w.dZtab.h ? w.dZtab.h + (size_t)d.C * D : nullptr, 10, d.M);   // dzs
         TEAM_LAUNCH(nrm_bwd_kernel, blocks, 256, 0, cx.st, nl);
     }
+    // the bias / prompt gradients (finish_bwd) only need the partials of nrm_bwd: side lane, beside wave 9
+    SideStream* fin_side = nullptr;
+    {
+        const cudaStream_t fst = fork_side(cx.st, &fin_side);
+        FinishArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        for (int i = 0; i < 4; ++i) { fa.part[i] = nl.s[i].partial; fa.nblk[i] = nblk[i]; }
+        fa.b_img = gr->b_img; fa.b_text = gr->b_text; fa.b_state = gr->b_state;
+        fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
+        fa.dbfc_parts = w.dbfc_parts; fa.dbfc = gr->b_fc;
+        TEAM_LAUNCH(finish_bwd_kernel, 4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, fst, fa);
+    }
     // ---- wave 9: gradients of the newest projections and of the state embedding
     const Mat dz0 = sub(w.dXo, 0, 0), dz1 = sub(w.dXo, d.B, 0), dzp = sub(w.dZtab, 0, 0), dzs = sub(w.dZtab, d.C, 0);
     seg(seg(wv.add(D, D, 0.f, fonly(gr->w_img, D)), true, dz0, true, w.img, d.B), true, dzp, true, w.protos, d.C);  // dWi = dz0^T x + dzp^T protos
@@ -540,19 +580,11 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(D, D, 0.f, fonly(gr->w_state, D)), true, dzs, true, w.E, 10);
     seg(wv.add(10, D, 0.f, fonly(gr->state_emb, D)), false, dzs, true, w.Wsum[2], D);                              // dE = dzs Ws
     RUN(wv);
-    {
-        FinishArgs fa;
-        memset(&fa, 0, sizeof(fa));
-        for (int i = 0; i < 4; ++i) { fa.part[i] = nl.s[i].partial; fa.nblk[i] = nblk[i]; }
-        fa.b_img = gr->b_img; fa.b_text = gr->b_text; fa.b_state = gr->b_state;
-        fa.Rfull = w.Rfull; fa.prompts = d.P > 0 ? gr->prompts : nullptr; fa.C = d.C; fa.P = d.P;
-        fa.dbfc_parts = w.dbfc_parts; fa.dbfc = gr->b_fc;
-        TEAM_LAUNCH(finish_bwd_kernel, 4 + (fa.prompts ? (d.P + 3) / 4 : 0), 512, 0, cx.st, fa);
-    }
+    if ((rc = join_side(cx.st, fin_side))) return rc;
     if (comm != nullptr) {
         if (comm_side != nullptr) {
             if ((rc = join_side(cx.st, comm_side))) return rc;
-        } else if ((rc = peer_allreduce_range(cx.st, comm, 0, comm->split_at))) {      // no side stream: both at the end
+        } else if ((rc = peer_allreduce_range(cx.st, comm, 0, comm->split_at))) {      // no side lanes: everything at the end
             return rc;
         }
         if ((rc = peer_allreduce_range(cx.st, comm, comm->split_at, comm->n_total - comm->split_at))) return rc;

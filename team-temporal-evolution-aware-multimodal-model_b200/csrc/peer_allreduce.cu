@@ -96,7 +96,7 @@ peer_allreduce_f32_kernel(const __grid_constant__ ArArgs a) {
         // out (multimem.st), so each rank moves 2/W of the buffer over its own links instead of 2 (W-1)/W
         float4* mc = reinterpret_cast<float4*>(a.mc);
         constexpr int U = 4;                                   // independent round trips in flight per thread
-        const long long stride = (long long)AR_BLOCKS * AR_THREADS;
+        const long long stride = (long long)gridDim.x * AR_THREADS;
         for (long long i0 = c0 + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i0 < c1; i0 += U * stride) {
             float4 s[U];
 #pragma unroll
@@ -111,7 +111,7 @@ peer_allreduce_f32_kernel(const __grid_constant__ ArArgs a) {
                                  ::"l"(mc + i0 + u * stride), "f"(s[u].x), "f"(s[u].y), "f"(s[u].z), "f"(s[u].w) : "memory");
         }
     } else
-    for (long long i = c0 + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < c1; i += (long long)AR_BLOCKS * AR_THREADS) {
+    for (long long i = c0 + (long long)blockIdx.x * AR_THREADS + threadIdx.x; i < c1; i += (long long)gridDim.x * AR_THREADS) {
         float4 v[AR_MAX_RANKS];
 #pragma unroll
         for (int r = 0; r < AR_MAX_RANKS; ++r)
@@ -125,6 +125,17 @@ peer_allreduce_f32_kernel(const __grid_constant__ ArArgs a) {
             if (r < W) reinterpret_cast<float4*>(a.buf[r])[i] = s;
     }
     ar_barrier(a, 1, epoch, true);
+}
+
+// Blocks per call: about two float4 per thread of a rank's slice, between 8 and AR_BLOCKS.  A small bucket that is
+// exchanged UNDER compute kernels should not park 64 spinning blocks on the SMs those kernels need; every rank
+// derives the same grid from the same n, and each block keeps its own epoch, so grids may differ between calls.
+static int ar_grid(int64_t n4, int world) {
+    const int64_t per_rank = (n4 + world - 1) / world;
+    int64_t g = (per_rank + 2 * AR_THREADS - 1) / (2 * AR_THREADS);
+    if (g < 8) g = 8;
+    if (g > AR_BLOCKS) g = AR_BLOCKS;
+    return (int)g;
 }
 
 // all-reduce of floats [offset, offset + n) of the buffers described by `c` (both multiples of 4)
@@ -141,7 +152,7 @@ int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offse
     }
     a.mc = c->multicast != nullptr ? reinterpret_cast<float*>(c->multicast) + offset : nullptr;
     a.rank = c->rank; a.world = c->world; a.n4 = n / 4;
-    TEAM_LAUNCH(peer_allreduce_f32_kernel, AR_BLOCKS, AR_THREADS, 0, st, a);
+    TEAM_LAUNCH(peer_allreduce_f32_kernel, ar_grid(a.n4, a.world), AR_THREADS, 0, st, a);
     return TEAM_OK;
 }
 
@@ -166,6 +177,6 @@ extern "C" int team_peer_allreduce_f32(void* const* bufs, void* const* flags, vo
     }
     a.mc = reinterpret_cast<float*>(multicast);
     a.rank = rank; a.world = world; a.n4 = n / 4;
-    TEAM_LAUNCH(peer_allreduce_f32_kernel, AR_BLOCKS, AR_THREADS, 0, (cudaStream_t)stream, a);
+    TEAM_LAUNCH(peer_allreduce_f32_kernel, ar_grid(a.n4, a.world), AR_THREADS, 0, (cudaStream_t)stream, a);
     return TEAM_OK;
 }

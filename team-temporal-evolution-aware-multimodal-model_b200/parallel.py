@@ -124,7 +124,8 @@ class PeerAllReduce:
         vp8 = C.c_void_p * self.world
         self._bufs = vp8(*[int(p) for p in self._hb.buffer_ptrs])
         self._flgs = vp8(*[int(p) for p in self._hf.buffer_ptrs])
-        mc = int(getattr(self._hb, "multicast_ptr", 0) or 0) if multicast else 0
+        # measured: the switch-side reduction (multimem) wins from 4 ranks up; at 2 ranks plain peer loads are faster
+        mc = int(getattr(self._hb, "multicast_ptr", 0) or 0) if (multicast and self.world >= 4) else 0
         ok = torch.tensor([1 if mc else 0], device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)      # all ranks take the same path
         self.multicast_ptr = mc if int(ok.item()) else 0
