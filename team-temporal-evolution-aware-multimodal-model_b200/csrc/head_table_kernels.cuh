@@ -77,10 +77,15 @@ table_rows_fwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
             ld_row(tabS + (size_t)tr * D, lane, t);
 #pragma unroll
             for (int i = 0; i < 4; ++i) u[i] = fma4s(rw.c_w, u[i], fma4s(rw.a_i, vi[i], fma4s(rw.a_t, vt[i], fma4s(rw.a_s, vs[i], t[i]))));
-            const float mean = warp_sum(sum_part(u)) * (1.0f / D);
-            shift_row(u, -mean);
-            const float var = warp_sum(dot_part(u, u)) * (1.0f / D);
+            // one reduction stage for both LayerNorm statistics (sum and sum of squares, interleaved shuffles):
+            // the serial shuffle chains, not the arithmetic, set the time per row of this kernel
+            float s1 = sum_part(u), s2 = dot_part(u, u);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            const float mean = s1 * (1.0f / D);
+            const float var = fmaxf(s2 * (1.0f / D) - mean * mean, 0.f);
             const float rstd = 1.0f / sqrtf(var + LN_EPS);
+            shift_row(u, -mean);
             if (k < d.C) {
                 axpy_row(acc, rstd, u);
             } else {
@@ -191,11 +196,6 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
                 for (int i = 0; i < 4; ++i) ybar[i] = fma4s(rw.c_w, ybar[i], fma4s(rw.a_i, vi[i], fma4s(rw.a_t, vt[i], mul4s(rw.a_s, vs[i]))));
                 ld_row(tabS + (size_t)tr * D, lane, xh);
                 add_row(xh, ybar);
-                const float mean = warp_sum(sum_part(xh)) * (1.0f / D);
-                shift_row(xh, -mean);
-                const float var = warp_sum(dot_part(xh, xh)) * (1.0f / D);
-                const float rstd = 1.0f / sqrtf(var + LN_EPS);
-                scale_row(xh, rstd);
                 float m1;
                 if (is_proto) {
 #pragma unroll
@@ -209,7 +209,21 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
                     for (int i = 0; i < 4; ++i) gg[i] = mul4(gg[i], g4[i]);
                     m1 = m1s;
                 }
-                const float m2 = warp_sum(dot_part(gg, xh)) * (1.0f / D);
+                // ONE reduction stage for mean, variance and m2 = mean(gg .* xhat): sum u, sum u^2, sum gg u (interleaved
+                // shuffles); m2 = rstd (sum gg u - mean sum gg) / D with sum gg = D m1.  The serial shuffle chains set the
+                // time per row here, so three stages folded into one is worth more than the extra multiply-adds.
+                float s1 = sum_part(xh), s2 = dot_part(xh, xh), s3 = dot_part(gg, xh);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                }
+                const float mean = s1 * (1.0f / D);
+                const float var = fmaxf(s2 * (1.0f / D) - mean * mean, 0.f);
+                const float rstd = 1.0f / sqrtf(var + LN_EPS);
+                const float m2 = rstd * (s3 * (1.0f / D) - mean * m1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xh[i] = mul4s(rstd, add4s(-mean, xh[i]));
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gg[i] = mul4s(rstd, fma4s(-m2, xh[i], add4s(-m1, gg[i])));     // dY
                 float p_yy = dot_part(gg, ybar), p_i = dot_part(gg, vi), p_t = dot_part(gg, vt), p_s = dot_part(gg, vs);
