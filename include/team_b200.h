@@ -239,6 +239,14 @@ int team_clip_loss(int mode, const float* image, const float* text, int64_t batc
                    float* loss, float* g_image, float* g_text,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused multi-tensor AdamW step (SURVEY 8f "next").
+ * Replaces: torch.optim.AdamW(...).step()    models/proof.py:361, :445  (decoupled weight decay, bias correction,
+ * amsgrad off).  params / grads / exp_avg / exp_avg_sq: HOST arrays of n_tensors device pointers (fp32, numel[i]
+ * elements each, at most 48 per call); step = 1 for the first update.  One launch, element-wise, capturable. */
+int team_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int64_t step, void* stream);
+
 /* ------------------------------------------------------------------ gradient all-reduce over NVLink peer memory
  * The reference has no working multi-GPU path (its nn.DataParallel wrap crashes, models/proof.py:312-313 vs :248);
  * this is the exchange step of the data-parallel training step (the sum autograd would produce on one big batch,

@@ -134,6 +134,9 @@ def _declare(lib):
         lib.team_peer_allreduce_flag_bytes.argtypes = []
         lib.team_peer_allreduce_f32.restype = i32
         lib.team_peer_allreduce_f32.argtypes = [C.POINTER(vp), C.POINTER(vp), vp, i32, i32, i64, vp]
+        lib.team_adamw_step.restype = i32
+        lib.team_adamw_step.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64),
+                                        C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64, vp]
         lib.team_loss_workspace_bytes.restype = sz
         lib.team_loss_workspace_bytes.argtypes = [i64]
         lib.team_unicl_loss.restype = i32

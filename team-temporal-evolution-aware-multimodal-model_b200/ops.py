@@ -160,3 +160,46 @@ def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, gr
                                 loss.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(), ws.data_ptr(), nbytes,
                                 _stream_ptr()), "team_clip_loss")
     return loss, (grads[0], grads[1])
+
+
+class FusedAdamW:
+    """torch.optim.AdamW(params, lr, betas, eps, weight_decay).step() (models/proof.py:361, :445) as ONE kernel over
+    all tensors (``team_adamw_step``).  ``step(grads)`` takes the gradients as a list aligned with ``params`` (e.g.
+    views of ``HeadStepRunner.flat_grads``) or uses ``p.grad``; tensors whose gradient is None are skipped.
+    ``lr`` may be changed between steps (the learner's cosine schedule, models/proof.py:363)."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        capi.require_device()
+        self.params = [p for p in params if p.requires_grad]
+        for p in self.params:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise capi.TeamB200Error("FusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)")
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self.steps = [0] * len(self.params)      # per tensor, like torch: a tensor without gradient does not advance
+
+    @torch.no_grad()
+    def step(self, grads=None):
+        import ctypes as C
+        if grads is None:
+            grads = [p.grad for p in self.params]
+        by_step = {}
+        for i, g in enumerate(grads):
+            if g is None:
+                continue
+            self.steps[i] += 1
+            by_step.setdefault(self.steps[i], []).append(i)
+        L = capi.lib()
+        for t, idx in by_step.items():           # normally one group: every tensor has seen the same number of steps
+            for lo in range(0, len(idx), 48):
+                chunk = idx[lo:lo + 48]
+                n = len(chunk)
+                vp = C.c_void_p * n
+                gs = [grads[i].detach().to(torch.float32).contiguous() for i in chunk]
+                capi.check(L.team_adamw_step(n, vp(*[self.params[i].data_ptr() for i in chunk]), vp(*[g.data_ptr() for g in gs]),
+                                             vp(*[self.exp_avg[i].data_ptr() for i in chunk]),
+                                             vp(*[self.exp_avg_sq[i].data_ptr() for i in chunk]),
+                                             (C.c_int64 * n)(*[self.params[i].numel() for i in chunk]), float(self.lr),
+                                             float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                             float(self.weight_decay), t, _stream_ptr()), "team_adamw_step")
