@@ -175,6 +175,9 @@ int team_head_tri_fwd(const team_head_weights* w, int mode, int64_t batch,
                       float* cls_logits, int64_t* cls_argmax,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* g_proto may be NULL = a zero cotangent for the prototype output (what the learner's losses produce: neither
+ * unicl_loss nor ClipLoss reads proto_feats, models/proof.py:434-442); the C prototype query rows of every sample
+ * are then skipped in the backward. */
 int team_head_tri_bwd(const team_head_weights* w, int mode, int64_t batch,
                       const float* image_feat, const float* text_feat, const int64_t* state_ids,
                       const float* g_image, const float* g_text, const float* g_state,

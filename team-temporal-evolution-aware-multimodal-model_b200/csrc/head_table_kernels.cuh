@@ -156,7 +156,7 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
             {   // GG rows (cotangent .* gamma) for the coefficient GEMM; zero the sparse rows of this sample
                 float4 g4[4], gs[4];
                 ld_row(gam, lane, g4);
-                ld_row(g_proto + (size_t)b * D, lane, ggp);
+                if (g_proto != nullptr) ld_row(g_proto + (size_t)b * D, lane, ggp); else zero_row(ggp);
                 ld_row(g_state + (size_t)b * D, lane, gs);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { ggp[i] = mul4(mul4s(invC, ggp[i]), g4[i]); gs[i] = mul4(gs[i], g4[i]); }
@@ -186,7 +186,9 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
             float4 acc_i[4], acc_t[4], acc_s[4], xs[4];
             zero_row(acc_i); zero_row(acc_t); zero_row(acc_s); zero_row(xs);
             float k_alpha = 0.f, k_beta = 0.f, k_mean = 0.f, k_m1 = 0.f, k_yy = 0.f, k_i = 0.f, k_t = 0.f, k_s = 0.f;
-            for (int k = 0; k <= d.C; ++k) {
+            // g_proto == NULL (the learner's losses never touch the prototype output, models/proof.py:434-442): the C
+            // prototype rows have a zero cotangent, so only the state row is differentiated
+            for (int k = g_proto != nullptr ? 0 : d.C; k <= d.C; ++k) {
                 const TableRowW rw = shfl_row_weights(mine, k);
                 const bool is_proto = k < d.C;
                 const int tr = is_proto ? k : d.C + sid;
@@ -240,7 +242,7 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
                 } else {
                     // last row: dgamma / dbeta contributions of this sample: gp .* sum_{j<C} xhat_j + gs .* xhat_state, gp C + gs
                     float4 gp[4], gs[4];
-                    ld_row(g_proto + (size_t)b * D, lane, gp);
+                    if (g_proto != nullptr) ld_row(g_proto + (size_t)b * D, lane, gp); else zero_row(gp);
                     ld_row(g_state + (size_t)b * D, lane, gs);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {

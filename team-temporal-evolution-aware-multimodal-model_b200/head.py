@@ -107,7 +107,7 @@ class _TriModalFn(torch.autograd.Function):
             ws.data_ptr(), nbytes, _stream_ptr()), "team_head_tri_fwd")
         ctx.hold = (image, text, sid, protos, flat, ws)
         ctx.meta = (mode, T, ppt, B, nbytes)
-        ctx.set_materialize_grads(True)
+        ctx.set_materialize_grads(False)        # an unused output arrives as None: a None g_proto skips the prototype rows
         res = (outs[0], outs[1].view(B, 1, capi.D), outs[2], outs[3])
         if n_cls:
             ctx.mark_non_differentiable(logits, amax)
@@ -130,10 +130,19 @@ class _TriModalFn(torch.autograd.Function):
         hg = capi.HeadGrads()
         for k, v in g.items():
             setattr(hg, k, v.data_ptr())
-        cots = [_f32c(x.reshape(B, capi.D), dev) for x in (g_img, g_txt, g_st, g_pr)]
+        zeros = None
+        cots = []
+        for k, x in enumerate((g_img, g_txt, g_st, g_pr)):
+            if x is None:
+                if k == 3:
+                    cots.append(None)
+                    continue
+                zeros = zeros if zeros is not None else torch.zeros((B, capi.D), dtype=torch.float32, device=dev)
+                x = zeros
+            cots.append(_f32c(x.reshape(B, capi.D), dev))
         capi.check(capi.lib().team_head_tri_bwd(
             C.byref(hw), mode, B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
-            cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr(),
+            cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr() if cots[3] is not None else None,
             C.byref(hg), ws.data_ptr(), nbytes, _stream_ptr()), "team_head_tri_bwd")
         need = ctx.needs_input_grad[8:]
         out: List[Optional[torch.Tensor]] = []
@@ -423,9 +432,10 @@ class HeadStepRunner:
             self.ws.data_ptr(), self.nbytes, _stream_ptr()), "team_head_tri_fwd")
 
     def backward(self, image, text, sid, cots):
+        """``cots[3]`` (cotangent of the prototype output) may be None: the prototype rows are then skipped."""
         capi.check(capi.lib().team_head_tri_bwd(
             C.byref(self.hw), self.mode, self.B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
-            cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr(),
+            cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr() if cots[3] is not None else None,
             C.byref(self.hg), self.ws.data_ptr(), self.nbytes, _stream_ptr()), "team_head_tri_bwd")
 
     def step(self, image, text, sid, text_cls, cots):

@@ -268,3 +268,45 @@ def test_large_batch_equals_its_chunks(mode_name, B, chunks):
     tol = 1e-2 if mode_name == "bf16" else 1e-5
     for k, r in enumerate(ref[:4]):
         assert rel(outs_full[k, :m], r.reshape(m, 512)) < tol, (k, rel(outs_full[k, :m], r.reshape(m, 512)))
+
+
+@pytest.mark.parametrize("mode_name", ["f32", "bf16"])
+def test_null_proto_cotangent_equals_zero_cotangent(mode_name):
+    """g_proto = NULL (the learner's losses never read the prototype output) skips the C prototype rows of every
+    sample in the backward; the gradients must equal those of an explicit all-zero cotangent, and through autograd an
+    unused prototype output takes the same path."""
+    from team_b200 import head
+    mode = head.MODE_BF16 if mode_name == "bf16" else head.MODE_F32
+    dev = torch.device("cuda")
+    T, B = 4, 70
+    C = 2 * T
+    params = synth.make_params(T, seed=31)
+    pdev = {k: v.to(dev) for k, v in params.items()}
+    pack = head.HeadParamPack.from_state_dict(pdev)
+    protos = synth.make_prototypes(C, seed=8).to(dev)
+    text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
+    b = synth.make_batch(B, C, step=6, five_state=True)
+    img, txt, sid = b["image"].to(dev), b["text"].to(dev), b["state"].to(dev)
+    cots = [c.reshape(B, 512).to(dev) for c in synth.make_cotangents(B, step=6)]
+    r = head.HeadStepRunner(pack, protos, B, C, mode)
+    r.forward(img, txt, sid, text_cls)
+    r.backward(img, txt, sid, [cots[0], cots[1], cots[2], torch.zeros_like(cots[3])])
+    torch.cuda.synchronize()
+    want = r.flat_grads.clone()
+    r.forward(img, txt, sid, text_cls)
+    r.backward(img, txt, sid, [cots[0], cots[1], cots[2], None])
+    torch.cuda.synchronize()
+    assert rel(r.flat_grads, want) < 1e-6, rel(r.flat_grads, want)
+    # autograd: a loss that ignores the prototype output
+    names = O.trainable_names(params)
+    p = {k: v.clone().requires_grad_(k in names) for k, v in pdev.items()}
+    outs = head.forward_tri_modal(head.HeadParamPack.from_state_dict(p), img, txt, sid, protos, mode=mode)
+    loss = (outs[0] * cots[0]).sum() + (outs[1].reshape(B, 512) * cots[1]).sum() + (outs[2] * cots[2]).sum()
+    grads = torch.autograd.grad(loss, [p[n] for n in names], allow_unused=True)
+    got = {n: g for n, g in zip(names, grads) if g is not None}
+    for name, view in r.grad_views.items():
+        key = {"w_q": "sel_attn.w_qs.weight", "w_fc": "sel_attn.fc.weight", "state_emb": "state_embedder.state_embeddings.weight",
+               "w_img": f"projs_img.{T - 1}.MLP.0.weight"}.get(name)
+        if key is not None:
+            lo = (view.data_ptr() - r.flat_grads.data_ptr()) // 4
+            assert rel(got[key].reshape(-1), want[lo:lo + view.numel()]) < 1e-6, name
