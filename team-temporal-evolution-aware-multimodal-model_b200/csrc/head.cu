@@ -334,7 +334,8 @@ extern "C" size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, 
         if (_rc != TEAM_OK) return _rc;               \
     } while (0)
 
-// Forward: 12 launches (prologue, prompt rows, 4 GEMM waves, 6 row kernels) - see DESIGN.md section 4.
+// Forward: 13 launches (prologue, prompt rows, 4 GEMM waves, 7 row kernels; three short side-lane branches) - see
+// DESIGN.md section 4.
 extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t batch, const float* image_feat,
                                  const float* text_feat, const int64_t* state_ids, const float* text_cls,
                                  int64_t num_text_cls, float* out_image, float* out_text, float* out_state,
@@ -423,7 +424,8 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     return TEAM_OK;
 }
 
-// Backward: 15 launches (5 GEMM waves, 10 row kernels); needs the workspace of the matching forward call.
+// Backward: 13 launches at the headline size (5 GEMM waves, 8 row kernels; more when split-K runs through the fix-up
+// kernel or the gradient exchange is folded in); needs the workspace of the matching forward call.
 extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t batch, const float* image_feat,
                                  const float* text_feat, const int64_t* state_ids, const float* g_image,
                                  const float* g_text, const float* g_state, const float* g_proto,
