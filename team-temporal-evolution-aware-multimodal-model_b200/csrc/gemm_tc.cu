@@ -1013,6 +1013,20 @@ static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, vo
     return TEAM_OK;
 }
 
+// co-resident CTA budget of a launch whose cluster size is `cluster` (TEAM_GEMM_CTAS_C2 / _C4 / _C8 override)
+static int tc_target_ctas(int cluster) {
+    static int cap[4] = {-1, -1, -1, -1};
+    if (cap[0] < 0) {
+        const char* names[4] = {nullptr, "TEAM_GEMM_CTAS_C2", "TEAM_GEMM_CTAS_C4", "TEAM_GEMM_CTAS_C8"};
+        const int defaults[4] = {TC_TARGET_CTAS, TC_TARGET_CTAS, 272, 240};      // measured at B = 1024: -2 % step time
+        for (int i = 3; i >= 0; --i) {
+            const char* e = names[i] != nullptr ? getenv(names[i]) : nullptr;
+            cap[i] = e != nullptr ? atoi(e) : defaults[i];
+        }
+    }
+    return cap[cluster >= 8 ? 3 : cluster >= 4 ? 2 : cluster >= 2 ? 1 : 0];
+}
+
 static int pk_min_tiles() {
     static int v = -1;
     if (v < 0) {
@@ -1111,7 +1125,11 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
                 const int per = (nkbs[i] + s - 1) / s;
                 const int per2 = (nkbs[i] + 2 * s - 1) / (2 * s);
                 const bool valid = 2 * s <= TC_MAX_SPLITS && (2 * s - 1) * per2 < nkbs[i];     // every split keeps >= 1 k-block
-                if (per > best_kb && valid && total + tiles[i] * s <= TC_TARGET_CTAS) { best = i; best_kb = per; }
+                // the launch's cluster size is its largest split: clusters are placed GPC by GPC, so a launch of
+                // 8-CTA clusters holds fewer co-resident CTAs than 2 per SM (a late second wave of clusters costs ~10 us)
+                int cl = 2 * s;
+                for (int q = 0; q < np; ++q) cl = grp.p[q].splits > cl ? grp.p[q].splits : cl;
+                if (per > best_kb && valid && total + tiles[i] * s <= tc_target_ctas(cl)) { best = i; best_kb = per; }
             }
             if (best < 0) break;
             total += tiles[best] * grp.p[best].splits;
