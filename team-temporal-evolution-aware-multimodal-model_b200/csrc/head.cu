@@ -48,7 +48,7 @@ void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     w->Aext = mat(B2, Nsp); w->aown = take(B2 * 2);
     w->Ybo = take(B2 * D);
     w->dYo = mat(B2, D); w->rowdot = take(B2); w->dsown = take(B2 * 2);
-    w->dSK = mat(B2, Nsp); w->dVFo = mat(B2, D);
+    w->dSK = mat(B2, Nsp); w->dVFo = mat(B2, D); w->dVFo_own = take(B2 * D);
     w->dQKVo = mat(B2, 3 * D); w->dXo = mat(B2, D);
     w->Rfull = take(Nsp * D); w->Gfull = mat(Nsp, D); w->hfull = take(Nsp);
     w->dTT = mat(Nsp, Nsp); w->tmpNN = take(Nsp * Nsp); w->dVFs = mat(Nsp, D);
@@ -443,6 +443,14 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
     const bool bf = cx.mode == TEAM_MODE_BF16;
     auto honly = [&](const Mat& m) { return bf ? Mat{nullptr, m.h, m.ld} : m; };
+    // ---- own query rows: independent of the table-query rows -> side lane, beside them (its dVF part goes to dVFo_own)
+    int ogrid = (d.B + 7) / 8;
+    if (ogrid > NUM_SMS) ogrid = NUM_SMS;
+    SideStream* own_side = nullptr;
+    {
+        const cudaStream_t ost = fork_side(cx.st, &own_side);
+        TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, ost, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo_own, (__nv_bfloat16*)nullptr, w.own_partials);
+    }
     // ---- table-query rows (prototype / state outputs)
     int tgrid;
     if (use_table2(d)) {          // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
@@ -459,16 +467,19 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
         TEAM_LAUNCH(table_rows_bwd_kernel, tgrid, TQ_WARPS * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
     }
-    // ---- own query rows
-    int ogrid = (d.B + 7) / 8;
-    if (ogrid > NUM_SMS) ogrid = NUM_SMS;
-    TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, cx.st, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo.f, w.dVFo.h, w.own_partials);
+    if ((rc = join_side(cx.st, own_side))) return rc;
+    // the fixed-order fold of the per-CTA partials and dVFo += dVFo_own are not needed before expand_table / wave 7:
+    // side lane, beside GEMM wave 5
+    SideStream* red_side = nullptr;
     {
+        const cudaStream_t rst = fork_side(cx.st, &red_side);
         ReduceJobs rj;
         rj.j[0] = ReduceJob{w.tab_partials, w.tab_reduced, to.len / 4, tgrid};
         rj.j[1] = ReduceJob{w.own_partials, w.own_reduced, OWN_PARTIAL_LEN / 4, ogrid};
         rj.blocks0 = (int)((to.len / 4 + RP_COLS - 1) / RP_COLS);
-        TEAM_LAUNCH(reduce_partials_kernel, rj.blocks0 + (OWN_PARTIAL_LEN / 4 + RP_COLS - 1) / RP_COLS, RP_COLS * RP_GROUPS, 0, cx.st, rj);
+        TEAM_LAUNCH(reduce_partials_kernel, rj.blocks0 + (OWN_PARTIAL_LEN / 4 + RP_COLS - 1) / RP_COLS, RP_COLS * RP_GROUPS, 0, rst, rj);
+        const int64_t n4 = (int64_t)d.B2 * D / 4;
+        TEAM_LAUNCH(add_rows_kernel, (unsigned)((n4 + 255) / 256), 256, 0, rst, n4, w.dVFo.f, w.dVFo_own, w.dVFo.h);
     }
     const Mat Qs = sub(w.QKVs, 0, 0), Ks = sub(w.QKVs, 0, D), Vs = sub(w.QKVs, 0, 2 * D);
     const Mat Qo = sub(w.QKVo, 0, 0), Ko = sub(w.QKVo, 0, D), Vo = sub(w.QKVo, 0, 2 * D);
@@ -481,6 +492,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.B2, D, 0.f, fonly(dKo.f, dKo.ld)), false, w.dSK, true, Qs, d.Nsp);      // bf16 shadow: own_own_bwd_kernel
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.dVFs_a, D)), true, w.Aext, true, w.dYo, d.B2);
     RUN(wv);
+    if ((rc = join_side(cx.st, red_side))) return rc;
     TEAM_LAUNCH(expand_table_kernel, d.Nsp + EXP_SUM_BLOCKS, 128, 0, cx.st, d, w.tab_reduced, w.own_reduced, w.RG, w.ldA / 2, w.NFt, w.S.f, w.VFs.f, hw->b_fc, w.Rfull, w.Gfull.f, w.Gfull.h, w.hfull, w.dTT.f, w.dVFs.f, w.dVFs_a, gr->ln_g, gr->ln_b, w.dbfc_parts);
     // ---- wave 6: G VFs^T, dVFs += Pt^T G
     seg(wv.add(d.Nsp, d.Nsp, 0.f, fonly(w.tmpNN, d.Nsp)), false, w.Gfull, false, w.VFs, D);

@@ -72,6 +72,7 @@ struct HeadWS {
     float* dsown;                     // [B2][2]
     Mat dSK;                          // [B2][Nsp]
     Mat dVFo;                         // [B2][D]
+    float* dVFo_own;                  // [B2][D]   own-row part (ln_own_bwd), summed into dVFo by add_rows_kernel
     Mat dQKVo;                        // [B2][3D]
     Mat dXo;                          // [B2][D]   du_o, then + dQKV Wqkv, then dz in place
     float* Rfull;                     // [Nsp][D]  residual gradient of the step rows, then + dQKVs Wqkv

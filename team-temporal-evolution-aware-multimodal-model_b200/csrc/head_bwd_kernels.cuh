@@ -423,11 +423,11 @@ ln_own_bwd_kernel(HeadDims d, const float* __restrict__ Ybo, const float* __rest
             axpy_row(accI, a0, du);
             axpy_row(accT, a1, du);
         }
-        float4 t[4];
-        ld_row(dVFo + (size_t)b * D, lane, t); add_row(t, accI); st_row(dVFo + (size_t)b * D, lane, t);
-        st_row_h(dVFoh != nullptr ? dVFoh + (size_t)b * D : nullptr, lane, t);
-        ld_row(dVFo + (size_t)(d.B + b) * D, lane, t); add_row(t, accT); st_row(dVFo + (size_t)(d.B + b) * D, lane, t);
-        st_row_h(dVFoh != nullptr ? dVFoh + (size_t)(d.B + b) * D : nullptr, lane, t);
+        // own-row part of dVF (image row, text row): kept apart from the table-row part that table_rows_bwd writes
+        // concurrently into dVFo; add_rows_kernel sums the two (and writes the bf16 shadow) later
+        (void)dVFoh;
+        st_row(dVFo + (size_t)b * D, lane, accI);
+        st_row(dVFo + (size_t)(d.B + b) * D, lane, accT);
     }
     st_row(fold[0][warp], lane, dgam);
     st_row(fold[1][warp], lane, dbet);
@@ -441,6 +441,20 @@ ln_own_bwd_kernel(HeadDims d, const float* __restrict__ Ybo, const float* __rest
         for (int w = 0; w < 8; ++w) s += fold[q][w][c];
         rec[i] = s;
     }
+}
+
+// a += b (fp32, in place) with the bf16 shadow of the sum; n4 float4 elements
+__global__ void __launch_bounds__(256)
+add_rows_kernel(int64_t n4, float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ ah) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n4) return;
+    float4 x = reinterpret_cast<const float4*>(a)[i];
+    const float4 y = reinterpret_cast<const float4*>(b)[i];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    reinterpret_cast<float4*>(a)[i] = x;
+    if (ah != nullptr) reinterpret_cast<uint2*>(ah)[i] = pack_bf16x4(x);
 }
 
 // dS = A .* (dA - rowdot) / tau, in place over dA (fp32 + bf16 shadow); 4 columns per thread (Nsp % 16 == 0)
