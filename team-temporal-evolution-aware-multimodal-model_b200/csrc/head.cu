@@ -450,6 +450,8 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     {
         const cudaStream_t ost = fork_side(cx.st, &own_side);
         TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, ost, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo_own, (__nv_bfloat16*)nullptr, w.own_partials);
+        // own x own score gradients: initial values of the dQ / dK rows (the GEMMs of waves 5 and 7 accumulate on top)
+        TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, ost, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, (__nv_bfloat16*)nullptr);
     }
     // ---- table-query rows (prototype / state outputs)
     int tgrid;
@@ -489,7 +491,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     // ---- wave 5: R/G coefficient GEMM (A1^T GG + A23^T VFo), dA = dYo VFs^T (into SQ), dKo = dSK Qs
     seg(seg(wv.add(w.ldA, D, 0.f, fonly(w.RG, D)), true, w.A1, true, w.GG, d.B2), true, w.A23, true, w.VFo, d.B2);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, w.dYo, false, w.VFs, D);
-    seg(wv.add(d.B2, D, 0.f, fonly(dKo.f, dKo.ld)), false, w.dSK, true, Qs, d.Nsp);      // bf16 shadow: own_own_bwd_kernel
+    seg(wv.add(d.B2, D, 1.f, dKo), false, w.dSK, true, Qs, d.Nsp);                       // += the own x own part (own_own_bwd_kernel)
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.dVFs_a, D)), true, w.Aext, true, w.dYo, d.B2);
     RUN(wv);
     if ((rc = join_side(cx.st, red_side))) return rc;
@@ -508,7 +510,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     }
     const Mat& dS = w.SQ;
     // ---- wave 7: score gradients -> dQ/dK, fc folded into V, dWfc
-    seg(wv.add(d.B2, D, 0.f, fonly(dQo.f, dQo.ld)), false, dS, true, Ks, d.Nsp);                                                    // dQo = dS Ks
+    seg(wv.add(d.B2, D, 1.f, dQo), false, dS, true, Ks, d.Nsp);                                                                     // dQo = dS Ks + the own x own part
     seg(seg(wv.add(d.Nsp, D, 0.f, honly(dKs)), true, dS, true, Qo, d.B2), true, w.dTT, true, Qs, d.Nsp);                  // dKs = dS^T Qo + dTT^T Qs
     seg(seg(wv.add(d.Nsp, D, 0.f, honly(dQs)), true, w.dSK, true, Ko, d.B2), false, w.dTT, true, Ks, d.Nsp);              // dQs = dSK^T Ko + dTT Ks
     seg(wv.add(d.B2, D, 0.f, honly(dVo)), false, w.dVFo, true, w.Wfc, D);                                                 // dVo = dVFo Wfc
@@ -532,7 +534,6 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         const cudaStream_t cst = fork_side(cx.st, &comm_side, 1);
         if (comm_side != nullptr && (rc = peer_allreduce_range(cst, comm, 0, DD))) return rc;
     }
-    TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, cx.st, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, w.dQKVo.h);
     // ---- wave 8: through the packed q/k/v projection
     seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
     seg(wv.add(d.Nsp, D, 1.f, fonly(w.Rfull, D)), false, w.dQKVs, true, w.Wqkv, 3 * D);                            // dS_rows (in Rfull)

@@ -474,7 +474,9 @@ ds_kernel(int64_t n4, int Nsp4, const float* __restrict__ Aext, const float* __r
     if (dSh != nullptr) reinterpret_cast<uint2*>(dSh)[i] = pack_bf16x4(v);
 }
 
-// own-query x own-key score gradients (the 2x2 per-sample block)
+// own-query x own-key score gradients (the 2x2 per-sample block): INITIAL values of the dQ / dK rows of the own rows
+// (fp32); the GEMMs that produce the rest of dKo (wave 5) and dQo (wave 7) accumulate on top (beta = 1) and write
+// the bf16 shadows, so this kernel sits beside the table-query rows instead of between two GEMM waves.
 __global__ void __launch_bounds__(256)
 own_own_bwd_kernel(HeadDims d, const float* __restrict__ QKVo, const __nv_bfloat16* __restrict__ QKVoh,
                    const float* __restrict__ dsown, float* __restrict__ dQKVo, __nv_bfloat16* __restrict__ dQKVoh) {
@@ -490,15 +492,11 @@ own_own_bwd_kernel(HeadDims d, const float* __restrict__ QKVo, const __nv_bfloat
     ld_row_any(QKVo + r0 + D, hq ? QKVoh + r0 + D : nullptr, lane, k0); ld_row_any(QKVo + r1 + D, hq ? QKVoh + r1 + D : nullptr, lane, k1);
     const float s00 = dsown[2 * b], s01 = dsown[2 * b + 1];
     const float s10 = dsown[2 * (d.B + b)], s11 = dsown[2 * (d.B + b) + 1];
-    __nv_bfloat16* const hn = nullptr;
-    ld_row(dQKVo + r0, lane, t); axpy_row(t, s00, k0); axpy_row(t, s01, k1); st_row(dQKVo + r0, lane, t);
-    st_row_h(dQKVoh != nullptr ? dQKVoh + r0 : hn, lane, t);
-    ld_row(dQKVo + r1, lane, t); axpy_row(t, s10, k0); axpy_row(t, s11, k1); st_row(dQKVo + r1, lane, t);
-    st_row_h(dQKVoh != nullptr ? dQKVoh + r1 : hn, lane, t);
-    ld_row(dQKVo + r0 + D, lane, t); axpy_row(t, s00, q0); axpy_row(t, s10, q1); st_row(dQKVo + r0 + D, lane, t);
-    st_row_h(dQKVoh != nullptr ? dQKVoh + r0 + D : hn, lane, t);
-    ld_row(dQKVo + r1 + D, lane, t); axpy_row(t, s01, q0); axpy_row(t, s11, q1); st_row(dQKVo + r1 + D, lane, t);
-    st_row_h(dQKVoh != nullptr ? dQKVoh + r1 + D : hn, lane, t);
+    (void)dQKVoh;
+    zero_row(t); axpy_row(t, s00, k0); axpy_row(t, s01, k1); st_row(dQKVo + r0, lane, t);
+    zero_row(t); axpy_row(t, s10, k0); axpy_row(t, s11, k1); st_row(dQKVo + r1, lane, t);
+    zero_row(t); axpy_row(t, s00, q0); axpy_row(t, s10, q1); st_row(dQKVo + r0 + D, lane, t);
+    zero_row(t); axpy_row(t, s01, q0); axpy_row(t, s11, q1); st_row(dQKVo + r1 + D, lane, t);
 }
 
 // dTT[r][j] += P[r][j] * (GV[r][j] - h[r]) / tau   for j < M; the bf16 shadow is written for every element
