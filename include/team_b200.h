@@ -255,7 +255,7 @@ int team_adamw_step(int32_t n_tensors, float* const* params, const float* const*
  * this is the exchange step of the data-parallel training step (the sum autograd would produce on one big batch,
  * models/proof.py:444).  In-place sum of n fp32 values: bufs[r] / flags[r] (r < world, HOST arrays of device
  * pointers) are every rank's buffer and flag array as mapped on THIS device (symmetric memory); flags are
- * team_peer_allreduce_flag_bytes() bytes each, zeroed once before the first call.  One kernel, two-shot, summed in
+ * team_peer_allreduce_flag_bytes() bytes each (two channels), zeroed once before the first call.  One kernel, two-shot, summed in
  * rank order (bit-identical on all ranks); every rank must make the matching call.  n % 4 == 0.
  * multicast: NVLS multicast mapping of the same buffers (NULL = none): the switch then adds (multimem.ld_reduce)
  * and replicates (multimem.st); the sum order is the switch's, still identical on all ranks. */

@@ -532,7 +532,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
                      inside(gr->state_emb, comm->split_at, comm->n_total) && inside(gr->b_fc, comm->split_at, comm->n_total),
                      "head bwd: gradient pointers do not match the peer-comm buckets");
         const cudaStream_t cst = fork_side(cx.st, &comm_side, 1);
-        if (comm_side != nullptr && (rc = peer_allreduce_range(cst, comm, 0, DD))) return rc;
+        if (comm_side != nullptr && (rc = peer_allreduce_range(cst, comm, 0, DD, 0))) return rc;
     }
     // ---- wave 8: through the packed q/k/v projection
     seg(wv.add(d.B2, D, 1.f, fonly(w.dXo.f, D)), false, w.dQKVo, true, w.Wqkv, 3 * D);                             // dXo += dQKVo Wqkv
@@ -548,7 +548,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         SideStream* again = nullptr;
         const cudaStream_t cst = fork_side(cx.st, &again, 1);            // second dependency of the same lane
         if (again != nullptr) {
-            if ((rc = peer_allreduce_range(cst, comm, DD, comm->split_at - DD))) return rc;
+            if ((rc = peer_allreduce_range(cst, comm, DD, comm->split_at - DD, 0))) return rc;
         } else {
             comm_side = nullptr;      // cannot happen once the lane exists; keep the end-of-call fallback consistent
         }
@@ -598,12 +598,18 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     RUN(wv);
     if ((rc = join_side(cx.st, fin_side))) return rc;
     if (comm != nullptr) {
-        if (comm_side != nullptr) {
+        // Late bucket.  Plain peer loads (no multicast mapping, i.e. 2 ranks): it starts on the second flag channel as
+        // soon as the last kernel is done, even if the q/k/v bucket on the comm lane is still finishing (N = 2:
+        // 0.229 vs 0.236 ms per step).  NVLS path (>= 4 ranks): join first - two multimem exchanges in flight slowed
+        // each other down more than the overlap saved (N = 8: 0.233 ms against 0.231 ms with kernels 10 us slower).
+        const bool overlap_late = comm_side != nullptr && comm->multicast == nullptr;
+        if (comm_side == nullptr) {
+            if ((rc = peer_allreduce_range(cx.st, comm, 0, comm->split_at, 0))) return rc;       // no side lanes: everything at the end
+        } else if (!overlap_late) {
             if ((rc = join_side(cx.st, comm_side))) return rc;
-        } else if ((rc = peer_allreduce_range(cx.st, comm, 0, comm->split_at))) {      // no side lanes: everything at the end
-            return rc;
         }
-        if ((rc = peer_allreduce_range(cx.st, comm, comm->split_at, comm->n_total - comm->split_at))) return rc;
+        if ((rc = peer_allreduce_range(cx.st, comm, comm->split_at, comm->n_total - comm->split_at, overlap_late ? 1 : 0))) return rc;
+        if (overlap_late && (rc = join_side(cx.st, comm_side))) return rc;
     }
     return TEAM_OK;
 }

@@ -103,7 +103,7 @@ HeadDims head_dims(int64_t B, int C, int P, int Tc);
 // carve `base` (may be null: sizing only) into the HeadWS pointers
 void head_plan(const HeadDims& d, int mode, void* base, HeadWS* ws);
 
-int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offset, int64_t n);
+int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offset, int64_t n, int channel);
 int cosine_logits_launch(cudaStream_t st, const float* x, int64_t n_rows, const float* w, int64_t num_classes,
                          const float* sigma_dev, float* logits, int64_t* argmax);
 

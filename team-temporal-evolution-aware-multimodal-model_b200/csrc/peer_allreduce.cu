@@ -139,7 +139,8 @@ static int ar_grid(int64_t n4, int world) {
 }
 
 // all-reduce of floats [offset, offset + n) of the buffers described by `c` (both multiples of 4)
-int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offset, int64_t n) {
+int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offset, int64_t n, int channel) {
+    TEAM_REQUIRE(channel == 0 || channel == 1, "peer_allreduce: channel %d", channel);
     TEAM_REQUIRE(c != nullptr && c->world >= 1 && c->world <= AR_MAX_RANKS && c->rank >= 0 && c->rank < c->world, "peer_allreduce: bad comm");
     TEAM_REQUIRE(offset >= 0 && n >= 0 && offset % 4 == 0 && n % 4 == 0 && offset + n <= c->n_total, "peer_allreduce: range [%lld, +%lld) of %lld", (long long)offset, (long long)n, (long long)c->n_total);
     if (n == 0 || c->world == 1) return TEAM_OK;
@@ -148,7 +149,7 @@ int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offse
     for (int r = 0; r < c->world; ++r) {
         TEAM_REQUIRE(c->bufs[r] != nullptr && c->flags[r] != nullptr && (reinterpret_cast<uintptr_t>(c->bufs[r]) & 15) == 0, "peer_allreduce: bad pointer of rank %d", r);
         a.buf[r] = reinterpret_cast<float*>(c->bufs[r]) + offset;
-        a.flag[r] = reinterpret_cast<uint32_t*>(c->flags[r]);
+        a.flag[r] = reinterpret_cast<uint32_t*>(c->flags[r]) + (size_t)channel * AR_FLAG_WORDS;
     }
     a.mc = c->multicast != nullptr ? reinterpret_cast<float*>(c->multicast) + offset : nullptr;
     a.rank = c->rank; a.world = c->world; a.n4 = n / 4;
@@ -160,7 +161,9 @@ int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offse
 
 using namespace team;
 
-extern "C" size_t team_peer_allreduce_flag_bytes(void) { return (size_t)AR_FLAG_WORDS * sizeof(uint32_t); }
+// two independent flag channels: two exchanges may be in flight at once (team_head_grads.comm: the late bucket starts
+// while the q/k/v bucket is still finishing)
+extern "C" size_t team_peer_allreduce_flag_bytes(void) { return (size_t)2 * AR_FLAG_WORDS * sizeof(uint32_t); }
 
 extern "C" int team_peer_allreduce_f32(void* const* bufs, void* const* flags, void* multicast, int32_t rank,
                                        int32_t world, int64_t n, void* stream) {
