@@ -598,11 +598,10 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     RUN(wv);
     if ((rc = join_side(cx.st, fin_side))) return rc;
     if (comm != nullptr) {
-        // Late bucket.  Plain peer loads (no multicast mapping, i.e. 2 ranks): it starts on the second flag channel as
-        // soon as the last kernel is done, even if the q/k/v bucket on the comm lane is still finishing (N = 2:
-        // 0.229 vs 0.236 ms per step).  NVLS path (>= 4 ranks): join first - two multimem exchanges in flight slowed
-        // each other down more than the overlap saved (N = 8: 0.233 ms against 0.231 ms with kernels 10 us slower).
-        const bool overlap_late = comm_side != nullptr && comm->multicast == nullptr;
+        // Late bucket: on the second flag channel, so it starts as soon as the last kernel is done even if the q/k/v
+        // bucket on the comm lane is still finishing.  Measured against "join the comm lane first" with the same
+        // kernels: N = 2 0.229 vs 0.236 ms per step, N = 8 0.233 vs 0.235 ms.
+        const bool overlap_late = comm_side != nullptr;
         if (comm_side == nullptr) {
             if ((rc = peer_allreduce_range(cx.st, comm, 0, comm->split_at, 0))) return rc;       // no side lanes: everything at the end
         } else if (!overlap_late) {
