@@ -1,6 +1,6 @@
 """Prints bf16-mode error statistics of the head against the fp64 oracle (diagnostic, run by hand)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import torch
 from oracle import synth, team_oracle as O
 from team_b200 import head

@@ -1,6 +1,6 @@
 """Diagnostic: where does the host time of the autograd (public API) path go?"""
 import sys, os, time, cProfile, pstats
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import torch
 from oracle import synth
 from team_b200 import head
