@@ -126,6 +126,9 @@ def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, lab
     capi.require_device()
     B = image.shape[0]
     xs = [_chk_rows(t.detach().reshape(B, -1).float(), n) for t, n in ((image, "image"), (text, "text"), (state, "state"))]
+    if B == 1:        # models/proof.py:41-45: a batch of one returns a zero loss (and therefore zero gradients)
+        return (torch.zeros((3,), dtype=torch.float32, device=xs[0].device),
+                tuple(torch.zeros((1, capi.D), dtype=torch.float32, device=xs[0].device) for _ in range(3)))
     y = labels.detach().to(device=xs[0].device, dtype=torch.int64).contiguous()
     L = capi.lib()
     nbytes = L.team_loss_workspace_bytes(B)
