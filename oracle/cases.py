@@ -37,6 +37,8 @@ CASES: Dict[str, dict] = {
     "unicl_B24": {"kind": "unicl", "B": 24, "C": 6, "seed": 6000, "epoch": 3, "max_epoch": 10},
     "unicl_B9_static_tau": {"kind": "unicl", "B": 9, "C": 20, "seed": 6001, "epoch": None, "max_epoch": None},
     "clip_B16": {"kind": "clip", "B": 16, "seed": 6002, "logit_scale": 14.285714},
+    # unicl_loss WITH evolution features (models/proof.py:51-106): 5 classes, class 3 has no feature, class ids >= 4 out of range
+    "unicl_B20_evolution": {"kind": "unicl", "B": 20, "C": 6, "seed": 6003, "epoch": 5, "max_epoch": 20, "evolution": True},
 }
 
 
@@ -90,7 +92,12 @@ def case_inputs(case: dict) -> dict:
             return {"image": F.normalize(feats[0], dim=1), "text": F.normalize(feats[1], dim=1)}
         labels = torch.randint(0, case["C"], (B,), generator=g, dtype=torch.int64)
         states = torch.tensor([1, 3, 4], dtype=torch.int64)[torch.randint(0, 3, (B,), generator=g)]
-        return {"image": feats[0], "text": feats[1].reshape(B, 1, 512), "state": feats[2], "labels": labels, "states": states}
+        out = {"image": feats[0], "text": feats[1].reshape(B, 1, 512), "state": feats[2], "labels": labels, "states": states}
+        if case.get("evolution"):
+            evo = [torch.randn((512,), generator=g) for _ in range(4)]
+            evo[3] = None
+            out["evolution"] = evo
+        return out
     if kind == "dynamic_gcn":
         g = torch.Generator(device="cpu").manual_seed(case["seed"])
         N, E = case["N"], case["E"]

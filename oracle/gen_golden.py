@@ -225,7 +225,7 @@ def gen_unicl(case):
     ci = case_inputs(case)
     x = [ci[k].clone().requires_grad_(True) for k in ("image", "text", "state")]
     total, info = unicl_loss(x[0], x[1], x[2], ci["labels"], ci["states"], state_distance=None,
-                             epoch=case["epoch"], max_epoch=case["max_epoch"], evolution_features=None)
+                             epoch=case["epoch"], max_epoch=case["max_epoch"], evolution_features=ci.get("evolution"))
     total.backward()
     return {"total": _np(total.detach()), "instance": np.float64(info["instance_loss"]), "category": np.float64(info["category_loss"]),
             "temperature": np.float64(info["temperature"]), "g_image": _np(x[0].grad), "g_text": _np(x[1].grad.reshape(-1, 512)),

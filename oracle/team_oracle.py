@@ -161,14 +161,17 @@ def forward_proof(p: Params, image, text, img_prototypes):
 
 
 # --------------------------------------------------------------------------- 8f: losses of the training step
-def unicl_loss(image_features, text_features, state_features, labels, temperature=0.07, epoch=None, max_epoch=None):
-    """unicl_loss with evolution_features=None: models/proof.py:21-191 (normalise :44-46, dynamic temperature
+def unicl_loss(image_features, text_features, state_features, labels, temperature=0.07, epoch=None, max_epoch=None,
+               state_ids=None, evolution_features=None):
+    """unicl_loss: models/proof.py:21-191 (evolution_features branch: enhance_state_features) (normalise :44-46, dynamic temperature
     :111-116, instance term :126-149 incl. the exp(row_sim * mask) quirk (the masked self entry counts as
     exp(0) = 1), category term :151-174, weights :177-179).  Returns (total, instance, category) as tensors."""
     B = image_features.shape[0]
     im = F.normalize(image_features.reshape(B, -1), dim=1)
     tx = F.normalize(text_features.reshape(B, -1), dim=1)
     st = F.normalize(state_features.reshape(B, -1), dim=1)
+    if evolution_features is not None and len(evolution_features) > 0:
+        st = enhance_state_features(st, labels, state_ids, evolution_features)
     if epoch is not None and max_epoch is not None:
         progress = float(epoch) / float(max_epoch)
         tau = temperature * (0.5 + 0.5 * 0.5 * (1.0 + math.cos(math.pi * progress)))
@@ -193,6 +196,44 @@ def unicl_loss(image_features, text_features, state_features, labels, temperatur
     else:
         category = torch.zeros((), dtype=sim.dtype)
     return instance + 0.5 * category, instance, category
+
+
+def enhance_state_features(state_features, labels, state_ids, evolution_features):
+    """The `evolution_features` branch of unicl_loss: models/proof.py:51-106.  `state_features` are the NORMALISED state
+    rows; returns the enhanced rows (differentiable).  Per class present in the batch with an evolution feature:
+      one sample  -> normalize(0.8 s + 0.2 normalize(evo))                                               (:100-103)
+      >= 2 samples with >= 2 distinct states -> time position of a state = its rank / (n_states - 1);
+          mixture_i = evo + sum_{j != i, w_ij > 0.3} 0.2 w_ij s_j,  w_ij = 1 - |t_i - t_j|;
+          row_i = normalize(0.7 s_i + 0.3 normalize(mixture_i))                                           (:79-98)
+      >= 2 samples, one distinct state -> unchanged                                                        (:76 guard)
+    Mixtures read the ORIGINAL rows (state_features), never rows already enhanced in this call (:92)."""
+    out = state_features.clone()
+    by_class = {}
+    for i, c in enumerate(labels.tolist()):
+        by_class.setdefault(c, []).append(i)
+    for c, idx in by_class.items():
+        if c >= len(evolution_features) or evolution_features[c] is None:
+            continue
+        evo = evolution_features[c].to(state_features.dtype)
+        if len(idx) >= 2:
+            states = [int(state_ids[i]) for i in idx]
+            uniq = sorted(set(states))
+            if len(uniq) < 2:
+                continue
+            tpos = {s: k / (len(uniq) - 1) for k, s in enumerate(uniq)}
+            for a, i in enumerate(idx):
+                mix = evo.clone()
+                for b2, j in enumerate(idx):
+                    if a == b2:
+                        continue
+                    w = 1.0 - abs(tpos[states[a]] - tpos[states[b2]])
+                    if w > 0.3:
+                        mix = mix + w * 0.2 * state_features[j]
+                out[i] = F.normalize(0.7 * state_features[i] + 0.3 * F.normalize(mix, dim=0), dim=0)
+        else:
+            i = idx[0]
+            out[i] = F.normalize(0.8 * state_features[i] + 0.2 * F.normalize(evo, dim=0), dim=0)
+    return out
 
 
 def clip_loss(image_features, text_features, logit_scale):

@@ -203,3 +203,18 @@ def test_clip_loss(golden):
     loss.backward()
     assert rel_err(loss.detach(), g["loss"]) < 1e-6
     assert rel_err(x[0].grad, g["g_image"]) < 2e-6 and rel_err(x[1].grad, g["g_text"]) < 2e-6
+
+
+def test_unicl_loss_with_evolution_features(golden):
+    """The evolution_features branch (models/proof.py:51-106; still CPU-only): oracle vs the real reference,
+    value and input gradients (the enhancement is differentiable w.r.t. the state rows)."""
+    case, g = CASES["unicl_B20_evolution"], golden("unicl_B20_evolution")
+    ci = case_inputs(case)
+    x = [ci[k].clone().double().requires_grad_(True) for k in ("image", "text", "state")]
+    evo = [None if e is None else e.double() for e in ci["evolution"]]
+    total, inst, cat = O.unicl_loss(x[0], x[1], x[2], ci["labels"], epoch=case["epoch"], max_epoch=case["max_epoch"],
+                                    state_ids=ci["states"], evolution_features=evo)
+    total.backward()
+    assert rel_err(total.detach(), g["total"]) < 1e-6
+    for k, t in zip(("g_image", "g_text", "g_state"), x):
+        assert rel_err(t.grad.reshape(-1, 512), g[k]) < 2e-6, k
