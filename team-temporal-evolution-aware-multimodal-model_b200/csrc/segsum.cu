@@ -25,6 +25,7 @@ constexpr int SEG_THREADS = 128;
 constexpr int SEG_UNROLL = 8;
 constexpr int SEG_CLUSTER = 8;
 constexpr int SEG_SLAB_KEYS = 24;      // 24 keys * 2 KB = 48 KB smem -> 4 CTAs / SM
+constexpr int SEG_MAX_SLAB_KEYS = 104; // 208 KB of accumulators: the most one CTA can hold
 
 template <typename T> struct RowLoad;
 template <> struct RowLoad<float> {
@@ -37,7 +38,7 @@ template <> struct RowLoad<__nv_bfloat16> {
     }
 };
 
-template <typename T, bool NORM>
+template <typename T, bool NORM, bool DEEP>
 __global__ void __launch_bounds__(SEG_THREADS)
 segsum_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels,
                       const int64_t* __restrict__ states, int64_t n_rows, int64_t rows_per_cta,
@@ -56,22 +57,33 @@ segsum_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ label
 
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t r1 = min(n_rows, r0 + rows_per_cta);
-    int buf = 0;
-    for (int64_t r = r0; r < r1; r += SEG_UNROLL) {
-        int key[SEG_UNROLL];
-        float4 v[SEG_UNROLL];
+    // Three-deep software pipeline over groups of SEG_UNROLL rows.  A group needs three dependent memory round
+    // trips (label, then state, then the feature row of a row whose key falls into this slab) before its serial
+    // shared-memory read-modify-write chain; issued back to back they cost ~3 us per group and the memory system idles
+    // (measured: 52 % of the HBM peak for class keys, 4 % for class x state keys).  Here the labels AND states of
+    // group g+2 are requested unconditionally while the feature rows of group g+1 are in flight and group g is
+    // accumulated, so every wait is one round trip old when it is consumed.
+    auto load_raw = [&](int64_t r, int64_t (&lab)[SEG_UNROLL], int64_t (&stt)[SEG_UNROLL]) {
+#pragma unroll
+        for (int u = 0; u < SEG_UNROLL; ++u) {
+            const int64_t row = r + u;
+            lab[u] = -1; stt[u] = 0;
+            if (row < r1) {
+                lab[u] = __ldg(labels + row);
+                if (states != nullptr) stt[u] = __ldg(states + row);
+            }
+        }
+    };
+    auto make_keys = [&](int64_t r, const int64_t (&lab)[SEG_UNROLL], const int64_t (&stt)[SEG_UNROLL], int (&key)[SEG_UNROLL]) {
 #pragma unroll
         for (int u = 0; u < SEG_UNROLL; ++u) {
             key[u] = -1;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int64_t row = r + u;
-            if (row < r1) {
-                const int64_t c = __ldg(labels + row) - class_base;
+            if (r + u < r1) {
+                const int64_t c = lab[u] - class_base;
                 int64_t k = -1;
                 if (c >= 0 && c < num_classes) {
                     if (states != nullptr) {
-                        const int64_t s = __ldg(states + row);
-                        if (s >= 0 && s < num_states) k = c * num_states + s;
+                        if (stt[u] >= 0 && stt[u] < num_states) k = c * num_states + stt[u];
                     } else {
                         k = c;
                     }
@@ -80,9 +92,37 @@ segsum_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ label
                 if (k >= 0 && k < nk) key[u] = (int)k;
             }
         }
+    };
+    auto load_feats = [&](int64_t r, const int (&key)[SEG_UNROLL], float4 (&v)[SEG_UNROLL]) {
 #pragma unroll
-        for (int u = 0; u < SEG_UNROLL; ++u)
+        for (int u = 0; u < SEG_UNROLL; ++u) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (key[u] >= 0) v[u] = RowLoad<T>::load(x + (r + u) * D, t);
+        }
+    };
+    int buf = 0;
+    int key[SEG_UNROLL], keyn[SEG_UNROLL];
+    float4 v[SEG_UNROLL], vn[SEG_UNROLL];
+    int64_t lab[SEG_UNROLL], stt[SEG_UNROLL];
+    // DEEP (class x state keys): the three-deep pipeline above.  Otherwise (class keys only: one round trip less per
+    // group, and measured no faster - for bf16 rows slower - with the deeper pipeline) a two-deep one: the next
+    // group's labels and features are requested before this group is accumulated.
+    load_raw(r0, lab, stt);
+    make_keys(r0, lab, stt, key);
+    load_feats(r0, key, v);
+    if (DEEP) load_raw(r0 + SEG_UNROLL, lab, stt);
+    for (int64_t r = r0; r < r1; r += SEG_UNROLL) {
+        if (DEEP) {
+            // group g+1: keys from the raw values requested one iteration ago, feature loads now in flight
+            make_keys(r + SEG_UNROLL, lab, stt, keyn);
+            load_feats(r + SEG_UNROLL, keyn, vn);
+            // group g+2: labels / states
+            load_raw(r + 2 * SEG_UNROLL, lab, stt);
+        } else {
+            load_raw(r + SEG_UNROLL, lab, stt);
+            make_keys(r + SEG_UNROLL, lab, stt, keyn);
+            load_feats(r + SEG_UNROLL, keyn, vn);
+        }
         if (NORM) {
             float ss[SEG_UNROLL];
 #pragma unroll
@@ -113,6 +153,8 @@ segsum_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ label
                 if (t == 0) cnt[key[u]] += 1;
             }
         }
+#pragma unroll
+        for (int u = 0; u < SEG_UNROLL; ++u) { key[u] = keyn[u]; v[u] = vn[u]; }
     }
     // fold the 8 CTAs of the cluster in rank order through distributed shared memory
     cg::cluster_group cluster = cg::this_cluster();
@@ -206,10 +248,20 @@ segmean_kernel(const float* __restrict__ sums, const int64_t* __restrict__ count
 }
 
 static void seg_plan(int64_t n_rows, int64_t K, int* n_clusters, int* n_slabs, int* slab_keys, int64_t* rows_per_cta) {
-    *slab_keys = (int)(K < SEG_SLAB_KEYS ? K : SEG_SLAB_KEYS);
-    *n_slabs = (int)((K + *slab_keys - 1) / *slab_keys);
-    // aim for >= 256 rows per CTA, at most ~4 CTAs per SM across all slabs
-    int64_t max_ctas = (int64_t)NUM_SMS * 4 / *n_slabs;
+    // Few keys (class-only, K <= 24): 48 KB of accumulators, 4 CTAs per SM.  Many keys (class x state): a CTA only
+    // loads the rows whose key falls into its slab, so small slabs mean sparse loads and an idle memory system
+    // (measured: 24-key slabs at K = 200 ran at 4 % of the HBM peak) - use the largest slabs shared memory allows
+    // (<= 104 keys = 208 KB, one CTA per SM), i.e. the fewest passes over the label stream.
+    if (K <= SEG_SLAB_KEYS) {
+        *slab_keys = (int)K;
+        *n_slabs = 1;
+    } else {
+        *n_slabs = (int)((K + SEG_MAX_SLAB_KEYS - 1) / SEG_MAX_SLAB_KEYS);
+        *slab_keys = (int)((K + *n_slabs - 1) / *n_slabs);
+    }
+    const int occ = *slab_keys <= SEG_SLAB_KEYS ? 4 : (*slab_keys <= 52 ? 2 : 1);       // CTAs per SM by shared memory
+    // aim for >= 256 rows per CTA, at most one resident wave across all slabs
+    int64_t max_ctas = (int64_t)NUM_SMS * occ / *n_slabs;
     if (max_ctas < SEG_CLUSTER) max_ctas = SEG_CLUSTER;
     int64_t ctas = (n_rows + 255) / 256;
     if (ctas > max_ctas) ctas = max_ctas;
@@ -223,14 +275,14 @@ static void seg_plan(int64_t n_rows, int64_t K, int* n_clusters, int* n_slabs, i
     *rows_per_cta = rpc;
 }
 
-template <typename T, bool NORM>
+template <typename T, bool NORM, bool DEEP>
 static int seg_launch(const void* x, const int64_t* labels, const int64_t* states, int64_t n_rows,
                       int64_t class_base, int num_classes, int num_states, int K, int n_clusters,
                       int n_slabs, int slab_keys, int64_t rows_per_cta, float* part_sums,
                       long long* part_counts, cudaStream_t st) {
     const size_t smem = (size_t)slab_keys * D * sizeof(float) + (size_t)slab_keys * sizeof(int) +
                         2 * 4 * SEG_UNROLL * sizeof(float);
-    auto kern = segsum_partial_kernel<T, NORM>;
+    auto kern = segsum_partial_kernel<T, NORM, DEEP>;
     TEAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_clusters * SEG_CLUSTER, n_slabs, 1);
@@ -285,13 +337,16 @@ extern "C" int team_segsum(const void* x, int x_dtype, const int64_t* labels, co
     long long* part_counts = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) +
                                                           align_up((size_t)ncl * K * D * sizeof(float), 256));
     int rc;
+#define SEG_GO(T, NORM, DEEP) seg_launch<T, NORM, DEEP>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st)
+    const bool deep = states != nullptr;
     if (x_dtype == TEAM_DTYPE_F32) {
-        rc = normalize_rows ? seg_launch<float, true>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st)
-                            : seg_launch<float, false>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st);
+        rc = normalize_rows ? (deep ? SEG_GO(float, true, true) : SEG_GO(float, true, false))
+                            : (deep ? SEG_GO(float, false, true) : SEG_GO(float, false, false));
     } else {
-        rc = normalize_rows ? seg_launch<__nv_bfloat16, true>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st)
-                            : seg_launch<__nv_bfloat16, false>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, ncl, nsl, sk, rpc, part_sums, part_counts, st);
+        rc = normalize_rows ? (deep ? SEG_GO(__nv_bfloat16, true, true) : SEG_GO(__nv_bfloat16, true, false))
+                            : (deep ? SEG_GO(__nv_bfloat16, false, true) : SEG_GO(__nv_bfloat16, false, false));
     }
+#undef SEG_GO
     if (rc != TEAM_OK) return rc;
     segsum_final_kernel<<<K, 512, 0, st>>>(part_sums, part_counts, ncl, K, sums, counts);
     TEAM_LAUNCH_CHECK("segsum_final_kernel");
