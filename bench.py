@@ -401,43 +401,47 @@ def run_team(a):
     if world == 1 and not a.no_scale:
         at_scale = []
         for Bs in (4096, 16384, 65536):
-            gen = torch.Generator(device="cpu").manual_seed(Bs)
-            sets = []
-            for i in range(2 if Bs > 4096 else 8):
-                si = torch.nn.functional.normalize(torch.randn(Bs, 512, generator=gen), dim=-1).to(dev)
-                stx = torch.nn.functional.normalize(torch.randn(Bs, 512, generator=gen), dim=-1).to(dev)
-                ss = torch.tensor([1, 3, 4])[torch.randint(0, 3, (Bs,), generator=gen)].to(dev)
-                sets.append((si, stx, ss, [torch.randn(Bs, 512, generator=gen).to(dev) for _ in range(4)]))
-            rs = head.HeadStepRunner(pack, protos, Bs, C, mode)
-            with torch.cuda.stream(stream):
-                for i in range(3):
-                    q = sets[i % len(sets)]
-                    rs.step(q[0], q[1], q[2], text_cls, q[3])
-                torch.cuda.synchronize()
-                k = 10
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record(stream)
-                for i in range(k):
-                    q = sets[i % len(sets)]
-                    rs.step(q[0], q[1], q[2], text_cls, q[3])
-                ev1.record(stream)
-                torch.cuda.synchronize()
-                msb = ev0.elapsed_time(ev1) / k
-                L.team_prof_enable(1)
-                for i in range(2):
-                    q = sets[i % len(sets)]
-                    rs.step(q[0], q[1], q[2], text_cls, q[3])
-                L.team_prof_enable(0)
-                capi.check(L.team_prof_collect(kind, ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(tby), ctypes.byref(nl)), "team_prof_collect")
-            falg = 55.07e6 * Bs + 0.47e9
-            at_scale.append({"batch_per_gpu": Bs, "ms_per_step": msb, "samples_per_s": Bs / msb * 1e3,
-                             "alg_tflops": falg / msb / 1e9, "frac_of_tensor_peak": falg / msb / 1e9 / pk["tensor_sustained"],
-                             "gemm_tflops": tfl.value / max(tms.value, 1e-9) / 1e9,
-                             "gemm_frac_of_tensor_peak": tfl.value / max(tms.value, 1e-9) / 1e9 / pk["tensor_sustained"],
-                             "gemm_share_of_step": tms.value / 2 / msb, "timing": f"CUDA events, {k} eager steps, "
-                             f"{len(sets)} rotating input sets ({len(sets) * Bs * 512 * 4 * 6 / 2**20:.0f} MiB)"})
-            del rs, sets
-            torch.cuda.empty_cache()
+            try:
+                gen = torch.Generator(device="cpu").manual_seed(Bs)
+                sets = []
+                for i in range(2 if Bs > 4096 else 8):
+                    si = torch.nn.functional.normalize(torch.randn(Bs, 512, generator=gen), dim=-1).to(dev)
+                    stx = torch.nn.functional.normalize(torch.randn(Bs, 512, generator=gen), dim=-1).to(dev)
+                    ss = torch.tensor([1, 3, 4])[torch.randint(0, 3, (Bs,), generator=gen)].to(dev)
+                    sets.append((si, stx, ss, [torch.randn(Bs, 512, generator=gen).to(dev) for _ in range(4)]))
+                rs = head.HeadStepRunner(pack, protos, Bs, C, mode)
+                with torch.cuda.stream(stream):
+                    for i in range(3):
+                        q = sets[i % len(sets)]
+                        rs.step(q[0], q[1], q[2], text_cls, q[3])
+                    torch.cuda.synchronize()
+                    k = 10
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record(stream)
+                    for i in range(k):
+                        q = sets[i % len(sets)]
+                        rs.step(q[0], q[1], q[2], text_cls, q[3])
+                    ev1.record(stream)
+                    torch.cuda.synchronize()
+                    msb = ev0.elapsed_time(ev1) / k
+                    L.team_prof_enable(1)
+                    for i in range(2):
+                        q = sets[i % len(sets)]
+                        rs.step(q[0], q[1], q[2], text_cls, q[3])
+                    L.team_prof_enable(0)
+                    capi.check(L.team_prof_collect(kind, ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(tby), ctypes.byref(nl)), "team_prof_collect")
+                falg = 55.07e6 * Bs + 0.47e9
+                at_scale.append({"batch_per_gpu": Bs, "ms_per_step": msb, "samples_per_s": Bs / msb * 1e3,
+                                 "alg_tflops": falg / msb / 1e9, "frac_of_tensor_peak": falg / msb / 1e9 / pk["tensor_sustained"],
+                                 "gemm_tflops": tfl.value / max(tms.value, 1e-9) / 1e9,
+                                 "gemm_frac_of_tensor_peak": tfl.value / max(tms.value, 1e-9) / 1e9 / pk["tensor_sustained"],
+                                 "gemm_share_of_step": tms.value / 2 / msb, "timing": f"CUDA events, {k} eager steps, "
+                                 f"{len(sets)} rotating input sets ({len(sets) * Bs * 512 * 4 * 6 / 2**20:.0f} MiB)"})
+                del rs, sets
+                torch.cuda.empty_cache()
+            except Exception as exc:      # an extra point must never cost the headline line
+                at_scale.append({"batch_per_gpu": Bs, "error": str(exc)[:200]})
+                torch.cuda.empty_cache()
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
