@@ -136,53 +136,102 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_step_fn(tasks: int, batch: int):
-    """The reference algorithm on the host CPU: oracle port (torch CPU fp32, as-written math:
-    replicated shared rows, full LxL attention) - the same step definition as the GPU arm."""
+def workload_config(tasks: int, batch: int, world: int) -> dict:
+    """The `config` object of BOTH arms (the driver compares them): only what names the workload."""
+    C = 2 * tasks
+    return {"workload": f"TEAM/PROOF head fwd+bwd (BASELINE configs[2]): T={tasks} tasks, C={C} classes, "
+                        f"P={10 * tasks} prompts, L={3 + 12 * tasks} tokens, batch {batch} per GPU",
+            "tasks": tasks, "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+            "l2": "rotating input + cotangent sets, together larger than L2 (count and MiB under `run`)",
+            "alg_flops_per_sample_survey": 55.07e6 if tasks == 10 else None}
+
+
+def cpu_reference_step_fn(tasks: int, batch: int, nsets: int = 4):
+    """One head step on the host CPU, same step definition as the GPU arm (no-grad classification logits +
+    forward_tri_modal + VJP with fixed cotangents).  kind "reference": the UNMODIFIED reference modules
+    (utils/inc_net.py Proof_Net, models/proof.py Learner.forward_for_classification) loaded from baseline/_ref
+    (or /root/reference) through oracle/ref_loader.py, fake CLIP = identity on the 512-d features, eval mode.
+    kind "port": the oracle restatement (only when the reference tree is not there)."""
+    import types
     import torch
-    from oracle import synth
+    from oracle import ref_loader, synth
     from oracle import team_oracle as O
     C = synth.CLASSES_PER_TASK * tasks
     params = synth.make_params(tasks, seed=42, perturb_ln=False)
     names = O.trainable_names(params)
-    p = {k: (v.clone().requires_grad_(k in names)) for k, v in params.items()}
     protos = synth.make_prototypes(C)
-    b = synth.make_batch(batch, C, step=0)
-    cots = synth.make_cotangents(batch, step=0)
+    sets = [(synth.make_batch(batch, C, step=i), synth.make_cotangents(batch, step=i)) for i in range(nsets)]
+    if ref_loader.available():
+        net = ref_loader.build_reference_net(params, protos)
+        from models.proof import Learner                     # reference module (baseline/_ref)
+        fake = types.SimpleNamespace(_network=net, _device=torch.device("cpu"))
+        sd = dict(net.named_parameters())
+        train = [sd[n] for n in names]
+        it = [0]
+
+        def step():
+            b, cots = sets[it[0] % nsets]
+            it[0] += 1
+            for q in train:
+                q.grad = None
+            with torch.no_grad():
+                logits = Learner.forward_for_classification(fake, b["image"], b["text_cls"])
+            outs = net.forward_tri_modal(b["image"], b["text"], b["state"])
+            torch.autograd.backward(list(outs[:4]), [c.reshape(o.shape) for c, o in zip(cots, outs[:4])])
+            return logits
+        return step, "reference"
+    p = {k: (v.clone().requires_grad_(k in names)) for k, v in params.items()}
+    it = [0]
 
     def step():
+        b, cots = sets[it[0] % nsets]
+        it[0] += 1
         return O.head_step_fwd_bwd(p, b, protos, cots, names)
-    return step
+    return step, "port"
 
 
-def time_cpu(tasks: int, sample_batch: int, steps: int, warmup: int):
+def time_cpu(tasks: int, batch: int, steps: int, warmup: int, budget_s: float = 0.0):
+    """Times `steps` CPU steps (fewer if `budget_s` > 0 would be exceeded - the count actually timed is returned)."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    fn = cpu_reference_step_fn(tasks, sample_batch)
+    fn, kind = cpu_reference_step_fn(tasks, batch)
     for _ in range(warmup):
         fn()
+    done = 0
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return {"value": sample_batch / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps of a {sample_batch}-sample batch (T={tasks}, C={2 * tasks}, L={3 + 12 * tasks}), "
-                      f"oracle port of the reference head in torch-CPU fp32, {cores} threads, {dt * 1e3:.1f} ms/step"}, dt
+        done += 1
+        if budget_s > 0 and time.perf_counter() - t0 > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / max(done, 1)
+    what = ("the unmodified reference (baseline/_ref: utils/inc_net.py Proof_Net.forward_tri_modal + models/proof.py "
+            "forward_for_classification + autograd), fake CLIP = identity" if kind == "reference"
+            else "oracle port of the reference head")
+    return {"value": batch / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{done} steps of a {batch}-sample batch (T={tasks}, C={2 * tasks}, L={3 + 12 * tasks}), "
+                      f"{what}, torch-CPU fp32 eval mode, {cores} threads, {dt * 1e3:.1f} ms/step"}, dt, done
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(a.batch, 256)
-    cb, dt = time_cpu(a.tasks, sample, a.steps, max(1, min(a.warmup, 2)))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warm = max(1, a.warmup)
+    # the same batch as the GPU arm (B per GPU); the whole run is bounded to a few minutes
+    cb, dt, done = time_cpu(a.tasks, a.batch, a.steps, warm, budget_s=240.0)
+    # BASELINE configs[0], exactly: B=64, T=1, CPU fp32 (the reference's own CPU-runnable case)
+    c1, dt1, n1 = time_cpu(1, 64, 10, 2, budget_s=30.0)
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": max(1, min(a.warmup, 2)), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"TEAM head fwd+bwd, T={a.tasks}, batch {sample} sample of {a.batch} per step, CPU",
-                       "tasks": a.tasks, "batch_per_step": sample},
+            "config": workload_config(a.tasks, a.batch, world),
+            "run": {"steps_timed": done, "host_threads": cb["cores"], "note": "rank 0 only; one per-GPU batch per step"},
             "cpu_baseline": cb,
+            "c1": {"workload": "BASELINE configs[0]: B=64, T=1 (C=2, P=10, L=15), CPU fp32", "samples_per_s": c1["value"],
+                   "ms_per_step": dt1 * 1e3, "steps": n1, "kind": c1["kind"], "cores": c1["cores"]},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -445,18 +494,15 @@ def run_team(a):
 
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cb, _ = time_cpu(T, min(B, 256), 3, 1)
+        cb, _, _ = time_cpu(T, B, 3, 1, budget_s=25.0)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.mode, "data": "synthetic",
-                "config": {"workload": f"TEAM/PROOF head fwd+bwd (BASELINE configs[2]): T={T} tasks, C={C} classes, "
-                                       f"P={10 * T} prompts, L={3 + 12 * T} tokens, batch {B} per GPU",
-                           "tasks": T, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "grad_exchange": comm,
-                           "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2",
-                           "cuda_graphs": graphs is not None,
-                           "alg_flops_per_sample_survey": 55.07e6},
+                "config": workload_config(T, B, world),
+                "run": {"grad_exchange": comm, "cuda_graphs": graphs is not None,
+                        "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2"},
                 "roofline": roof, "at_scale": at_scale, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_per_step) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}

@@ -262,6 +262,11 @@ int team_adamw_step(int32_t n_tensors, float* const* params, const float* const*
 size_t team_peer_allreduce_flag_bytes(void);
 int team_peer_allreduce_f32(void* const* bufs, void* const* flags, void* multicast, int32_t rank, int32_t world,
                             int64_t n, void* stream);
+/* A peer that never arrives is waited for until a device-clock deadline (environment TEAM_PEER_TIMEOUT_S, default
+ * 1800 s, 0 = for ever); the kernel then gives up WITHOUT trapping (the context stays usable).  This call
+ * synchronises `stream` and returns this rank's status word: 0 = all exchanges completed, otherwise
+ * 1 + (phase << 8) + (peer << 16) of the first wait that timed out.  own_flags = flags[rank]. */
+int team_peer_allreduce_status(const void* own_flags, void* stream, uint32_t* status);
 
 /* ------------------------------------------------------------------ temporal GCN + state distances
  * Replaces: TemporalStateGCN.forward / TemporalGCNBlock.forward   models/dynamic_modal_graph.py:239-337

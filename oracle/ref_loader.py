@@ -1,8 +1,10 @@
-"""Import the *real* reference head in the build container (TEST INFRASTRUCTURE).
+"""Import the *real* reference head (TEST / BASELINE INFRASTRUCTURE, never the product).
 
-Only ``oracle/gen_golden.py`` uses this, and only where ``/root/reference`` is mounted
-(it is not on the GPU box; nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py``
-imports this file).  Three third-party modules the reference imports are absent from
+Users: ``oracle/gen_golden.py`` (build container, ``/root/reference``), the CPU reference arm of
+``bench.py`` (``--impl reference`` / ``cpu_baseline``) and the drop-in learner test, which run on the
+GPU box from ``baseline/_ref`` - an unmodified, git-ignored copy of the reference tree that
+``__graft_entry__.build()`` refreshes and ``gpurun`` ships.  Resolution order:
+``$TEAM_REFERENCE_ROOT``, ``/root/reference``, ``<repo>/baseline/_ref``.  Three third-party modules the reference imports are absent from
 the image and are stubbed: ``timm`` (imported, never used:
 utils/inc_net.py:6), ``matplotlib`` (utils/state_distance.py:5, models/proof.py:15)
 and ``open_clip`` (utils/inc_net.py:17-19) -> a fake CLIP that is the identity on
@@ -20,7 +22,18 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("TEAM_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _resolve_root() -> str:
+    cands = [os.environ.get("TEAM_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "utils")) and os.path.isdir(os.path.join(c, "models")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _resolve_root()
 
 
 class FakeCLIP(nn.Module):

@@ -857,10 +857,13 @@ size_t tc_workspace_bytes(size_t) { return 256; }
 int tc_workspace_init(cudaStream_t, void*, size_t) { return TEAM_OK; }
 
 static int tc_launch(cudaStream_t st, const TcGroup& grp, int total_ctas, double flops, double bytes) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // per device (a process may drive several GPUs) and cheap enough to skip a lock: a racing second call only repeats it
+    static bool attr_set[64] = {};
+    int dev = 0;
+    TEAM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         TEAM_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(TC_MAX_STAGES)));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const int pslot = prof_enabled() ? prof_begin(st, 1, flops, bytes) : -1;
     cudaLaunchConfig_t cfg = {};
@@ -899,10 +902,12 @@ static bool pk_eligible(const TcGemm& g) {
 }
 
 static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, void* ws, size_t ws_bytes) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    TEAM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         TEAM_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PK_SMEM_BYTES));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     PkGroup grp;
     memset(&grp, 0, sizeof(grp));

@@ -11,6 +11,7 @@
 // Flags carry a monotonically increasing epoch kept in the rank's own flag array, so nothing is ever reset and the
 // launch can sit inside a replayed CUDA graph.  Block b of every rank works on the same float4 indices, so the
 // barriers are per block (no grid-wide sync); the grid is small enough to be co-resident.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace team {
@@ -20,6 +21,9 @@ constexpr int AR_BLOCKS = 64;
 constexpr int AR_THREADS = 512;
 // flag array layout (uint32): [0, AR_BLOCKS) own epoch per block | A flags [AR_BLOCKS][8] | B flags [AR_BLOCKS][8]
 constexpr int AR_FLAG_WORDS = AR_BLOCKS + 2 * AR_BLOCKS * AR_MAX_RANKS;
+// after the two channels: AR_STATUS_WORDS status words of the rank itself.  word 0: 0 = healthy, else
+// 1 + (phase << 8) + (peer << 16) of the first wait that ran past its deadline (team_peer_allreduce_status)
+constexpr int AR_STATUS_WORDS = 16;
 
 struct ArArgs {
     float* buf[AR_MAX_RANKS];
@@ -27,7 +31,14 @@ struct ArArgs {
     float* mc;                 // multicast (NVLS) mapping of the same buffer on all ranks, or null
     int rank, world;
     long long n4;              // float4 count
+    uint32_t* status;          // this rank's status words (after both flag channels)
+    unsigned long long timeout_ns;   // 0: wait for ever
 };
+__device__ __forceinline__ unsigned long long ar_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -55,11 +66,17 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 
 // All threads of the block call it; threads [0, world) of warp 0 each handle one peer.
 //   START barrier (release_writes = false): what the peers are about to read was written by EARLIER kernels of
-//   this rank (complete and at its home L2 when this kernel runs), so plain volatile flag stores / polls suffice.
+//   this rank (complete and at its home L2 when this kernel runs), so a plain volatile flag store suffices; the
+//   poll is an ACQUIRE load (ld.acquire.sys - a strong load, not a MEMBAR.SYS), which orders the peer-data loads /
+//   multimem.ld_reduce that follow behind the flag it observed, inside the PTX memory model.
 //   END barrier (release_writes = true): this block's stores into the peers' buffers must be performed before the
 //   flag - one system-scope release per polling thread (the CTA barrier in front makes the whole block's writes
-//   part of it).  The readers of the result are LATER kernels (kernel boundary), so no acquire fence is needed.
+//   part of it).  The readers of the result are LATER kernels (kernel boundary).
 // MEMBAR.SYS, not the NVLink round trip, is the expensive part of such a barrier: 1 instead of 4 per call.
+// A peer that does not show up (rank skew: evaluation / checkpointing on one rank, a stalled loader, lazy init) is
+// waited for until a %globaltimer deadline (TEAM_PEER_TIMEOUT_S, default 1800 s, 0 = for ever); past it the wait
+// gives up, records who / where in the rank's status word and the kernel finishes WITHOUT trapping - the CUDA
+// context stays usable and the host reads the status (team_peer_allreduce_status) instead of a sticky error.
 __device__ __forceinline__ void ar_barrier(const ArArgs& a, int phase, uint32_t epoch, bool release_writes) {
     __syncthreads();
     const int t = threadIdx.x;
@@ -68,9 +85,17 @@ __device__ __forceinline__ void ar_barrier(const ArArgs& a, int phase, uint32_t 
         if (release_writes) st_release_sys(a.flag[t] + slot + a.rank, epoch);      // tell peer t
         else st_volatile_u32(a.flag[t] + slot + a.rank, epoch);
         const uint32_t* mine = a.flag[a.rank] + slot + t;                          // hear from peer t
-        long long spins = 0;
-        while ((int)(ld_volatile_u32(mine) - epoch) < 0) {
-            if (++spins > (1ll << 27)) __trap();                                   // a lost peer traps instead of hanging the GPU
+        unsigned long long deadline = 0;
+        uint32_t spins = 0;
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if ((++spins & 1023u) == 0u && a.timeout_ns != 0ull) {
+                const unsigned long long now = ar_gtime();
+                if (deadline == 0) deadline = now + a.timeout_ns;
+                else if (now > deadline) {
+                    atomicCAS(a.status, 0u, 1u + ((uint32_t)phase << 8) + ((uint32_t)t << 16));
+                    break;
+                }
+            }
         }
     }
     __syncthreads();
@@ -130,6 +155,16 @@ peer_allreduce_f32_kernel(const __grid_constant__ ArArgs a) {
 // Blocks per call: about two float4 per thread of a rank's slice, between 8 and AR_BLOCKS.  A small bucket that is
 // exchanged UNDER compute kernels should not park 64 spinning blocks on the SMs those kernels need; every rank
 // derives the same grid from the same n, and each block keeps its own epoch, so grids may differ between calls.
+static unsigned long long ar_timeout_ns() {
+    static long long v = -1;
+    if (v < 0) {
+        const char* e = getenv("TEAM_PEER_TIMEOUT_S");
+        double sec = e != nullptr ? atof(e) : 1800.0;
+        if (sec < 0) sec = 0;
+        v = (long long)(sec * 1e9);
+    }
+    return (unsigned long long)v;
+}
 static int ar_grid(int64_t n4, int world) {
     const int64_t per_rank = (n4 + world - 1) / world;
     int64_t g = (per_rank + 2 * AR_THREADS - 1) / (2 * AR_THREADS);
@@ -153,6 +188,8 @@ int peer_allreduce_range(cudaStream_t st, const team_peer_comm* c, int64_t offse
     }
     a.mc = c->multicast != nullptr ? reinterpret_cast<float*>(c->multicast) + offset : nullptr;
     a.rank = c->rank; a.world = c->world; a.n4 = n / 4;
+    a.status = reinterpret_cast<uint32_t*>(c->flags[c->rank]) + (size_t)2 * AR_FLAG_WORDS;
+    a.timeout_ns = ar_timeout_ns();
     TEAM_LAUNCH(peer_allreduce_f32_kernel, ar_grid(a.n4, a.world), AR_THREADS, 0, st, a);
     return TEAM_OK;
 }
@@ -163,7 +200,17 @@ using namespace team;
 
 // two independent flag channels: two exchanges may be in flight at once (team_head_grads.comm: the late bucket starts
 // while the q/k/v bucket is still finishing)
-extern "C" size_t team_peer_allreduce_flag_bytes(void) { return (size_t)2 * AR_FLAG_WORDS * sizeof(uint32_t); }
+extern "C" size_t team_peer_allreduce_flag_bytes(void) { return ((size_t)2 * AR_FLAG_WORDS + AR_STATUS_WORDS) * sizeof(uint32_t); }
+
+// Health of the exchanges issued so far on this rank: synchronises `stream`, then reads the rank's status word.
+// 0 = every wait completed; otherwise 1 + (phase << 8) + (peer << 16) of the first wait that ran past the deadline
+// (the data of that exchange is then NOT the sum over the ranks).  `own_flags` = flags[rank] of the calls.
+extern "C" int team_peer_allreduce_status(const void* own_flags, void* stream, uint32_t* status) {
+    TEAM_REQUIRE(own_flags != nullptr && status != nullptr, "peer_allreduce_status: null pointer");
+    TEAM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    TEAM_CUDA_CHECK(cudaMemcpy(status, reinterpret_cast<const uint32_t*>(own_flags) + (size_t)2 * AR_FLAG_WORDS, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return TEAM_OK;
+}
 
 extern "C" int team_peer_allreduce_f32(void* const* bufs, void* const* flags, void* multicast, int32_t rank,
                                        int32_t world, int64_t n, void* stream) {
@@ -180,6 +227,8 @@ extern "C" int team_peer_allreduce_f32(void* const* bufs, void* const* flags, vo
     }
     a.mc = reinterpret_cast<float*>(multicast);
     a.rank = rank; a.world = world; a.n4 = n / 4;
+    a.status = reinterpret_cast<uint32_t*>(flags[rank]) + (size_t)2 * AR_FLAG_WORDS;
+    a.timeout_ns = ar_timeout_ns();
     TEAM_LAUNCH(peer_allreduce_f32_kernel, ar_grid(a.n4, a.world), AR_THREADS, 0, (cudaStream_t)stream, a);
     return TEAM_OK;
 }

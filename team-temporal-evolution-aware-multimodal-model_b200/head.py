@@ -21,6 +21,13 @@ def _stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _check_state_ids(sid: torch.Tensor) -> torch.Tensor:
+    """nn.Embedding(10, 512) raises on an id outside [0, 10) (models/state_evolution.py:16, :45-47); the kernels
+    would clamp it silently.  Device-side assert, no host synchronisation."""
+    torch._assert_async(((sid >= 0) & (sid < capi.NUM_STATES)).all(), "state id outside [0, 10)")
+    return sid
+
+
 def _f32c(t: torch.Tensor, dev) -> torch.Tensor:
     t = t.detach()
     if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
@@ -85,7 +92,7 @@ class _TriModalFn(torch.autograd.Function):
             raise capi.TeamB200Error("forward_tri_modal needs CUDA tensors (no CPU fallback)")
         B = image.shape[0]
         image = _f32c(image, dev); text = _f32c(text, dev); protos = _f32c(protos, dev)
-        sid = state_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+        sid = _check_state_ids(state_ids.detach().to(device=dev, dtype=torch.int64).contiguous())
         if image.shape != (B, capi.D) or text.shape != (B, capi.D) or sid.shape != (B,):
             raise ValueError("image/text must be [B,512] with per-sample text, state_ids [B]")
         flat = [_f32c(p, dev) for p in params]
@@ -179,7 +186,7 @@ def encode(pack: HeadParamPack, which: str, x: Optional[torch.Tensor], img_proto
     if idx == 3:
         n, xp = protos.shape[0], None
     elif idx == 2:
-        x = x.detach().to(device=dev, dtype=torch.int64).contiguous(); n, xp = x.shape[0], x.data_ptr()
+        x = _check_state_ids(x.detach().to(device=dev, dtype=torch.int64).contiguous()); n, xp = x.shape[0], x.data_ptr()
     else:
         x = _f32c(x, dev); n, xp = x.shape[0], x.data_ptr()
     L = capi.lib()
@@ -227,7 +234,7 @@ def forward_tri_modal_class_text(pack: HeadParamPack, image: torch.Tensor, text:
         raise capi.TeamB200Error("forward_tri_modal needs CUDA tensors (no CPU fallback)")
     dev = image.device
     image, text, protos = _f32c(image, dev), _f32c(text, dev), _f32c(img_prototypes, dev)
-    sid = state_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+    sid = _check_state_ids(state_ids.detach().to(device=dev, dtype=torch.int64).contiguous())
     B, Tn = image.shape[0], text.shape[0]
     if image.shape != (B, capi.D) or text.shape != (Tn, capi.D) or sid.shape != (B,) or B < 1 or Tn < 1:
         raise ValueError("image must be [B,512], text [num_text,512], state_ids [B]")

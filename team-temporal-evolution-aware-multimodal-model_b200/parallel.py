@@ -142,6 +142,24 @@ class PeerAllReduce:
         c.rank, c.world, c.n_total, c.split_at = self.rank, self.world, self.numel, int(split_at)
         return c
 
+    def status(self, stream=None) -> int:
+        """Synchronises ``stream`` and returns this rank's exchange status: 0 = every exchange so far completed;
+        otherwise ``1 + (phase << 8) + (peer << 16)`` of the first wait that ran past the deadline
+        (``TEAM_PEER_TIMEOUT_S``, default 1800 s) - the buffer is then NOT the sum over the ranks."""
+        import ctypes as C
+        from . import capi
+        st = (stream or torch.cuda.current_stream()).cuda_stream
+        out = C.c_uint32(0)
+        capi.check(self._lib.team_peer_allreduce_status(int(self._hf.buffer_ptrs[self.rank]), st, C.byref(out)),
+                   "team_peer_allreduce_status")
+        return int(out.value)
+
+    def check(self, stream=None):
+        s = self.status(stream)
+        if s:
+            raise RuntimeError(f"peer all-reduce on rank {self.rank}: peer {(s >> 16) & 0xff} did not arrive at barrier "
+                               f"{(s >> 8) & 0xff} before the deadline (TEAM_PEER_TIMEOUT_S)")
+
     def __call__(self, stream=None):
         """Enqueue the all-reduce of ``buffer`` on ``stream`` (default: the current stream); capturable."""
         from . import capi
