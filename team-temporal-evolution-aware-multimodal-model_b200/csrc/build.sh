@@ -20,5 +20,6 @@ for f in *.cu; do
   fi
 done
 for p in $pids; do wait $p; done
-$NVCC -shared -o $OUT $objs -lcuda
+# shared cudart: only the runtime symbols actually used are imported (the static runtime carries every entry point)
+$NVCC -shared --cudart=shared -Xlinker -rpath=/usr/local/cuda/lib64 -o $OUT $objs -lcuda
 echo "built $(realpath $OUT)"

@@ -54,7 +54,7 @@ static_assert(TC_BM * (TC_MAX_BN + 4) * 4 <= TC_STAGES * TC_STAGE_BYTES, "epilog
 
 struct alignas(64) TcSegDev {
     CUtensorMap ma, mb;
-    int K, nkb, a_mn, b_mn;
+    int K, nkb, a_mn, b_mn, a_f16, b_f16;
 };
 struct alignas(64) TcProb {
     TcSegDev s[2];            // K-segments accumulated into the same TMEM tile (s[1].nkb == 0: single segment)
@@ -64,7 +64,7 @@ struct alignas(64) TcProb {
     long long ldc, ldcb;
     float alpha, beta;
     int M, N;
-    int bn, tiles_n, n_tiles, cta_begin, splits, kb_per_split;
+    int bn, tiles_n, n_tiles, cta_begin, splits, kb_per_split, cb_f16;
 };
 struct TcGroup {
     TcProb p[TC_MAXP];
@@ -161,9 +161,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor, kind::f16: D=f32, A=B=bf16, majors, N>>3 @17, M>>4 @24
-__host__ __device__ inline uint32_t umma_idesc(int M, int N, int a_mn, int b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+// instruction descriptor, kind::f16: D=f32, A / B format (0 = f16, 1 = bf16) @7 / @10, majors, N>>3 @17, M>>4 @24
+__host__ __device__ inline uint32_t umma_idesc(int M, int N, int a_mn, int b_mn, int a_f16 = 0, int b_f16 = 0) {
+    return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -251,8 +251,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
         TC_STAMP(3);
     } else if (threadIdx.x == 32) {
         // ===================== MMA issuer (one thread) =====================
-        const uint32_t idesc0 = umma_idesc(TC_BM, bn, P.s[0].a_mn, P.s[0].b_mn);
-        const uint32_t idesc1 = umma_idesc(TC_BM, bn, P.s[1].a_mn, P.s[1].b_mn);
+        const uint32_t idesc0 = umma_idesc(TC_BM, bn, P.s[0].a_mn, P.s[0].b_mn, P.s[0].a_f16, P.s[0].b_f16);
+        const uint32_t idesc1 = umma_idesc(TC_BM, bn, P.s[1].a_mn, P.s[1].b_mn, P.s[1].a_f16, P.s[1].b_f16);
         int stage = 0; uint32_t phase = 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
             const int si = kb >= nkb0 ? 1 : 0;
@@ -330,6 +330,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
                             (Cb == nullptr || ((ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 7) == 0)));
         const float alpha = P.alpha, beta = P.beta;
         const bool acc_c = beta != 0.f && C != nullptr;
+        const bool cb_f16 = P.cb_f16 != 0;
         const float* bias = P.bias;
         // thread -> (row offset r_off, float4 column c4): lanes run along the columns, rpp rows per pass
         const int lpr = bn >> 2;                                   // float4 columns per row (4..32)
@@ -395,7 +396,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
                     if (vec_ok) {
                         if (acc_c) { x.x = fmaf(beta, o[j].x, x.x); x.y = fmaf(beta, o[j].y, x.y); x.z = fmaf(beta, o[j].z, x.z); x.w = fmaf(beta, o[j].w, x.w); }
                         if (cp != nullptr) *reinterpret_cast<float4*>(cp + (q0 + j) * cstep) = x;
-                        if (bp != nullptr) *reinterpret_cast<uint2*>(bp + (q0 + j) * bstep) = pack_bf16x4(x);
+                        if (bp != nullptr) *reinterpret_cast<uint2*>(bp + (q0 + j) * bstep) = pack_h16x4(x, cb_f16);
                     } else {
                         // ragged N / unaligned outputs: element-wise with guards
                         const float xs[4] = {x.x, x.y, x.z, x.w};
@@ -408,7 +409,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
                                 if (acc_c) y = fmaf(beta, *dst, y);
                                 *dst = y;
                             }
-                            if (bp != nullptr) bp[(q0 + j) * bstep + i] = __float2bfloat16_rn(y);
+                            if (bp != nullptr) reinterpret_cast<unsigned short*>(bp)[(q0 + j) * bstep + i] = pack_h16(y, cb_f16);
                         }
                     }
                 }
@@ -461,7 +462,7 @@ struct alignas(64) PkProb {
     long long ldc, ldcb;
     float alpha, beta;
     int M, N;
-    int bn, tiles_n, n_tiles, item_begin, splits, kb_per_split;
+    int bn, tiles_n, n_tiles, item_begin, splits, kb_per_split, cb_f16;
     float* partials;              // [n_tiles][splits][128][bn] fp32 (splits > 1): summed by pk_fixup_kernel
 };
 struct PkGroup {
@@ -586,8 +587,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ PkGroup g) {
                 mbar_wait(&acc_empty[buf], accph ^ 1);              // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * PK_BN_MAX);
-                const uint32_t idesc0 = umma_idesc(TC_BM, it.bn, P.s[0].a_mn, P.s[0].b_mn);
-                const uint32_t idesc1 = umma_idesc(TC_BM, it.bn, P.s[1].a_mn, P.s[1].b_mn);
+                const uint32_t idesc0 = umma_idesc(TC_BM, it.bn, P.s[0].a_mn, P.s[0].b_mn, P.s[0].a_f16, P.s[0].b_f16);
+                const uint32_t idesc1 = umma_idesc(TC_BM, it.bn, P.s[1].a_mn, P.s[1].b_mn, P.s[1].a_f16, P.s[1].b_f16);
                 for (int kb = it.kb_begin; kb < it.kb_end; ++kb) {
                     const int si = kb >= it.nkb0 ? 1 : 0;
                     const int a_mn = P.s[si].a_mn, b_mn = P.s[si].b_mn;
@@ -714,7 +715,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ PkGroup g) {
                         if (bp != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                if (j < nj) *reinterpret_cast<uint2*>(bp + j * bstep) = pack_bf16x4(v[j]);
+                                if (j < nj) *reinterpret_cast<uint2*>(bp + j * bstep) = pack_h16x4(v[j], P.cb_f16 != 0);
                         }
                     }
                 }
@@ -740,7 +741,7 @@ struct PkFixProb {
     const float* bias;
     long long ldc, ldcb;
     float alpha, beta;
-    int M, N, bn, tiles_n, n_tiles, splits, blk_begin;
+    int M, N, bn, tiles_n, n_tiles, splits, blk_begin, cb_f16;
 };
 struct PkFix {
     PkFixProb p[TC_MAXP];
@@ -783,7 +784,7 @@ pk_fixup_kernel(const __grid_constant__ PkFix f) {
             x.x = fmaf(P.beta, o.x, x.x); x.y = fmaf(P.beta, o.y, x.y); x.z = fmaf(P.beta, o.z, x.z); x.w = fmaf(P.beta, o.w, x.w);
         }
         if (P.C != nullptr) *reinterpret_cast<float4*>(P.C + (long long)row * P.ldc + col) = x;
-        if (P.Cb != nullptr) *reinterpret_cast<uint2*>(P.Cb + (long long)row * P.ldcb + col) = pack_bf16x4(x);
+        if (P.Cb != nullptr) *reinterpret_cast<uint2*>(P.Cb + (long long)row * P.ldcb + col) = pack_h16x4(x, P.cb_f16 != 0);
     }
 }
 
@@ -958,7 +959,7 @@ static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, vo
         const TcGemm& g = *sel[i];
         PkProb& p = out.p[o];
         p.partials = grp.p[i].partials;
-        p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias;
+        p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias; p.cb_f16 = g.cb_f16 ? 1 : 0;
         p.alpha = g.alpha; p.beta = g.beta; p.M = (int)g.M; p.N = (int)g.N;
         p.bn = bn_[i]; p.tiles_n = tiles_n_[i]; p.n_tiles = tiles_[i]; p.splits = splits_[i]; p.kb_per_split = kbps_[i];
         p.item_begin = item;
@@ -967,7 +968,7 @@ static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, vo
         for (int q = 0; q < g.nseg; ++q) {
             const TcSeg& sg = g.s[q];
             TcSegDev& sd = p.s[q];
-            sd.K = (int)sg.K; sd.a_mn = sg.a_mn ? 1 : 0; sd.b_mn = sg.b_mn ? 1 : 0;
+            sd.K = (int)sg.K; sd.a_mn = sg.a_mn ? 1 : 0; sd.b_mn = sg.b_mn ? 1 : 0; sd.a_f16 = sg.a_f16 ? 1 : 0; sd.b_f16 = sg.b_f16 ? 1 : 0;
             sd.nkb = (int)((sg.K + TC_BK - 1) / TC_BK);
             if (!sg.a_mn) rc = make_map(&sd.ma, sg.A, sg.K, g.M, sg.lda, TC_BK, TC_BM); else rc = make_map(&sd.ma, sg.A, g.M, sg.K, sg.lda, 64, TC_BK);
             if (rc) return rc;
@@ -1009,7 +1010,7 @@ static int pk_launch_group(cudaStream_t st, const TcGemm* const* sel, int np, vo
             if (p.splits <= 1) continue;
             PkFixProb& q = fx.p[fx.n++];
             q.partials = p.partials; q.C = p.C; q.Cb = p.Cb; q.bias = p.bias; q.ldc = p.ldc; q.ldcb = p.ldcb;
-            q.alpha = p.alpha; q.beta = p.beta; q.M = p.M; q.N = p.N; q.bn = p.bn; q.tiles_n = p.tiles_n;
+            q.alpha = p.alpha; q.beta = p.beta; q.M = p.M; q.N = p.N; q.bn = p.bn; q.tiles_n = p.tiles_n; q.cb_f16 = p.cb_f16;
             q.n_tiles = p.n_tiles; q.splits = p.splits; q.blk_begin = blocks;
             blocks += 16 * p.n_tiles;
         }
@@ -1099,13 +1100,13 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
             p.tiles_n = (int)((g.N + bn - 1) / bn);
             p.M = (int)g.M; p.N = (int)g.N;
             p.alpha = g.alpha; p.beta = g.beta;
-            p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias;
+            p.C = g.C; p.ldc = g.ldc; p.Cb = reinterpret_cast<__nv_bfloat16*>(g.Cb); p.ldcb = g.ldcb; p.bias = g.bias; p.cb_f16 = g.cb_f16 ? 1 : 0;
             nkbs[i] = 0;
             kflops[i] = 0;
             for (int q = 0; q < g.nseg; ++q) {
                 const TcSeg& sg = g.s[q];
                 TcSegDev& sd = p.s[q];
-                sd.K = (int)sg.K; sd.a_mn = sg.a_mn ? 1 : 0; sd.b_mn = sg.b_mn ? 1 : 0;
+                sd.K = (int)sg.K; sd.a_mn = sg.a_mn ? 1 : 0; sd.b_mn = sg.b_mn ? 1 : 0; sd.a_f16 = sg.a_f16 ? 1 : 0; sd.b_f16 = sg.b_f16 ? 1 : 0;
                 sd.nkb = (int)((sg.K + TC_BK - 1) / TC_BK);
                 // K-major operand [rows,K]: inner = K, box {64, tile rows};  MN-major operand [K,rows]: inner = rows, box {64, 64}
                 if (!sg.a_mn) rc = make_map(&sd.ma, sg.A, sg.K, g.M, sg.lda, TC_BK, TC_BM); else rc = make_map(&sd.ma, sg.A, g.M, sg.K, sg.lda, 64, TC_BK);

@@ -12,6 +12,7 @@ struct TcSeg {
     int64_t lda;
     const void* B;            // bf16
     int64_t ldb;
+    bool a_f16, b_f16;        // operand holds IEEE half instead of bf16 (tcgen05 kind::f16 formats are per operand)
 };
 
 // C[M,N] = alpha * sum_s op(A_s) op(B_s) (+ bias[N]) (+ beta * C): up to two K-segments accumulate into the
@@ -26,6 +27,7 @@ struct TcGemm {
     int64_t ldc;
     void* Cb;                 // bf16 [M,N] copy of the output, may be null
     int64_t ldcb;
+    bool cb_f16;              // write Cb as IEEE half instead of bf16
     const float* bias;        // fp32 [N] or null
 };
 

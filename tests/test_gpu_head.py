@@ -105,36 +105,45 @@ def _quantised_operand_params(params):
     return q
 
 
-@pytest.mark.parametrize("T,B", [(1, 64), (10, 512)])
+@pytest.mark.parametrize("T,B", [(1, 64), (10, 512), (10, 1024)])
 def test_head_bf16_mode(T, B):
-    """bf16 mode (tcgen05 GEMMs, every GEMM operand rounded to bf16 once, fp32 accumulate, fp32 outputs).
-    Bars: classification logits <= 1e-3 against the oracle evaluated on identically quantised
-    operands (north_star), argmax exact where the fp64 margin exceeds the error bound; fused features
-    and gradients <= 1e-2 (norm-wise) against the UNquantised fp64 oracle (measured 3-6e-3: one bf16
-    rounding per GEMM stage)."""
+    """16-bit tensor-core mode (TEAM_MODE_BF16): every GEMM operand (inputs, weights, forward activations,
+    gradients) rounded to bf16 once, fp32 accumulation in tensor memory, all row-wise math and every output fp32
+    (DESIGN.md 4).  (10, 1024) is the benchmarked shape.  Bars (norm-wise relative error):
+      B. against the same algorithm in fp64 with a rounding at every point where the kernels round
+         (oracle/quantised_model.py, pinned on CPU against the reference-generated oracle): all four feature
+         outputs <= 1e-3 (measured 3e-4), every gradient <= 5e-3 (measured <= 4e-3: the coefficient GEMMs of the
+         table-row gradients round their operands too, the model evaluates them exactly);
+      A. against the reference evaluated in fp64 on the identically quantised OPERANDS (only inputs / weights
+         rounded - SURVEY 7.3 (i), north_star "logits within 1e-3 relative in bf16"): classification logits <= 1e-3,
+         argmax exact where the fp64 margin exceeds the bound; the fused features carry one more bf16 rounding per
+         GEMM stage and are held to 1e-2 here (measured 3-6e-3), gradients to 1.5e-2."""
     from team_b200 import head
+    from oracle import quantised_model as Q
     C = 2 * T
     params = synth.make_params(T, seed=100 + T)
     protos = synth.make_prototypes(C, seed=7)
     batch = synth.make_batch(B, C, step=T)
     cots = synth.make_cotangents(B, step=T)
     outs, grads = run_head(params, batch, protos, cots, head.MODE_BF16)
-    q = _quantised_operand_params(params)
-    xq = batch["image"].to(torch.bfloat16).double()
-    tq = batch["text_cls"].to(torch.bfloat16).double()
-    lq = O.forward_for_classification({k: v.double() for k, v in q.items()}, xq, tq)
-    assert rel(outs[4], lq) < 1e-3, rel(outs[4], lq)
-    top2 = lq.topk(2, dim=1).values
+    p64 = {k: v.double() for k, v in params.items()}
+    args = (p64, batch["image"].double(), batch["text"].double(), batch["state"], protos.double(), [c.double() for c in cots])
+    # ---- A: operand-quantised reference
+    oa, ga, la = Q.head_fwd_bwd(*args, text_cls=batch["text_cls"].double(), operands_only=True)
+    for key, o, r in zip(("image", "text", "state", "proto"), outs[:4], oa):
+        assert rel(o, r) < 1e-2, ("A", key, rel(o, r))
+    assert rel(outs[4], la) < 1e-3, rel(outs[4], la)
+    top2 = la.topk(2, dim=1).values
     safe = (top2[:, 0] - top2[:, 1]) > 2e-3
-    assert torch.equal(outs[5].cpu()[safe], lq.argmax(1)[safe])
-    p64 = {k: v.double().requires_grad_(v.dim() > 0) for k, v in params.items()}
-    ref = O.forward_tri_modal(p64, batch["image"].double(), batch["text"].double(), batch["state"], protos.double())
-    for key, o, r in zip(("image", "text", "state", "proto"), outs[:4], ref[:4]):
-        assert rel(o, r) < 1e-2, (key, rel(o, r))
-    names = O.trainable_names(params)
-    gref = torch.autograd.grad(ref[:4], [p64[n] for n in names], grad_outputs=[c.double() for c in cots])
-    for n, gr in zip(names, gref):
-        assert rel(grads[n], gr) < 1.5e-2, (n, rel(grads[n], gr))
+    assert torch.equal(outs[5].cpu()[safe], la.argmax(1)[safe])
+    # ---- B: rounding at the kernels' own rounding points
+    ob, gb = Q.head_fwd_bwd(*args)
+    for key, o, r in zip(("image", "text", "state", "proto"), outs[:4], ob):
+        assert rel(o, r) < 1e-3, ("B", key, rel(o, r))
+    worst = {n: rel(grads[n], gb[n]) for n in gb}
+    assert max(worst.values()) < 5e-3, worst
+    worst_a = {n: rel(grads[n], ga[n]) for n in ga}
+    assert max(worst_a.values()) < 1.5e-2, worst_a
 
 
 def test_host_batch_pipeline_matches_direct_step():
