@@ -225,7 +225,7 @@ int team_head_tri_classtext_fwd(const team_head_weights* w, int mode, int64_t ba
                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ losses of the training step (SURVEY 8f "next")
- * Replaces: unicl_loss (evolution_features = None)        models/proof.py:21-191, called at :434-441
+ * Replaces: unicl_loss                                     models/proof.py:21-191, called at :434-441
  *           ClipLoss.forward (world_size 1)               utils/toolkit.py:128-141, called at :431
  * Both return the loss value(s) on the device AND the gradient w.r.t. their feature inputs times grad_scale (the
  * learner's weights: total = ce + clip + 0.3 unicl, models/proof.py:442), i.e. the cotangents of team_head_tri_bwd /
@@ -238,6 +238,20 @@ int team_unicl_loss(int mode, const float* image, const float* text, const float
                     int64_t batch, float temperature, float grad_scale, float* losses,
                     float* g_image, float* g_text, float* g_state,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* unicl_loss with evolution_features (models/proof.py:51-106 - what the learner always passes once
+ * evolve_state_prototypes() has run, :435-441): the normalised state rows are first enhanced per class with the
+ * class's evolution feature and, when the class occurs with >= 2 life stages in the batch, a time-weighted mixture of
+ * the class's other state rows; the gradient flows back through the enhancement into every contributing state row.
+ * state_ids [B] int64 in [0,10); evo [num_evo,512] fp32 (row c = evolution_features[c]); evo_mask [num_evo] bytes
+ * (0 = evolution_features[c] is None).  Classes >= num_evo are left alone like in the reference.  Everything runs on
+ * the device (keyed sums over (class, state) instead of the reference's host loops).
+ * workspace: team_loss_evo_workspace_bytes(batch, num_evo). */
+size_t team_loss_evo_workspace_bytes(int64_t batch, int num_evo);
+int team_unicl_loss_evo(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
+                        const int64_t* state_ids, const float* evo, const unsigned char* evo_mask, int num_evo,
+                        int64_t batch, float temperature, float grad_scale, float* losses,
+                        float* g_image, float* g_text, float* g_state,
+                        void* workspace, size_t workspace_bytes, void* stream);
 int team_clip_loss(int mode, const float* image, const float* text, int64_t batch, float logit_scale, float grad_scale,
                    float* loss, float* g_image, float* g_text,
                    void* workspace, size_t workspace_bytes, void* stream);

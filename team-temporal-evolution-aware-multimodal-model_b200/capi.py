@@ -143,6 +143,10 @@ def _declare(lib):
         lib.team_loss_workspace_bytes.argtypes = [i64]
         lib.team_unicl_loss.restype = i32
         lib.team_unicl_loss.argtypes = [i32, vp, vp, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, sz, vp]
+        lib.team_loss_evo_workspace_bytes.restype = sz
+        lib.team_loss_evo_workspace_bytes.argtypes = [i64, i32]
+        lib.team_unicl_loss_evo.restype = i32
+        lib.team_unicl_loss_evo.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i32, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp, sz, vp]
         lib.team_clip_loss.restype = i32
         lib.team_clip_loss.argtypes = [i32, vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, sz, vp]
         lib.team_head_tri_classtext_fwd.restype = i32

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include "head_proof_kernels.cuh"
 #include "head_table_kernels.cuh"
+#include "head_table_gram.cuh"
 #include "gemm_tc.cuh"
 
 namespace team {
@@ -42,7 +43,8 @@ void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     w->img = mat(Bn, D, false); w->txt = mat(Bn, D, false);
     w->Ztab = take(Rt * D);
     w->S = mat(Nsp, D, true, ACT); w->invS = take(Nsp);
-    w->QKVs = mat(Nsp, 3 * D, true, ACT); w->VFs = mat(Nsp, D, true, ACT);
+    w->QKVs = mat(Nsp, 3 * D, true, ACT);
+    w->VFs = mat(Nsp + 2 * TG_RP, D, true, ACT);    // + the table rows (s, n) of the Gram GEMM (head_table_gram.cuh)
     w->TT = take(Nsp * Nsp); w->mt = take(Nsp); w->Zt = take(Nsp); w->Pt = mat(Nsp, Nsp, true, ACT); w->NFt = take(Nsp * D);
     w->Xo = mat(B2, D, true, ACT); w->invo = take(B2);
     w->QKVo = mat(B2, 3 * D, true, ACT); w->VFo = mat(B2, D, true, ACT);
@@ -63,6 +65,7 @@ void head_plan(const HeadDims& d, int mode, void* base, HeadWS* w) {
     w->tab_partials = take((size_t)d.nctas * to.len); w->tab_reduced = take(to.len);
     w->own_partials = take((size_t)d.nctas * OWN_PARTIAL_LEN); w->own_reduced = take(OWN_PARTIAL_LEN);
     w->nrm_partials = take((size_t)4 * NRM_MAX_PARTIALS * D);
+    w->W0 = take(B2 * (size_t)tg_ldw(d)); w->xs = take(Bn * D); w->xst = take(Bn * D); w->RS = take(Bn * (size_t)TG_NRS * 32); w->GT = take(TG_GT_LEN);
     // split-K scratch: largest user is a [512,512] weight gradient reduced over 2B rows
     size_t g = gemm_f32_workspace_bytes(D, D, B2);
     const size_t g2 = gemm_f32_workspace_bytes(Nsp, D, B2);
@@ -312,6 +315,26 @@ static bool use_table2(const HeadDims& d) {
     return v1 == 0 && table2_supported(d) && table2_bwd_smem_floats(d) * sizeof(float) <= 227 * 1024;
 }
 
+// Gram formulation of the table-query rows (head_table_gram.cuh) for batches of at least TEAM_TABLE_GRAM_MIN_B samples
+// (default 32768).  Measured (profiles/EXPERIMENTS.md round 2): its kernels are 1.5 - 1.9x faster than the second
+// generation in isolation at 65 536 samples, but the step gains only 2 % there (both generations fill the register file,
+// so the side-lane kernels no longer overlap) and loses below ~16 384 samples, where its two extra step-level launches
+// sit on the critical path.  TEAM_TABLE_V2 / TEAM_TABLE_V1 force the older kernels.  Read per call (tests flip it).
+static bool use_table_gram(const HeadDims& d) {
+    if (getenv("TEAM_TABLE_V2") != nullptr || getenv("TEAM_TABLE_V1") != nullptr) return false;
+    const char* e = getenv("TEAM_TABLE_GRAM_MIN_B");
+    const int min_b = e != nullptr ? atoi(e) : 32768;
+    return d.B >= min_b && table_gram_supported(d);
+}
+// warps per CTA of the Gram kernels (TEAM_TG_FW / TEAM_TG_BW override, A/B runs)
+static int tg_warps_of(const HeadDims& d, const char* env, int dflt) {
+    const char* e = getenv(env);
+    int nw = e != nullptr ? atoi(e) : dflt;
+    if (nw != 8 && nw != 16) nw = dflt;
+    (void)d;
+    return nw;
+}
+
 static void norm_add(NormList& nl, int& blocks, const float* Z, float* X, __nv_bfloat16* Xh, float* inv, int64_t rows) {
     if (rows <= 0) return;
     NormSeg& s = nl.s[nl.n++];
@@ -396,15 +419,28 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
     seg(wv.add(d.B2, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
     RUN(wv);
+    SideStream* gram_side = nullptr;
     {   // the two softmax kernels (step-row table, own rows) are independent
         const cudaStream_t tst = fork_side(cx.st, &side);
-        TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, tst, w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+        const bool gram = use_table_gram(d);
+        const int xwarps = gram ? TG_RP : 0;                 // + the s rows of the Gram formulation (head_table_gram.cuh)
+        TEAM_LAUNCH(table_prep_kernel, (d.Nsp + xwarps + 7) / 8, 256, 0, tst, w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h, w.S.f, hw->b_fc,
+                    w.VFs.f, (const __nv_bfloat16*)w.VFs.h, d.C, TG_RP,
+                    gram ? w.VFs.f + (size_t)d.Nsp * D : (float*)nullptr, gram && w.VFs.h ? w.VFs.h + (size_t)d.Nsp * D : (__nv_bfloat16*)nullptr);
+        if (gram)             // ... and its n rows
+            TEAM_LAUNCH(table_nf_kernel, d.Rt, 256, ((d.M + 3) / 4 * 4 + 512) * sizeof(float), tst, w.TT, d.M, d.Nsp, d.C, w.VFs.f, (const __nv_bfloat16*)w.VFs.h,
+                        w.VFs.f + (size_t)(d.Nsp + TG_RP) * D, w.VFs.h ? w.VFs.h + (size_t)(d.Nsp + TG_RP) * D : (__nv_bfloat16*)nullptr);
         TEAM_LAUNCH(attn_own_kernel, (d.B2 + 7) / 8, 256, 0, cx.st, d, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, state_ids, w.Aext.f, w.Aext.h, w.aown);
         if ((rc = join_side(cx.st, side))) return rc;
+        // step-level dot products of the table rows: beside GEMM wave 4 (joined before the table-row kernel)
+        if (gram) TEAM_LAUNCH(table_gram_prep_kernel, (d.Rt + 10 + 7) / 8, 256, 0, side != nullptr ? side->st : cx.st, d.Rt, w.VFs.f + (size_t)d.Nsp * D, w.VFs.f + (size_t)d.M * D, w.GT);
+        gram_side = gram ? side : nullptr;
     }
     // ---- wave 4: probabilities x (fc-space) values
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
     seg(wv.add(d.B2, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);
+    // sample x table dot products of the table-query rows (head_table_gram.cuh): W0 = VFo x [VFs ; S_table + b_fc]^T
+    if (use_table_gram(d)) seg(wv.add(d.B2, tg_ldw(d), 0.f, fonly(w.W0, tg_ldw(d))), false, w.VFo, false, w.VFs, D);
     RUN(wv);
     // the own-row outputs and the classification logits do not depend on the table-query rows: side stream
     const cudaStream_t sst = fork_side(cx.st, &side);
@@ -413,7 +449,13 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
         if ((rc = cosine_logits_launch(sst, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
     }
-    if (use_table2(d)) {          // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
+    if (use_table_gram(d)) {      // Gram formulation: scalar LayerNorm algebra per (sample, row), vector outputs as coefficient sums
+        if ((rc = join_side(cx.st, gram_side))) return rc;          // table_gram_prep_kernel
+        const int nw = tg_warps_of(d, "TEAM_TG_FW", tg_warps(d)), groups = (d.B + nw - 1) / nw;
+        const size_t tsm = tg_fwd_smem_floats(d) * sizeof(float);
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_gram_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        TEAM_LAUNCH(table_gram_fwd_kernel, groups < NUM_SMS ? groups : NUM_SMS, nw * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.VFs.f + (size_t)d.Nsp * D, w.GT, w.W0, w.VFo.f, w.VFs.f, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state, w.xs, w.xst, w.RS);
+    } else if (use_table2(d)) {   // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
         const int groups = (d.B + TW - 1) / TW;
         const size_t tsm = table2_fwd_smem_floats(d) * sizeof(float);
         TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
@@ -458,7 +500,15 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     }
     // ---- table-query rows (prototype / state outputs)
     int tgrid;
-    if (use_table2(d)) {          // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
+    if (use_table_gram(d)) {      // Gram formulation (head_table_gram.cuh); needs W0 / GT / xs / xst / RS of the matching forward
+        const int nw = tg_warps_of(d, "TEAM_TG_BW", 8), groups = (d.B + nw - 1) / nw;
+        tgrid = groups < NUM_SMS ? groups : NUM_SMS;
+        // LayerNorm gamma / beta gradients of the table rows: own kernel on the side lane (fields dgam / dbet of the records)
+        TEAM_LAUNCH(table_dgamma_kernel, tgrid, 256, 0, own_side != nullptr ? own_side->st : cx.st, d, g_proto, g_state, w.xs, w.xst, w.tab_partials);
+        const size_t tsm = tg_bwd_smem_floats(d, nw) * sizeof(float);
+        TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_gram_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+        TEAM_LAUNCH(table_gram_bwd_kernel, tgrid, nw * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.VFs.f + (size_t)d.Nsp * D, w.GT, w.VFo.f, w.VFs.f, hw->ln_g, state_ids, g_proto, g_state, w.RS, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
+    } else if (use_table2(d)) {   // warp per sample, table rows resident in shared memory (head_table_kernels.cuh)
         const int groups = (d.B + TW - 1) / TW;
         tgrid = groups < NUM_SMS ? groups : NUM_SMS;
         const size_t tsm = table2_bwd_smem_floats(d) * sizeof(float);
@@ -694,7 +744,7 @@ extern "C" int team_head_proof_fwd(const team_head_weights* hw, int mode, int64_
     seg(wv.add(B, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
     seg(wv.add(B, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
     RUN(wv);
-    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const __nv_bfloat16*)nullptr, 0, 0, (float*)nullptr, (__nv_bfloat16*)nullptr);
     TEAM_LAUNCH(proof_attn_own_kernel, (B + 7) / 8, 256, 0, cx.st, B, M, d.Nsp, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, w.Aext.f, w.Aext.h, w.aown);
     // ---- wave 4: probabilities x (fc-space) values
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
@@ -774,7 +824,7 @@ extern "C" int team_head_tri_classtext_fwd(const team_head_weights* hw, int mode
     seg(wv.add(B, d.Nsp, 0.f, fonly(w.SQ.f, d.Nsp)), false, Qo, false, Ks, D);
     seg(wv.add(B, d.Nsp, 0.f, fonly(w.SK, d.Nsp)), false, Ko, false, Qs, D);
     RUN(wv);
-    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h);
+    TEAM_LAUNCH(table_prep_kernel, (d.Nsp + 7) / 8, 256, 0, cx.st, w.TT, M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h, (const float*)nullptr, (const float*)nullptr, (const float*)nullptr, (const __nv_bfloat16*)nullptr, 0, 0, (float*)nullptr, (__nv_bfloat16*)nullptr);
     TEAM_LAUNCH(ct_attn_own_kernel, (B + 7) / 8, 256, 0, cx.st, B, M, d.Nsp, w.SQ.f, w.QKVo.f, cx.mode == TEAM_MODE_BF16 ? w.QKVo.h : nullptr, state_ids, w.Aext.f, w.Aext.h, w.aown);
     seg(wv.add(d.Nsp, D, 0.f, fonly(w.NFt, D)), false, w.Pt, true, w.VFs, d.Nsp);
     seg(wv.add(B, D, 0.f, fonly(w.Ybo, D)), false, w.Aext, true, w.VFs, d.Nsp);

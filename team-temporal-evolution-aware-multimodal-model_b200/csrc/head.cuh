@@ -55,7 +55,7 @@ struct HeadWS {
     Mat S;                            // [Nsp][D] step rows
     float* invS;                      // [Nsp] inverse norms (proto + state rows)
     Mat QKVs;                         // [Nsp][3D]
-    Mat VFs;                          // [Nsp][D]
+    Mat VFs;                          // [Nsp + 64][D]: VF rows of the step, then the table rows s and n of the Gram formulation
     float* TT;                        // [Nsp][Nsp]
     float *mt, *Zt;                   // [Nsp]
     Mat Pt;                           // [Nsp][Nsp]
@@ -98,6 +98,10 @@ struct HeadWS {
     float* own_partials;              // [nctas][OWN_PARTIAL_LEN]
     float* own_reduced;               // [OWN_PARTIAL_LEN]
     float* nrm_partials;              // [4][NRM_MAX_PARTIALS][D]
+    float* W0;                        // [B2][Nsp + 64] sample x table dot products of the table-query rows (head_table_gram.cuh)
+    float *xs, *xst;                  // [B][D] sum_{k<C} xhat_k and xhat of the state row (forward -> backward)
+    float* RS;                        // [B][8][32] per (sample, row) scalars of the forward (lane = row)
+    float* GT;                        // [832] step-level dot products of the table rows (table_gram_prep_kernel)
     void* gemm_ws;                    // split-K scratch
     size_t gemm_ws_bytes;
     size_t total_bytes;

@@ -160,14 +160,41 @@ fill_prompt_rows_kernel(PtrList prompts, int ppt, int C, int Ns, int Nsp, float*
 
 // ------------------------------------------------------------------ per-step softmax partials of step-row queries
 // For every step row r: m_r = max_j<M TT[r][j]/tau, P[r][j] = exp(TT[r][j]/tau - m_r) (0 for j>=M), Z_r = sum_j P.
+// Warps past the Nsp step rows (optional, Xf != null) write the TABLE rows of the Gram formulation of the table-query
+// rows (head_table_gram.cuh) behind the VF rows of the step - extra B-operand rows of W0 = VFo x [VFs ; s ; n]^T:
+//   Xf[tr]      = s_tr = S_r + b_fc                       (tr < 32: r = the C prototype rows, then the ten state rows)
+//   Xf[32 + tr] = n_tr = sum_{j<M} P[r][j] VFs_j           (table_nf_kernel below)
+// rows past Rt are zero.
 __global__ void __launch_bounds__(256)
 table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restrict__ mt, float* __restrict__ Zt,
-                  float* __restrict__ Pt, __nv_bfloat16* __restrict__ Pth) {
+                  float* __restrict__ Pt, __nv_bfloat16* __restrict__ Pth, const float* __restrict__ S,
+                  const float* __restrict__ bfc, const float* __restrict__ VFsf, const __nv_bfloat16* __restrict__ VFsh,
+                  int C, int xrows, float* __restrict__ Xf, __nv_bfloat16* __restrict__ Xh) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= Nsp) return;
+    if (r >= Nsp) {
+        if (Xf == nullptr) return;
+        const int x = r - Nsp, Rt = C + 10;
+        if (x < xrows) {                                   // s rows (and the zero padding of both tables)
+            float4 v[4];
+            zero_row(v);
+            if (x < Rt) {
+                float4 b[4];
+                ld_row(S + (size_t)(x < C ? x : M + x - C) * D, lane, v);
+                ld_row(bfc, lane, b);
+                add_row(v, b);
+            } else {
+                st_row(Xf + (size_t)(xrows + x) * D, lane, v);
+                st_row_act(Xh != nullptr ? Xh + (size_t)(xrows + x) * D : nullptr, lane, v);
+            }
+            st_row(Xf + (size_t)x * D, lane, v);
+            st_row_act(Xh != nullptr ? Xh + (size_t)x * D : nullptr, lane, v);
+            return;
+        }
+        return;
+    }
     float mx = -INFINITY;
     for (int j = lane; j < M; j += 32) mx = fmaxf(mx, TT[(size_t)r * Nsp + j] * INV_TAU);
     mx = warp_max(mx);
@@ -180,6 +207,59 @@ table_prep_kernel(const float* __restrict__ TT, int M, int Nsp, float* __restric
     }
     z = warp_sum(z);
     if (lane == 0) { mt[r] = mx; Zt[r] = z; }
+}
+
+// n rows of the Gram formulation: Xn[tr] = sum_{j<M} P[r(tr)][j] VFs_j, one CTA per table row, thread = (float4 column,
+// half of the j range).  Operands rounded to bf16 in BF16 mode (VFsh != null) - exactly what the tensor-core product
+// Pt x VFs of GEMM wave 4 multiplies - fp32 accumulation.  Recomputes the row's softmax numerators itself, so it only
+// depends on GEMM wave 3 and runs beside table_prep_kernel.
+__global__ void __launch_bounds__(256)
+table_nf_kernel(const float* __restrict__ TT, int M, int Nsp, int C, const float* __restrict__ VFsf,
+                const __nv_bfloat16* __restrict__ VFsh, float* __restrict__ Xn, __nv_bfloat16* __restrict__ Xnh) {
+    pdl_trigger();
+    pdl_wait();
+    extern __shared__ __align__(16) float nf_smem[];          // p[M] | half sums [128] float4
+    float* p = nf_smem;
+    float4* part = reinterpret_cast<float4*>(nf_smem + ((M + 3) / 4) * 4);
+    const int tr = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int rr = tr < C ? tr : M + tr - C;
+    float mx = -INFINITY;
+    for (int j = lane; j < M; j += 32) mx = fmaxf(mx, TT[(size_t)rr * Nsp + j] * INV_TAU);
+    mx = warp_max(mx);
+    for (int j = tid; j < M; j += blockDim.x) {
+        float v = expf(TT[(size_t)rr * Nsp + j] * INV_TAU - mx);
+        if (VFsh != nullptr) v = __bfloat162float(__float2bfloat16_rn(v));
+        p[j] = v;
+    }
+    __syncthreads();
+    const int c4 = tid & 127, half = tid >> 7;
+    const int jmid = (M + 1) / 2;
+    const int j0 = half == 0 ? 0 : jmid, j1 = half == 0 ? jmid : M;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (VFsh != nullptr) {
+#pragma unroll 8
+        for (int j = j0; j < j1; ++j) {
+            const uint2 u = reinterpret_cast<const uint2*>(VFsh + (size_t)j * D)[c4];
+            const float pj = p[j];
+            acc.x = fmaf(pj, bf16_lo(u.x), acc.x); acc.y = fmaf(pj, bf16_hi(u.x), acc.y);
+            acc.z = fmaf(pj, bf16_lo(u.y), acc.z); acc.w = fmaf(pj, bf16_hi(u.y), acc.w);
+        }
+    } else {
+#pragma unroll 8
+        for (int j = j0; j < j1; ++j) {
+            const float4 v = reinterpret_cast<const float4*>(VFsf + (size_t)j * D)[c4];
+            const float pj = p[j];
+            acc.x = fmaf(pj, v.x, acc.x); acc.y = fmaf(pj, v.y, acc.y); acc.z = fmaf(pj, v.z, acc.z); acc.w = fmaf(pj, v.w, acc.w);
+        }
+    }
+    if (half == 1) part[c4] = acc;
+    __syncthreads();
+    if (half == 0) {
+        const float4 o = part[c4];
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        reinterpret_cast<float4*>(Xn + (size_t)tr * D)[c4] = acc;
+        if (Xnh != nullptr) reinterpret_cast<uint2*>(Xnh + (size_t)tr * D)[c4] = pack_h16x4(acc, ACT_F16);
+    }
 }
 
 // ------------------------------------------------------------------ softmax of the own (image/text) query rows

@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256)
 unicl_instance_kernel(int B, const float* __restrict__ Xi, const float* __restrict__ Xt, const float* __restrict__ Xs,
                       const float* __restrict__ inv_i, const float* __restrict__ inv_t, const float* __restrict__ inv_s,
                       const float* __restrict__ dcat, float inv_tau, float inst_weight, float* __restrict__ g_image,
-                      float* __restrict__ g_text, float* __restrict__ g_state, float* __restrict__ rloss) {
+                      float* __restrict__ g_text, float* __restrict__ g_state, float* __restrict__ rloss,
+                      float* __restrict__ d_state_hat) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -236,12 +237,192 @@ unicl_instance_kernel(int B, const float* __restrict__ Xi, const float* __restri
             ld_row(dcat + (size_t)b * D, lane, t);
             add_row(dv, t);
         }
+        if (r == 2 && d_state_hat != nullptr) {      // evolution branch: the state rows went through evo_fwd_kernel first;
+            st_row(d_state_hat + (size_t)b * D, lane, dv);   // its backward (evo_bwd*_kernel) finishes g_state
+            continue;
+        }
         const float proj = warp_sum(dot_part(dv, v[r]));
         const float iv = invs[r][b];
 #pragma unroll
         for (int i = 0; i < 4; ++i) dv[i] = mul4s(iv, fma4s(-proj, v[r][i], dv[i]));
         st_row(outs[r] + (size_t)b * D, lane, dv);
     }
+}
+
+// ------------------------------------------------------------------ evolution_features branch of unicl_loss
+// models/proof.py:51-106 (restated in oracle/team_oracle.py:enhance_state_features).  With s_j the normalised state
+// rows, c the class and st the state id of sample i, and `evo_c` the class's evolution feature:
+//   class seen once in the batch          : out_i = N(0.8 s_i + 0.2 N(evo_c))
+//   class seen >= 2x with >= 2 states     : t(st) = rank of st among the class's states / (n_states - 1),
+//                                           w(i,j) = 1 - |t_i - t_j| (only if > 0.3),
+//                                           mix_i = evo_c + 0.2 sum_{j != i in class} w(i,j) s_j,  out_i = N(0.7 s_i + 0.3 N(mix_i))
+//   otherwise                             : out_i = s_i
+// The weights depend on (state_i, state_j) only, so with the keyed sums SS[c][st] = sum_{j in class c, state st} s_j
+//   mix_i = evo_c + 0.2 (sum_st w(st_i, st) SS[c][st] - s_i)
+// and the backward needs the same keyed sum of dL/dmix: no O(B^2) loops, no host round trips (the reference reads
+// every label and state id on the host).  Keyed sums are one CTA per key scanning the batch in index order
+// (deterministic).  State ids must lie in [0, 10) (they index the 10-row state embedding).
+constexpr int EVO_NS = 10;
+
+__global__ void __launch_bounds__(128)
+evo_keysum_kernel(int B, const float* __restrict__ rows, const unsigned char* __restrict__ rowmask,
+                  const int64_t* __restrict__ labels, const int64_t* __restrict__ states, int num_evo,
+                  const unsigned char* __restrict__ evo_mask, float* __restrict__ out, int* __restrict__ cnt) {
+    pdl_trigger();
+    pdl_wait();
+    const int key = blockIdx.x, c = key / EVO_NS, st = key - c * EVO_NS;
+    if (!evo_mask[c]) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = 0;
+    for (int j = 0; j < B; ++j) {
+        if (labels[j] != c || clamp_state(states[j]) != st) continue;
+        ++n;
+        if (rowmask != nullptr && !rowmask[j]) continue;
+        const float4 v = reinterpret_cast<const float4*>(rows + (size_t)j * D)[threadIdx.x];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out + (size_t)key * D)[threadIdx.x] = acc;
+    if (cnt != nullptr && threadIdx.x == 0) cnt[key] = n;
+    (void)num_evo;
+}
+
+// time weights of sample i's state against the ten states of its class (0 for absent states / weights <= 0.3);
+// returns the enhancement mode: 0 = unchanged, 1 = single sample, 2 = temporal mixture
+__device__ __forceinline__ int evo_class_weights(const int* __restrict__ cnt_c, int st_i, float (&w)[EVO_NS]) {
+    int n = 0, uniq = 0, rank_i = 0;
+#pragma unroll
+    for (int s = 0; s < EVO_NS; ++s) {
+        const int k = cnt_c[s];
+        n += k;
+        if (k > 0) { if (s < st_i) ++rank_i; ++uniq; }
+        w[s] = 0.f;
+    }
+    if (n <= 1) return 1;
+    if (uniq < 2) return 0;
+    const float inv = 1.0f / (float)(uniq - 1);
+    const float t_i = (float)rank_i * inv;
+    int rank = 0;
+#pragma unroll
+    for (int s = 0; s < EVO_NS; ++s) {
+        if (cnt_c[s] <= 0) continue;
+        const float ws = 1.0f - fabsf(t_i - (float)rank * inv);
+        if (ws > 0.3f) w[s] = ws;
+        ++rank;
+    }
+    return 2;
+}
+
+// forward: enhanced rows Xe, normalised mixtures Mh, per-row scalars sc[b] = {mode, 1/|e|, 1/|mix|, -}
+__global__ void __launch_bounds__(256)
+evo_fwd_kernel(int B, const float* __restrict__ Xs, const int64_t* __restrict__ labels, const int64_t* __restrict__ states,
+               int num_evo, const float* __restrict__ evo, const unsigned char* __restrict__ evo_mask,
+               const float* __restrict__ SS, const int* __restrict__ cnt, float* __restrict__ Xe, float* __restrict__ Mh,
+               float* __restrict__ sc, unsigned char* __restrict__ rowmask) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float4 s[4];
+    ld_row(Xs + (size_t)b * D, lane, s);
+    const int64_t c = labels[b];
+    int mode = 0;
+    float w[EVO_NS];
+    const int st_i = clamp_state(states[b]);
+    if (c >= 0 && c < num_evo && evo_mask[c]) mode = evo_class_weights(cnt + (size_t)c * EVO_NS, st_i, w);
+    float inv_e = 1.f, inv_m = 1.f;
+    if (mode != 0) {
+        float4 m[4];
+        ld_row(evo + (size_t)c * D, lane, m);
+        if (mode == 2) {
+            axpy_row(m, -0.2f, s);
+#pragma unroll
+            for (int q = 0; q < EVO_NS; ++q) {
+                if (w[q] == 0.f) continue;                 // warp-uniform
+                float4 t[4];
+                ld_row(SS + ((size_t)c * EVO_NS + q) * D, lane, t);
+                axpy_row(m, 0.2f * w[q], t);
+            }
+        }
+        inv_m = 1.0f / fmaxf(sqrtf(warp_sum(dot_part(m, m))), NORM_EPS);
+        scale_row(m, inv_m);
+        st_row(Mh + (size_t)b * D, lane, m);
+        const float ks = mode == 2 ? 0.7f : 0.8f, km = mode == 2 ? 0.3f : 0.2f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = fma4s(km, m[i], mul4s(ks, s[i]));
+        inv_e = 1.0f / fmaxf(sqrtf(warp_sum(dot_part(s, s))), NORM_EPS);
+        scale_row(s, inv_e);
+    }
+    st_row(Xe + (size_t)b * D, lane, s);
+    if (lane == 0) {
+        sc[(size_t)b * 4] = (float)mode; sc[(size_t)b * 4 + 1] = inv_e; sc[(size_t)b * 4 + 2] = inv_m;
+        rowmask[b] = mode == 2 ? 1 : 0;
+    }
+}
+
+// backward 1: g = dL/dXe (in dXe) -> dXe := direct part of dL/ds, dMix := dL/dmix (rows of mode 2 only)
+__global__ void __launch_bounds__(256)
+evo_bwd1_kernel(int B, const float* __restrict__ Xe, const float* __restrict__ Mh, const float* __restrict__ sc,
+                float* __restrict__ dXe, float* __restrict__ dMix) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int mode = (int)sc[(size_t)b * 4];
+    if (mode == 0) return;
+    const float inv_e = sc[(size_t)b * 4 + 1], inv_m = sc[(size_t)b * 4 + 2];
+    float4 g[4], o[4];
+    ld_row(dXe + (size_t)b * D, lane, g);
+    ld_row(Xe + (size_t)b * D, lane, o);
+    const float pg = warp_sum(dot_part(g, o));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = mul4s(inv_e, fma4s(-pg, o[i], g[i]));        // dL/de
+    if (mode == 2) {
+        float4 m[4], dm[4];
+        ld_row(Mh + (size_t)b * D, lane, m);
+        const float pm = warp_sum(dot_part(g, m));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dm[i] = mul4s(0.3f * inv_m, fma4s(-pm, m[i], g[i]));   // dL/dmix
+        st_row(dMix + (size_t)b * D, lane, dm);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g[i] = fma4s(-0.2f, dm[i], mul4s(0.7f, g[i]));          // own row is excluded from its mixture
+    } else {
+        scale_row(g, 0.8f);
+    }
+    st_row(dXe + (size_t)b * D, lane, g);
+}
+
+// backward 2: add the mixture part 0.2 sum_st w(st_j, st) DM[c][st], then the normalise-backward of the raw state rows
+__global__ void __launch_bounds__(256)
+evo_bwd2_kernel(int B, const float* __restrict__ Xs, const float* __restrict__ inv_s, const int64_t* __restrict__ labels,
+                const int64_t* __restrict__ states, const float* __restrict__ sc, const float* __restrict__ DM,
+                const int* __restrict__ cnt, const float* __restrict__ dXe, float* __restrict__ g_state) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float4 d[4], s[4];
+    ld_row(dXe + (size_t)b * D, lane, d);
+    ld_row(Xs + (size_t)b * D, lane, s);
+    if ((int)sc[(size_t)b * 4] == 2) {
+        const int64_t c = labels[b];
+        float w[EVO_NS];
+        evo_class_weights(cnt + (size_t)c * EVO_NS, clamp_state(states[b]), w);
+#pragma unroll
+        for (int q = 0; q < EVO_NS; ++q) {
+            if (w[q] == 0.f) continue;
+            float4 t[4];
+            ld_row(DM + ((size_t)c * EVO_NS + q) * D, lane, t);
+            axpy_row(d, 0.2f * w[q], t);
+        }
+    }
+    const float proj = warp_sum(dot_part(d, s));
+    const float iv = inv_s[b];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = mul4s(iv, fma4s(-proj, s[i], d[i]));
+    st_row(g_state + (size_t)b * D, lane, d);
 }
 
 // losses[0] = total, [1] = instance, [2] = category   (scal: 0 valid, 1 category sum, 2 instance sum)
@@ -326,21 +507,56 @@ extern "C" size_t team_loss_workspace_bytes(int64_t batch) {
     return w.total;
 }
 
-extern "C" int team_unicl_loss(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
-                               int64_t batch, float temperature, float grad_scale, float* losses, float* g_image,
-                               float* g_text, float* g_state, void* workspace, size_t workspace_bytes, void* stream) {
+struct EvoArgs {
+    const int64_t* state_ids;
+    const float* evo;                 // [num_evo][D]
+    const unsigned char* evo_mask;    // [num_evo]
+    int num_evo;
+};
+static size_t evo_plan(int64_t B, int num_evo, char* base, float** Xe, float** Mh, float** dXe, float** dMix, float** SS,
+                       float** DM, int** cnt, float** sc, unsigned char** rowmask) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+    const size_t keys = (size_t)num_evo * EVO_NS;
+    *Xe = reinterpret_cast<float*>(take((size_t)B * D * 4)); *Mh = reinterpret_cast<float*>(take((size_t)B * D * 4));
+    *dXe = reinterpret_cast<float*>(take((size_t)B * D * 4)); *dMix = reinterpret_cast<float*>(take((size_t)B * D * 4));
+    *SS = reinterpret_cast<float*>(take(keys * D * 4)); *DM = reinterpret_cast<float*>(take(keys * D * 4));
+    *cnt = reinterpret_cast<int*>(take(keys * 4)); *sc = reinterpret_cast<float*>(take((size_t)B * 16));
+    *rowmask = reinterpret_cast<unsigned char*>(take((size_t)B));
+    return off;
+}
+
+static int unicl_impl(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
+                      const EvoArgs* ev, int64_t batch, float temperature, float grad_scale, float* losses, float* g_image,
+                      float* g_text, float* g_state, void* workspace, size_t workspace_bytes, void* stream) {
     TEAM_REQUIRE(mode == TEAM_MODE_F32 || mode == TEAM_MODE_BF16, "unicl_loss: bad mode %d", mode);
     TEAM_REQUIRE(image && text && state && labels && losses && g_image && g_text && g_state, "unicl_loss: null pointer");
     TEAM_REQUIRE(temperature > 0.f, "unicl_loss: temperature must be positive");
     LossWS w;
     int rc = loss_setup(w, batch, workspace, workspace_bytes, "unicl_loss");
     if (rc) return rc;
+    float *Xe = nullptr, *Mh = nullptr, *dXe = nullptr, *dMix = nullptr, *SS = nullptr, *DM = nullptr, *sc = nullptr;
+    int* cnt = nullptr;
+    unsigned char* rowmask = nullptr;
+    if (ev != nullptr) {
+        TEAM_REQUIRE(ev->state_ids && ev->evo && ev->evo_mask && ev->num_evo >= 1 && ev->num_evo <= 4096, "unicl_loss: bad evolution arguments");
+        const size_t extra = evo_plan(batch, ev->num_evo, reinterpret_cast<char*>(workspace) + w.total, &Xe, &Mh, &dXe, &dMix, &SS, &DM, &cnt, &sc, &rowmask);
+        if (workspace_bytes < w.total + extra) {
+            set_error("unicl_loss: workspace %zu < %zu bytes", workspace_bytes, w.total + extra);
+            return TEAM_EWORKSPACE;
+        }
+    }
     cudaStream_t st = (cudaStream_t)stream;
     const int B = (int)batch, ld = (int)w.G.ld;
     const bool bf = mode == TEAM_MODE_BF16;
     const float inv_tau = 1.0f / temperature;
     TEAM_LAUNCH(loss_normalize_kernel, (3 * B + 7) / 8, 256, 0, st, batch, image, text, state, w.X[0].f, w.X[1].f, w.X[2].f,
                 bf ? w.X[0].h : nullptr, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, w.inv[0], w.inv[1], w.inv[2], 3, 1);
+    if (ev != nullptr) {          // enhanced state rows (models/proof.py:51-106) replace the normalised ones in the instance term
+        const int keys = ev->num_evo * EVO_NS;
+        TEAM_LAUNCH(evo_keysum_kernel, keys, 128, 0, st, B, w.X[2].f, (const unsigned char*)nullptr, labels, ev->state_ids, ev->num_evo, ev->evo_mask, SS, cnt);
+        TEAM_LAUNCH(evo_fwd_kernel, (B + 7) / 8, 256, 0, st, B, w.X[2].f, labels, ev->state_ids, ev->num_evo, ev->evo, ev->evo_mask, SS, cnt, Xe, Mh, sc, rowmask);
+    }
     {   // sim = Xi Xi^T
         LSeg s{false, false, D, w.X[0], w.X[0]};
         if ((rc = loss_gemm(st, mode, w, B, B, w.sim, ld, &s, 1))) return rc;
@@ -352,10 +568,40 @@ extern "C" int team_unicl_loss(int mode, const float* image, const float* text, 
         LSeg s[2] = {{false, true, B, w.G, w.X[0]}, {true, true, B, w.G, w.X[0]}};
         if ((rc = loss_gemm(st, mode, w, B, D, w.dcat, D, s, 2))) return rc;
     }
-    TEAM_LAUNCH(unicl_instance_kernel, (B + 7) / 8, 256, 0, st, B, w.X[0].f, w.X[1].f, w.X[2].f, w.inv[0], w.inv[1], w.inv[2], w.dcat, inv_tau, grad_scale / (3.0f * (float)B), g_image, g_text, g_state, w.rloss + B);
+    TEAM_LAUNCH(unicl_instance_kernel, (B + 7) / 8, 256, 0, st, B, w.X[0].f, w.X[1].f, ev != nullptr ? Xe : w.X[2].f, w.inv[0], w.inv[1], w.inv[2], w.dcat, inv_tau, grad_scale / (3.0f * (float)B), g_image, g_text, g_state, w.rloss + B, dXe);
+    if (ev != nullptr) {
+        const int keys = ev->num_evo * EVO_NS;
+        TEAM_LAUNCH(evo_bwd1_kernel, (B + 7) / 8, 256, 0, st, B, Xe, Mh, sc, dXe, dMix);
+        TEAM_LAUNCH(evo_keysum_kernel, keys, 128, 0, st, B, dMix, rowmask, labels, ev->state_ids, ev->num_evo, ev->evo_mask, DM, (int*)nullptr);
+        TEAM_LAUNCH(evo_bwd2_kernel, (B + 7) / 8, 256, 0, st, B, w.X[2].f, w.inv[2], labels, ev->state_ids, sc, DM, cnt, dXe, g_state);
+    }
     TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, B, w.rloss + B, (const float*)nullptr, w.scal + 2);
     TEAM_LAUNCH(unicl_finish_kernel, 1, 32, 0, st, w.scal, 1.0f / (3.0f * (float)B), losses);
     return TEAM_OK;
+}
+
+extern "C" int team_unicl_loss(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
+                               int64_t batch, float temperature, float grad_scale, float* losses, float* g_image,
+                               float* g_text, float* g_state, void* workspace, size_t workspace_bytes, void* stream) {
+    return unicl_impl(mode, image, text, state, labels, nullptr, batch, temperature, grad_scale, losses, g_image, g_text,
+                      g_state, workspace, workspace_bytes, stream);
+}
+
+extern "C" size_t team_loss_evo_workspace_bytes(int64_t batch, int num_evo) {
+    if (batch < 1 || batch > LOSS_MAX_BATCH || num_evo < 1 || num_evo > 4096) return 0;
+    LossWS w;
+    loss_plan(batch, nullptr, &w);
+    float *a, *b, *c, *d, *e, *f, *g; int* n; unsigned char* m;
+    return w.total + evo_plan(batch, num_evo, nullptr, &a, &b, &c, &d, &e, &f, &n, &g, &m);
+}
+
+extern "C" int team_unicl_loss_evo(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
+                                   const int64_t* state_ids, const float* evo, const unsigned char* evo_mask, int num_evo,
+                                   int64_t batch, float temperature, float grad_scale, float* losses, float* g_image,
+                                   float* g_text, float* g_state, void* workspace, size_t workspace_bytes, void* stream) {
+    EvoArgs ev{state_ids, evo, evo_mask, num_evo};
+    return unicl_impl(mode, image, text, state, labels, &ev, batch, temperature, grad_scale, losses, g_image, g_text,
+                      g_state, workspace, workspace_bytes, stream);
 }
 
 extern "C" int team_clip_loss(int mode, const float* image, const float* text, int64_t batch, float logit_scale,

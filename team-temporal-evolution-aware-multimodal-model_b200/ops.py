@@ -118,9 +118,24 @@ def dynamic_temperature(temperature: float = 0.07, epoch=None, max_epoch=None) -
     return float(temperature * (0.5 + 0.5 * 0.5 * (1.0 + math.cos(math.pi * progress))))
 
 
+def pack_evolution_features(evolution_features, device):
+    """``evolution_features`` as the reference passes it (a list indexed by class id, entries None or a 512-vector;
+    Proof_Net.evolution_embeddings, utils/inc_net.py:594-617) -> (table [E,512] fp32, mask [E] uint8) on ``device``."""
+    E = len(evolution_features)
+    table = torch.zeros((E, capi.D), dtype=torch.float32, device=device)
+    mask = torch.zeros((E,), dtype=torch.uint8, device=device)
+    rows = [i for i, e in enumerate(evolution_features) if e is not None]
+    if rows:
+        table[rows] = torch.stack([evolution_features[i].detach().reshape(-1).to(device=device, dtype=torch.float32) for i in rows])
+        mask[rows] = 1
+    return table, mask
+
+
 def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, labels: torch.Tensor, *,
+               state_ids: Optional[torch.Tensor] = None, evolution_features=None,
                temperature: float = 0.07, epoch=None, max_epoch=None, grad_scale: float = 1.0, mode: int = capi.MODE_F32):
-    """unicl_loss (models/proof.py:21-191, evolution_features=None) forward + gradient in one call.
+    """unicl_loss (models/proof.py:21-191) forward + gradient in one call, including the ``evolution_features``
+    branch (:51-106; pass the list the learner passes, or a ``(table, mask)`` pair from ``pack_evolution_features``).
     Returns (losses [3] = total / instance / category on the device, (g_image, g_text, g_state) [B,512] =
     grad_scale * d total / d input) - the gradients are the cotangents of the head's backward."""
     capi.require_device()
@@ -129,19 +144,37 @@ def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, lab
     if B == 1:        # models/proof.py:41-45: a batch of one returns a zero loss (and therefore zero gradients)
         return (torch.zeros((3,), dtype=torch.float32, device=xs[0].device),
                 tuple(torch.zeros((1, capi.D), dtype=torch.float32, device=xs[0].device) for _ in range(3)))
-    y = labels.detach().to(device=xs[0].device, dtype=torch.int64).contiguous()
+    dev = xs[0].device
+    y = labels.detach().to(device=dev, dtype=torch.int64).contiguous()
     L = capi.lib()
-    nbytes = L.team_loss_workspace_bytes(B)
+    evo = None
+    if evolution_features is not None and len(evolution_features) > 0:          # models/proof.py:52
+        if state_ids is None:
+            raise ValueError("unicl_loss: evolution_features needs state_ids")
+        evo = evolution_features if isinstance(evolution_features, tuple) else pack_evolution_features(evolution_features, dev)
+        sid = state_ids.detach().to(device=dev, dtype=torch.int64).contiguous()
+        if sid.shape != (B,):
+            raise ValueError("state_ids must be [B]")
+        nbytes = L.team_loss_evo_workspace_bytes(B, evo[0].shape[0])
+    else:
+        nbytes = L.team_loss_workspace_bytes(B)
     if nbytes == 0:
         raise ValueError(f"unicl_loss: batch {B} out of range")
-    dev = xs[0].device
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     losses = torch.empty((3,), dtype=torch.float32, device=dev)
     grads = torch.empty((3, B, capi.D), dtype=torch.float32, device=dev)
-    capi.check(L.team_unicl_loss(mode, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), y.data_ptr(), B,
-                                 dynamic_temperature(temperature, epoch, max_epoch), float(grad_scale), losses.data_ptr(),
-                                 grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ws.data_ptr(), nbytes,
-                                 _stream_ptr()), "team_unicl_loss")
+    tau = dynamic_temperature(temperature, epoch, max_epoch)
+    if evo is None:
+        capi.check(L.team_unicl_loss(mode, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), y.data_ptr(), B,
+                                     tau, float(grad_scale), losses.data_ptr(),
+                                     grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ws.data_ptr(), nbytes,
+                                     _stream_ptr()), "team_unicl_loss")
+    else:
+        capi.check(L.team_unicl_loss_evo(mode, xs[0].data_ptr(), xs[1].data_ptr(), xs[2].data_ptr(), y.data_ptr(),
+                                         sid.data_ptr(), evo[0].data_ptr(), evo[1].data_ptr(), evo[0].shape[0], B,
+                                         tau, float(grad_scale), losses.data_ptr(),
+                                         grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ws.data_ptr(), nbytes,
+                                         _stream_ptr()), "team_unicl_loss_evo")
     return losses, (grads[0], grads[1], grads[2])
 
 

@@ -146,6 +146,45 @@ def test_head_bf16_mode(T, B):
     assert max(worst_a.values()) < 1.5e-2, worst_a
 
 
+@pytest.mark.parametrize("mode_name,T,B", [("f32", 3, 40), ("f32", 10, 300), ("bf16", 10, 512)])
+def test_gram_table_rows_match_the_oracle(mode_name, T, B, monkeypatch):
+    """The Gram formulation of the table-query rows (csrc/head_table_gram.cuh, the default from 32 768 samples per
+    GPU) forced on at small batches: the same parity bars as the default kernels - fp32 <= 1e-5 / 2e-5 against the
+    fp64 oracle, bf16 against the model that rounds where the kernels round - and it must agree with the
+    second-generation kernels on every output and gradient."""
+    from team_b200 import head
+    from oracle import quantised_model as Q
+    C = 2 * T
+    params = synth.make_params(T, seed=300 + T)
+    protos = synth.make_prototypes(C, seed=11)
+    batch = synth.make_batch(B, C, step=T, five_state=(T == 3))
+    cots = synth.make_cotangents(B, step=T)
+    mode = head.MODE_F32 if mode_name == "f32" else head.MODE_BF16
+    monkeypatch.setenv("TEAM_TABLE_GRAM_MIN_B", "0")
+    outs_g, grads_g = run_head(params, batch, protos, cots, mode)
+    monkeypatch.setenv("TEAM_TABLE_GRAM_MIN_B", "1000000000")
+    outs_2, grads_2 = run_head(params, batch, protos, cots, mode)
+    tol = 2e-5 if mode_name == "f32" else 2e-3
+    for a, b in zip(outs_g[:4], outs_2[:4]):
+        assert rel(a, b) < tol, rel(a, b)
+    assert max(rel(grads_g[n], grads_2[n]) for n in grads_2) < (5e-5 if mode_name == "f32" else 5e-3)
+    p64 = {k: v.double().requires_grad_(v.dim() > 0) for k, v in params.items()}
+    if mode_name == "f32":
+        ref = O.forward_tri_modal(p64, batch["image"].double(), batch["text"].double(), batch["state"], protos.double())
+        names = O.trainable_names(params)
+        gref = torch.autograd.grad(ref[:4], [p64[n] for n in names], grad_outputs=[c.double() for c in cots])
+        for o, r in zip(outs_g[:4], ref[:4]):
+            assert rel(o, r) < 1e-5, rel(o, r)
+        for n, gr in zip(names, gref):
+            assert rel(grads_g[n], gr) < 2e-5, (n, rel(grads_g[n], gr))
+    else:
+        pd = {k: v.double() for k, v in params.items()}
+        ob, gb = Q.head_fwd_bwd(pd, batch["image"].double(), batch["text"].double(), batch["state"], protos.double(), [c.double() for c in cots])
+        for o, r in zip(outs_g[:4], ob):
+            assert rel(o, r) < 1e-3, rel(o, r)
+        assert max(rel(grads_g[n], gb[n]) for n in gb) < 5e-3
+
+
 def test_host_batch_pipeline_matches_direct_step():
     """HostBatchPipeline (pinned host batches, copy stream, graph replay, D2H predictions) gives the same
     predictions and the same gradient bucket as a direct HeadStepRunner step on the same data."""
