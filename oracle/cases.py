@@ -39,6 +39,8 @@ CASES: Dict[str, dict] = {
     "clip_B16": {"kind": "clip", "B": 16, "seed": 6002, "logit_scale": 14.285714},
     # unicl_loss WITH evolution features (models/proof.py:51-106): 5 classes, class 3 has no feature, class ids >= 4 out of range
     "unicl_B20_evolution": {"kind": "unicl", "B": 20, "C": 6, "seed": 6003, "epoch": 5, "max_epoch": 20, "evolution": True},
+    # the complete reference learner: 2 incremental tasks x 2 epochs on the synthetic DataManager (oracle/learner_harness.py)
+    "learner_2tasks": {"kind": "learner", "tasks": 2, "epochs": 2, "seed": 7},
 }
 
 

@@ -242,7 +242,17 @@ def gen_clip(case):
     return {"loss": _np(loss.detach()), "g_image": _np(x[0].grad), "g_text": _np(x[1].grad)}
 
 
-GENERATORS = {"head": gen_head, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward,
+def gen_learner(case):
+    """The unmodified reference learner (models/proof.py Learner.incremental_train) on the synthetic DataManager of
+    oracle/learner_harness.py, CPU, dropout p = 0: accuracy curve, prototypes, per-state prototypes, distance factors,
+    exemplar memory and trained parameters after `tasks` tasks."""
+    from oracle import learner_harness
+    import contextlib, io
+    with contextlib.redirect_stderr(io.StringIO()):
+        return learner_harness.run(torch.device("cpu"), swap=False, tasks=case["tasks"], epochs=case["epochs"], seed=case["seed"])
+
+
+GENERATORS = {"head": gen_head, "learner": gen_learner, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward,
               "cosine_linear": gen_cosine_linear, "cal_prototype": gen_cal_prototype,
               "simplecil": gen_simplecil, "evolve": gen_evolve,
               "state_distance_forward": gen_state_distance_forward,

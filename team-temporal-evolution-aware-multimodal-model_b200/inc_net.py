@@ -264,6 +264,21 @@ class Proof_Net(nn.Module):
         self.img_prototypes = self.img_prototypes.to(self._device)
         return self.img_prototypes
 
+    def extract_vector(self, x):
+        """SimpleClipNet.extract_vector (utils/inc_net.py:324-325): the frozen tower's features (exemplar herding,
+        models/base.py:213-238)."""
+        return self.convnet.encode_image(x)
+
+    def _check_dropout(self):
+        """The reference applies Dropout(0.1) to the attention probabilities and to the fc output in train mode
+        (convs/projections.py:28,62,84; `.train()` at models/proof.py:398).  The fused kernels share the softmax of
+        the step rows between all samples, which a per-(sample, query, key) mask would break, so they implement
+        p = 0 only - and say so instead of silently training without dropout."""
+        if self.training and self.sel_attn.dropout.p > 0:
+            raise NotImplementedError(
+                "team_b200 evaluates sel_attn without dropout: set net.sel_attn.dropout.p = 0.0 (INTEGRATION.md, "
+                "'Dropout') or call the head in eval() mode; the reference default is p = 0.1 in train mode")
+
     def encode_image(self, x, normalize: bool = False):
         feats = self.convnet.encode_image(x.to(self._device))
         return head.encode_grad(self._pack(), "image", feats, normalize=normalize, mode=self.team_mode)
@@ -281,6 +296,7 @@ class Proof_Net(nn.Module):
     def forward_tri_modal(self, image, text, state_ids):
         """(image [B,512], text [B,1,512], state [B,512], proto [B,512], exp(logit_scale)); per-sample text
         (``len(text) == B``, the only form the learner uses, models/proof.py:421-425)."""
+        self._check_dropout()
         img = self.convnet.encode_image(image.to(self._device))
         if isinstance(text, list):
             text = self.tokenizer(text)
