@@ -492,6 +492,56 @@ def run_team(a):
                 at_scale.append({"batch_per_gpu": Bs, "error": str(exc)[:200]})
                 torch.cuda.empty_cache()
 
+    # ---- the COMPLETE training step of the learner's loop body (models/proof.py:403-451 after the frozen towers):
+    # logits + forward_tri_modal + ClipLoss branch + unicl_loss with evolution features + backward + fused AdamW,
+    # captured as one CUDA graph (team_b200.train.TrainStep), N = 1.  Device-resident batches (value) and host
+    # batches through load() with the losses read back every step (e2e).
+    train_step = None
+    if world == 1 and not a.no_e2e:
+        try:
+            from team_b200 import train
+            ptrain = {k: v.clone() for k, v in pdev.items()}
+            gen = torch.Generator().manual_seed(5)
+            evo = [torch.randn(512, generator=gen) for _ in range(C)]
+            ts = train.TrainStep(ptrain, protos, B, text_cls, mode=mode, evolution_features=evo)
+            nrot = min(rot, 16)
+            labs = [synth.make_batch(B, C, step=rank * 1000 + j)["label"].to(dev) for j in range(nrot)]
+            with torch.cuda.stream(stream):
+                for i in range(3):
+                    ts.load(imgs[i], txts[i], sids[i], labs[i]); ts.step(epoch=0)
+                torch.cuda.synchronize()
+                c0 = L.team_launch_count()
+                ts._body(0)                                   # one eager pass only to count the library launches
+                tl = L.team_launch_count() - c0
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(stream)
+                for i in range(a.steps):
+                    j = i % nrot
+                    ts.load(imgs[j], txts[j], sids[j], labs[j]); ts.step(epoch=0)
+                ev1.record(stream)
+                torch.cuda.synchronize()
+                tms_dev = ev0.elapsed_time(ev1) / a.steps
+                h = [(imgs[j].cpu().pin_memory(), txts[j].cpu().pin_memory(), sids[j].cpu().pin_memory(), labs[j].cpu().pin_memory())
+                     for j in range(nrot)]
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                last = None
+                for i in range(a.steps):
+                    ts.load(*h[i % nrot])
+                    lossv = ts.step(epoch=0).cpu()            # D2H of the step's losses (and the sync a logging loop has)
+                    last = lossv
+                dt = time.perf_counter() - t0
+            train_step = {"what": "cls logits + forward_tri_modal + ClipLoss branch + unicl_loss (evolution features) + backward "
+                                  "+ fused AdamW as one CUDA graph (team_b200.train.TrainStep)",
+                          "batch": B, "ms_per_step": tms_dev, "samples_per_s": B / tms_dev * 1e3, "library_launches_per_step": int(tl),
+                          "e2e": {"ms_per_step": dt / a.steps * 1e3, "samples_per_s": B * a.steps / dt,
+                                  "h2d_bytes_per_step": B * (512 * 4 * 2 + 16), "d2h_bytes_per_step": 20,
+                                  "api": "TrainStep.load(pinned host batch) + step() + losses.cpu() every step"},
+                          "last_losses": [float(v) for v in last]}
+            del ts
+        except Exception as exc:
+            train_step = {"error": str(exc)[:300]}
+
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb, _, _ = time_cpu(T, B, 3, 1, budget_s=25.0)
@@ -503,7 +553,7 @@ def run_team(a):
                 "config": workload_config(T, B, world),
                 "run": {"grad_exchange": comm, "cuda_graphs": graphs is not None,
                         "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2"},
-                "roofline": roof, "at_scale": at_scale, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
+                "roofline": roof, "at_scale": at_scale, "train_step": train_step, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_per_step) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
         print(json.dumps(line), flush=True)

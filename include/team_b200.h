@@ -263,6 +263,12 @@ int team_clip_loss(int mode, const float* image, const float* text, int64_t batc
 int team_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                     float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int64_t step, void* stream);
+/* The same update for a CUDA graph that is replayed every step: the step count t lives in device memory (*step_dev =
+ * number of updates done so far, int64), the bias corrections are computed from it on the device; with advance != 0 a
+ * one-thread kernel increments it behind the update (pass 0 for all but the last call of a step with > 48 tensors). */
+int team_adamw_step_graph(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                          float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int64_t* step_dev, int32_t advance, void* stream);
 
 /* ------------------------------------------------------------------ gradient all-reduce over NVLink peer memory
  * The reference has no working multi-GPU path (its nn.DataParallel wrap crashes, models/proof.py:312-313 vs :248);

@@ -21,9 +21,15 @@ struct OptList {
 //   p *= 1 - lr wd;  m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 __global__ void __launch_bounds__(256)
-adamw_kernel(const __grid_constant__ OptList L, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+adamw_kernel(const __grid_constant__ OptList L, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+             const long long* __restrict__ step_dev) {
     pdl_trigger();
     pdl_wait();
+    if (step_dev != nullptr) {          // graph form: the step count lives on the device (adamw_tick_kernel advances it)
+        const double t = (double)(*step_dev + 1);
+        bc1 = (float)(1.0 - pow((double)b1, t));
+        bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+    }
     int t = 0;
     for (int i = 1; i < L.count; ++i)
         if ((long long)blockIdx.x >= L.blk0[i]) t = i;
@@ -43,16 +49,43 @@ adamw_kernel(const __grid_constant__ OptList L, float lr, float b1, float b2, fl
     }
 }
 
+__global__ void adamw_tick_kernel(long long* step_dev) {
+    pdl_trigger();
+    pdl_wait();
+    if (threadIdx.x == 0) *step_dev += 1;
+}
+
 }  // namespace team
 
 using namespace team;
 
+static int adamw_launch(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int64_t step, long long* step_dev, void* stream);
+
 extern "C" int team_adamw_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
                                float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
                                float eps, float weight_decay, int64_t step, void* stream) {
+    TEAM_REQUIRE(step >= 1, "adamw: step counts from 1");
+    return adamw_launch(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, nullptr, stream);
+}
+
+extern "C" int team_adamw_step_graph(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                                     float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2,
+                                     float eps, float weight_decay, int64_t* step_dev, int32_t advance, void* stream) {
+    TEAM_REQUIRE(step_dev != nullptr, "adamw: null step counter");
+    int rc = adamw_launch(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, 1,
+                          reinterpret_cast<long long*>(step_dev), stream);
+    if (rc) return rc;
+    if (advance) TEAM_LAUNCH(adamw_tick_kernel, 1, 32, 0, (cudaStream_t)stream, reinterpret_cast<long long*>(step_dev));
+    return TEAM_OK;
+}
+
+static int adamw_launch(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                        float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int64_t step, long long* step_dev, void* stream) {
     TEAM_REQUIRE(n_tensors >= 0 && n_tensors <= OPT_MAX_TENSORS, "adamw: %d tensors (max %d per call)", n_tensors, OPT_MAX_TENSORS);
     TEAM_REQUIRE(n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numel), "adamw: null table");
-    TEAM_REQUIRE(step >= 1, "adamw: step counts from 1");
     if (n_tensors == 0) return TEAM_OK;
     OptList L;
     memset(&L, 0, sizeof(L));
@@ -67,6 +100,6 @@ extern "C" int team_adamw_step(int32_t n_tensors, float* const* params, const fl
     L.count = n_tensors;
     if (blocks == 0) return TEAM_OK;
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    TEAM_LAUNCH(adamw_kernel, blocks, 256, 0, (cudaStream_t)stream, L, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+    TEAM_LAUNCH(adamw_kernel, blocks, 256, 0, (cudaStream_t)stream, L, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), (const long long*)step_dev);
     return TEAM_OK;
 }

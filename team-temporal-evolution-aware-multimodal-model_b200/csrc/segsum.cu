@@ -181,6 +181,143 @@ segsum_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ label
     cluster.sync();     // keep smem alive until every peer has read it
 }
 
+// ------------------------------------------------------------------ second generation of pass 1 (K <= 400 keys)
+// The first generation above reaches 55 % of the HBM copy peak with class keys and 8.5 % with class x state keys
+// (profiles/r1j_*): a feature row is only requested once its label has arrived and says its key lies in the CTA's key
+// slab - every group of rows costs dependent round trips, and with several slabs the loads are sparse.  Here
+//   * the COLUMNS are split instead of the keys: a CTA owns 128 * VEC columns (VEC = 4 / 2 / 1 floats per thread ->
+//     1 / 2 / 4 CTAs side by side per row chunk) of ALL keys (K * VEC * 512 bytes of accumulators), so every row is
+//     read exactly once, densely and unconditionally - the loads never wait for a label;
+//   * keys are computed once per CTA for a block of 128 rows (thread t: row t) into shared memory, one block ahead;
+//   * 2 x U rows are in flight per thread (double-buffered register groups);
+//   * no clusters: the per-CTA partials ([chunks][K][512]) are summed by pass 2 in chunk order (< 2 % extra traffic).
+// Thread t still owns its columns of every key accumulator and adds rows in row order: no atomics, bit-reproducible.
+constexpr int SEG2_KBLK = 128;
+
+template <typename T, int VEC> struct VecLoad;
+template <> struct VecLoad<float, 4> { static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { const float4 a = ld_stream_f4(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; } };
+template <> struct VecLoad<float, 2> { static __device__ __forceinline__ void load(const float* p, float (&v)[2]) { const uint2 a = ld_stream_u2(p); v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); } };
+template <> struct VecLoad<float, 1> { static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = __ldg(p); } };
+template <> struct VecLoad<__nv_bfloat16, 4> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) { const uint2 u = ld_stream_u2(p); v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y); } };
+template <> struct VecLoad<__nv_bfloat16, 2> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[2]) { const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p)); v[0] = bf16_lo(u); v[1] = bf16_hi(u); } };
+template <> struct VecLoad<__nv_bfloat16, 1> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); } };
+
+template <typename T, int VEC, int U, bool NORM>
+__global__ void __launch_bounds__(SEG_THREADS)
+segsum2_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, const int64_t* __restrict__ states,
+                       int64_t n_rows, int64_t rows_per_cta, int64_t class_base, int num_classes, int num_states, int K,
+                       float* __restrict__ part_sums, long long* __restrict__ part_counts) {
+    static_assert(!NORM || VEC == 4, "row normalisation needs the whole row in one CTA");
+    static_assert(SEG2_KBLK % (2 * U) == 0, "key block must hold whole group pairs");
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    constexpr int W = SEG_THREADS * VEC;                        // columns of this CTA
+    constexpr int NCOL = D / W;
+    float* acc = reinterpret_cast<float*>(seg_smem);            // [K][W]
+    int* cnt = reinterpret_cast<int*>(acc + (size_t)K * W);     // [K]
+    int* keys = cnt + K;                                        // [2][SEG2_KBLK]
+    float* red = reinterpret_cast<float*>(keys + 2 * SEG2_KBLK);    // [2][4][U] (NORM)
+    const int t = threadIdx.x;
+    const int cs = blockIdx.x % NCOL;
+    const int64_t chunk = blockIdx.x / NCOL;
+    for (int i = t; i < K * W; i += SEG_THREADS) acc[i] = 0.f;
+    for (int i = t; i < K; i += SEG_THREADS) cnt[i] = 0;
+    const int64_t r0 = chunk * rows_per_cta;
+    const int64_t r1 = min(n_rows, r0 + rows_per_cta);
+    const T* xc = x + (size_t)cs * W + (size_t)t * VEC;         // this thread's columns of row 0
+    auto key_of = [&](int64_t row) -> int {
+        if (row >= r1) return -1;
+        const int64_t c = __ldg(labels + row) - class_base;
+        if (c < 0 || c >= num_classes) return -1;
+        if (states == nullptr) return (int)c;
+        const int64_t s = __ldg(states + row);
+        return (s >= 0 && s < num_states) ? (int)(c * num_states + s) : -1;
+    };
+    auto load_group = [&](int64_t r, float (&v)[U][VEC]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u < r1) {
+                VecLoad<T, VEC>::load(xc + (r + u) * D, v[u]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) v[u][q] = 0.f;
+            }
+        }
+    };
+    int nbuf = 0;
+    auto add_group = [&](const int* kb, float (&v)[U][VEC]) {
+        if (NORM) {
+            float ss[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ss[u] = 0.f;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) ss[u] = fmaf(v[u][q], v[u][q], ss[u]);
+                ss[u] = warp_sum(ss[u]);
+            }
+            if ((t & 31) == 0) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) red[(nbuf * 4 + (t >> 5)) * U + u] = ss[u];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float tot = red[(nbuf * 4 + 0) * U + u] + red[(nbuf * 4 + 1) * U + u] + red[(nbuf * 4 + 2) * U + u] + red[(nbuf * 4 + 3) * U + u];
+                const float inv = 1.0f / fmaxf(sqrtf(tot), NORM_EPS);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) v[u][q] *= inv;
+            }
+            nbuf ^= 1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = kb[u];
+            if (k >= 0) {
+                float* a = acc + (size_t)k * W + t * VEC;
+                if (VEC == 4) {
+                    float4 o = *reinterpret_cast<float4*>(a);
+                    o.x += v[u][0]; o.y += v[u][1 % VEC]; o.z += v[u][2 % VEC]; o.w += v[u][3 % VEC];
+                    *reinterpret_cast<float4*>(a) = o;
+                } else if (VEC == 2) {
+                    float2 o = *reinterpret_cast<float2*>(a);
+                    o.x += v[u][0]; o.y += v[u][1 % VEC];
+                    *reinterpret_cast<float2*>(a) = o;
+                } else {
+                    a[0] += v[u][0];
+                }
+                if (t == 0 && cs == 0) cnt[k] += 1;
+            }
+        }
+    };
+    float va[U][VEC], vb[U][VEC];
+    keys[t] = key_of(r0 + t);                    // SEG_THREADS == SEG2_KBLK: thread t computes the key of row t of a block
+    load_group(r0, va);
+    __syncthreads();
+    int cur = 0;
+    for (int64_t blk = r0; blk < r1; blk += SEG2_KBLK) {
+        const int knext = key_of(blk + SEG2_KBLK + t);           // next block's keys: in flight under this block
+        const int* kb = keys + cur * SEG2_KBLK;
+#pragma unroll 1
+        for (int g = 0; g < SEG2_KBLK; g += 2 * U) {
+            const int64_t r = blk + g;
+            load_group(r + U, vb);
+            add_group(kb + g, va);
+            load_group(r + 2 * U, va);
+            add_group(kb + g + U, vb);
+        }
+        keys[(cur ^ 1) * SEG2_KBLK + t] = knext;
+        __syncthreads();
+        cur ^= 1;
+    }
+    // per-CTA partial: [chunk][K][512], this CTA's columns
+    float* out = part_sums + ((size_t)chunk * K) * D + (size_t)cs * W;
+    for (int i = t; i < K * (W / VEC); i += SEG_THREADS) {
+        const int k = i / (W / VEC), c = (i - k * (W / VEC)) * VEC;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) out[(size_t)k * D + c + q] = acc[(size_t)k * W + c + q];
+    }
+    if (cs == 0) for (int i = t; i < K; i += SEG_THREADS) part_counts[(size_t)chunk * K + i] = cnt[i];
+}
+
 // pass 2: fixed-order sum over clusters.  grid = K, 512 threads = 128 float4 columns x 4 lanes
 // of cluster partials; lane g sums clusters g, g+4, ... then the 4 lanes fold in order.
 __global__ void __launch_bounds__(512)
@@ -275,6 +412,43 @@ static void seg_plan(int64_t n_rows, int64_t K, int* n_clusters, int* n_slabs, i
     *rows_per_cta = rpc;
 }
 
+// second generation: VEC floats per thread, n_chunks row chunks; returns false when the first generation must run
+static bool seg2_plan(int64_t n_rows, int64_t K, bool norm, int* vec, int* n_chunks, int64_t* rows_per_cta) {
+    if (getenv("TEAM_SEGSUM_V1") != nullptr || K > 400 || (norm && K > 100)) return false;
+    const int v = K <= 100 ? 4 : (K <= 200 ? 2 : 1);
+    const size_t smem = (size_t)K * v * SEG_THREADS * sizeof(float) + 8192;
+    int occ = (int)((size_t)(220 * 1024) / smem);
+    if (occ < 1) occ = 1;
+    const int reg_occ = v == 4 ? 4 : 6;                 // ~100 registers x 128 threads per CTA
+    if (occ > reg_occ) occ = reg_occ;
+    const int ncol = 4 / v;
+    int64_t chunks = (int64_t)NUM_SMS * occ / ncol;
+    const int64_t by_rows = (n_rows + 4 * SEG2_KBLK - 1) / (4 * SEG2_KBLK);      // at least 512 rows per chunk
+    if (chunks > by_rows) chunks = by_rows;
+    if (chunks < 1) chunks = 1;
+    int64_t rpc = (n_rows + chunks - 1) / chunks;
+    rpc = (rpc + SEG2_KBLK - 1) / SEG2_KBLK * SEG2_KBLK;
+    if (rpc < SEG2_KBLK) rpc = SEG2_KBLK;
+    chunks = n_rows > 0 ? (n_rows + rpc - 1) / rpc : 1;
+    *vec = v; *n_chunks = (int)chunks; *rows_per_cta = rpc;
+    return true;
+}
+
+template <typename T, int VEC, int U, bool NORM>
+static int seg2_launch(const void* x, const int64_t* labels, const int64_t* states, int64_t n_rows, int64_t class_base,
+                       int num_classes, int num_states, int K, int n_chunks, int64_t rows_per_cta, float* part_sums,
+                       long long* part_counts, cudaStream_t st) {
+    const size_t smem = (size_t)K * VEC * SEG_THREADS * sizeof(float) + (size_t)K * sizeof(int) + 2 * SEG2_KBLK * sizeof(int) +
+                        2 * 4 * U * sizeof(float);
+    auto kern = segsum2_partial_kernel<T, VEC, U, NORM>;
+    TEAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_chunks * (4 / VEC), SEG_THREADS, smem, st>>>(reinterpret_cast<const T*>(x), labels, states, n_rows, rows_per_cta,
+                                                          class_base, num_classes, num_states, K, part_sums, part_counts);
+    count_launch();
+    TEAM_LAUNCH_CHECK("segsum2_partial_kernel");
+    return TEAM_OK;
+}
+
 template <typename T, bool NORM, bool DEEP>
 static int seg_launch(const void* x, const int64_t* labels, const int64_t* states, int64_t n_rows,
                       int64_t class_base, int num_classes, int num_states, int K, int n_clusters,
@@ -311,6 +485,8 @@ extern "C" size_t team_segsum_workspace_bytes(int64_t n_rows, int64_t num_keys) 
     int64_t rpc;
     if (num_keys < 1) num_keys = 1;
     seg_plan(n_rows, num_keys, &ncl, &nsl, &sk, &rpc);
+    int vec, chunks;
+    if (seg2_plan(n_rows, num_keys, false, &vec, &chunks, &rpc) && chunks > ncl) ncl = chunks;      // partial records of either generation
     return align_up((size_t)ncl * num_keys * D * sizeof(float), 256) + align_up((size_t)ncl * num_keys * sizeof(long long), 256);
 }
 
@@ -334,6 +510,27 @@ extern "C" int team_segsum(const void* x, int x_dtype, const int64_t* labels, co
     }
     cudaStream_t st = (cudaStream_t)stream;
     float* part_sums = reinterpret_cast<float*>(workspace);
+    int vec2 = 0, chunks2 = 0;
+    int64_t rpc2 = 0;
+    if (seg2_plan(n_rows, K, normalize_rows != 0, &vec2, &chunks2, &rpc2)) {       // column-partitioned pass 1 (K <= 400)
+        long long* pc = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + align_up((size_t)chunks2 * K * D * sizeof(float), 256));
+        TEAM_REQUIRE(align_up((size_t)chunks2 * K * D * sizeof(float), 256) + (size_t)chunks2 * K * sizeof(long long) <= workspace_bytes, "team_segsum: workspace too small");
+        int rc2;
+#define SEG2_GO(T, VEC, U, NORM) seg2_launch<T, VEC, U, NORM>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, chunks2, rpc2, part_sums, pc, st)
+        if (x_dtype == TEAM_DTYPE_F32) {
+            rc2 = vec2 == 4 ? (normalize_rows ? SEG2_GO(float, 4, 8, true) : SEG2_GO(float, 4, 8, false))
+                            : (vec2 == 2 ? SEG2_GO(float, 2, 16, false) : SEG2_GO(float, 1, 16, false));
+        } else {
+            rc2 = vec2 == 4 ? (normalize_rows ? SEG2_GO(__nv_bfloat16, 4, 8, true) : SEG2_GO(__nv_bfloat16, 4, 8, false))
+                            : (vec2 == 2 ? SEG2_GO(__nv_bfloat16, 2, 16, false) : SEG2_GO(__nv_bfloat16, 1, 16, false));
+        }
+#undef SEG2_GO
+        if (rc2 != TEAM_OK) return rc2;
+        segsum_final_kernel<<<K, 512, 0, st>>>(part_sums, pc, chunks2, K, sums, counts);
+        count_launch();
+        TEAM_LAUNCH_CHECK("segsum_final_kernel");
+        return TEAM_OK;
+    }
     long long* part_counts = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) +
                                                           align_up((size_t)ncl * K * D * sizeof(float), 256));
     int rc;

@@ -239,3 +239,28 @@ class FusedAdamW:
                                              (C.c_int64 * n)(*[self.params[i].numel() for i in chunk]), float(self.lr),
                                              float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                              float(self.weight_decay), t, _stream_ptr()), "team_adamw_step")
+
+    @torch.no_grad()
+    def step_graph(self, grads):
+        """The same update in a form a CUDA graph can replay every step: the step count lives on the device
+        (``self.step_dev``; every tensor must receive a gradient at every step).  ``lr`` is baked into the captured
+        launch - re-capture when the schedule changes it (once per epoch for the learner's cosine schedule)."""
+        import ctypes as C
+        if any(g is None for g in grads) or len(grads) != len(self.params):
+            raise ValueError("step_graph needs one gradient per parameter")
+        if not hasattr(self, "step_dev"):
+            self.step_dev = torch.zeros((1,), dtype=torch.int64, device=self.params[0].device)
+        L = capi.lib()
+        idx = list(range(len(self.params)))
+        for lo in range(0, len(idx), 48):
+            chunk = idx[lo:lo + 48]
+            n = len(chunk)
+            vp = C.c_void_p * n
+            capi.check(L.team_adamw_step_graph(n, vp(*[self.params[i].data_ptr() for i in chunk]), vp(*[grads[i].data_ptr() for i in chunk]),
+                                               vp(*[self.exp_avg[i].data_ptr() for i in chunk]),
+                                               vp(*[self.exp_avg_sq[i].data_ptr() for i in chunk]),
+                                               (C.c_int64 * n)(*[self.params[i].numel() for i in chunk]), float(self.lr),
+                                               float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                               float(self.weight_decay), self.step_dev.data_ptr(),
+                                               1 if lo + 48 >= len(idx) else 0, _stream_ptr()), "team_adamw_step_graph")
+
