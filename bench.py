@@ -542,6 +542,83 @@ def run_team(a):
         except Exception as exc:
             train_step = {"error": str(exc)[:300]}
 
+    # ---- BASELINE configs[1]: SimpleCIL prototype build (keyed segmented sum) + cosine classifier at 4 M rows (8.6 GB of
+    # fp32 features, far beyond L2) against the measured HBM copy peak; N = 1.  Algorithmic bytes per row: 512 e + 8 (label)
+    # [+ 8 (state)] for the build, 512 e + 4 C + 8 for logits + argmax.
+    proto_build = None
+    if world == 1 and not a.no_scale:
+        try:
+            from team_b200 import ops
+            Np = 4 * 1024 * 1024
+            gdev = torch.Generator(device=dev).manual_seed(0)
+            proto_build = {"rows": Np, "hbm_peak_gbs": pk["hbm"], "peak_source": pk["src"], "timing": "CUDA events, 5 launches after a warm-up launch"}
+            for name, dt, e in (("fp32", torch.float32, 4), ("bf16", torch.bfloat16, 2)):
+                xr = torch.randn((Np, 512), generator=gdev, device=dev, dtype=torch.float32).to(dt)
+                yr = torch.randint(0, 20, (Np,), generator=gdev, device=dev)
+                sr = torch.randint(0, 10, (Np,), generator=gdev, device=dev)
+                Wr = torch.randn((20, 512), generator=gdev, device=dev)
+
+                def timed(fn, iters=5):
+                    fn(); torch.cuda.synchronize()
+                    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    q0.record()
+                    for _ in range(iters):
+                        fn()
+                    q1.record(); torch.cuda.synchronize()
+                    return q0.elapsed_time(q1) / iters
+
+                for key, fn, by in ((f"segsum_class_{name}", lambda: ops.keyed_sums(xr, yr, num_classes=20), 512 * e + 8),
+                                    (f"segsum_class_state_{name}", lambda: ops.keyed_sums(xr, yr, sr, num_classes=20), 512 * e + 16),
+                                    (f"cosine_logits_argmax_{name}", lambda: ops.cosine_logits(xr, Wr, want_argmax=True), 512 * e + 88)):
+                    msq = timed(fn)
+                    proto_build[key] = {"ms": msq, "rows_per_s": Np / msq * 1e3, "gbs": Np * by / msq / 1e6,
+                                        "frac_of_hbm_peak": Np * by / msq / 1e6 / pk["hbm"], "bytes_per_row": by}
+                del xr
+                torch.cuda.empty_cache()
+        except Exception as exc:
+            proto_build = {"error": str(exc)[:300]}
+            torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[3] graph path: evolve_and_update (graph build on the host + temporal GCN + pairwise state
+    # distances), evolve_state_prototypes (second GCN pass + prototype sync) and the state-distance EMA, wall clock with a
+    # device sync per call (the learner calls them once per epoch, models/proof.py:463-513); native size (20 classes,
+    # 46 nodes; the reference takes 1.24 s per evolve_and_update call on 8 host threads) and scaled graphs.
+    graph_path = None
+    if world == 1 and not a.no_scale:
+        try:
+            from team_b200 import graph
+            gp = {k: v.to(dev) for k, v in synth.make_params(2, seed=77).items()}
+            graph_path = []
+            for ncls in (20, 200, 2000):       # 46 / 466 / 4 666 nodes (the pairwise state distances are O(nodes^2): 57 s at 46 666)
+                bs = synth.make_state_prototype_dict(ncls, seed=9)
+                bs = {c: {s_: v.to(dev) for s_, v in sd.items()} for c, sd in bs.items()}
+                protos_g = torch.zeros(ncls, 512, device=dev)
+                nodes = sum(len(sd) for sd in bs.values())
+                f = graph.prior_distance_factors(device=dev)
+
+                def wall(fn, iters):
+                    fn(); torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(iters):
+                        fn()
+                    torch.cuda.synchronize()
+                    return (time.perf_counter() - t0) / iters * 1e3
+
+                iters = 10 if ncls <= 200 else 2
+                res_box = {}
+
+                def ev():
+                    res_box["r"] = graph.evolve_and_update(gp, bs, {})
+                ms_ev = wall(ev, iters)
+                ms_sync = wall(lambda: graph.evolve_state_prototypes(gp, protos_g, bs, {}), iters)
+                ms_ema = wall(lambda: graph.update_state_distance_matrix(f, res_box["r"]["distances"]), iters)
+                c0 = L.team_launch_count(); ev(); nl_ev = L.team_launch_count() - c0
+                graph_path.append({"classes": ncls, "nodes": nodes, "evolve_and_update_ms": ms_ev, "evolve_state_prototypes_ms": ms_sync,
+                                   "update_state_distance_matrix_ms": ms_ema, "library_launches_evolve_and_update": int(nl_ev)})
+                del bs
+        except Exception as exc:
+            graph_path = {"error": str(exc)[:300]}
+
     cb = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb, _, _ = time_cpu(T, B, 3, 1, budget_s=25.0)
@@ -553,7 +630,7 @@ def run_team(a):
                 "config": workload_config(T, B, world),
                 "run": {"grad_exchange": comm, "cuda_graphs": graphs is not None,
                         "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2"},
-                "roofline": roof, "at_scale": at_scale, "train_step": train_step, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
+                "roofline": roof, "at_scale": at_scale, "train_step": train_step, "proto_build": proto_build, "graph": graph_path, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_per_step) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
         print(json.dumps(line), flush=True)

@@ -202,25 +202,25 @@ template <> struct VecLoad<__nv_bfloat16, 4> { static __device__ __forceinline__
 template <> struct VecLoad<__nv_bfloat16, 2> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[2]) { const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p)); v[0] = bf16_lo(u); v[1] = bf16_hi(u); } };
 template <> struct VecLoad<__nv_bfloat16, 1> { static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); } };
 
-template <typename T, int VEC, int U, bool NORM>
-__global__ void __launch_bounds__(SEG_THREADS)
+template <typename T, int VEC, int U, bool NORM, int NT>
+__global__ void __launch_bounds__(NT)
 segsum2_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labels, const int64_t* __restrict__ states,
                        int64_t n_rows, int64_t rows_per_cta, int64_t class_base, int num_classes, int num_states, int K,
                        float* __restrict__ part_sums, long long* __restrict__ part_counts) {
-    static_assert(!NORM || VEC == 4, "row normalisation needs the whole row in one CTA");
+    static_assert(NT >= SEG2_KBLK && (!NORM || (VEC == 4 && NT == 128)), "row normalisation needs the whole row in one CTA");
     static_assert(SEG2_KBLK % (2 * U) == 0, "key block must hold whole group pairs");
     extern __shared__ __align__(16) unsigned char seg_smem[];
-    constexpr int W = SEG_THREADS * VEC;                        // columns of this CTA
+    constexpr int W = NT * VEC;                        // columns of this CTA
     constexpr int NCOL = D / W;
     float* acc = reinterpret_cast<float*>(seg_smem);            // [K][W]
     int* cnt = reinterpret_cast<int*>(acc + (size_t)K * W);     // [K]
     int* keys = cnt + K;                                        // [2][SEG2_KBLK]
-    float* red = reinterpret_cast<float*>(keys + 2 * SEG2_KBLK);    // [2][4][U] (NORM)
+    float* red = reinterpret_cast<float*>(keys + 2 * SEG2_KBLK);    // [2][NT / 32][U] (NORM)
     const int t = threadIdx.x;
     const int cs = blockIdx.x % NCOL;
     const int64_t chunk = blockIdx.x / NCOL;
-    for (int i = t; i < K * W; i += SEG_THREADS) acc[i] = 0.f;
-    for (int i = t; i < K; i += SEG_THREADS) cnt[i] = 0;
+    for (int i = t; i < K * W; i += NT) acc[i] = 0.f;
+    for (int i = t; i < K; i += NT) cnt[i] = 0;
     const int64_t r0 = chunk * rows_per_cta;
     const int64_t r1 = min(n_rows, r0 + rows_per_cta);
     const T* xc = x + (size_t)cs * W + (size_t)t * VEC;         // this thread's columns of row 0
@@ -268,33 +268,71 @@ segsum2_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labe
             }
             nbuf ^= 1;
         }
+        // Four rows at a time.  The read-modify-write of a row depends on the previous one only when the keys collide, but
+        // the compiler has to assume they always do: one serial shared-memory round trip per row (~180 cycles measured)
+        // bounded the row rate of the whole CTA - every warp has to walk every row of the chunk.  With four DISTINCT valid
+        // keys (a CTA-uniform test) the four updates are independent and issue back to back; otherwise in row order.
+        auto rmw = [&](int k, const float (&x)[VEC]) {
+            float* a = acc + (size_t)k * W + t * VEC;
+            if (VEC == 4) {
+                float4 o = *reinterpret_cast<float4*>(a);
+                o.x += x[0]; o.y += x[1 % VEC]; o.z += x[2 % VEC]; o.w += x[3 % VEC];
+                *reinterpret_cast<float4*>(a) = o;
+            } else if (VEC == 2) {
+                float2 o = *reinterpret_cast<float2*>(a);
+                o.x += x[0]; o.y += x[1 % VEC];
+                *reinterpret_cast<float2*>(a) = o;
+            } else {
+                a[0] += x[0];
+            }
+        };
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int k = kb[u];
-            if (k >= 0) {
-                float* a = acc + (size_t)k * W + t * VEC;
+        for (int u = 0; u < U; u += 4) {
+            const int k0 = kb[u], k1 = kb[u + 1], k2 = kb[u + 2], k3 = kb[u + 3];
+            const bool indep = (k0 | k1 | k2 | k3) >= 0 && k0 != k1 && k0 != k2 && k0 != k3 && k1 != k2 && k1 != k3 && k2 != k3;
+            if (indep) {
+                float* a0 = acc + (size_t)k0 * W + t * VEC; float* a1 = acc + (size_t)k1 * W + t * VEC;
+                float* a2 = acc + (size_t)k2 * W + t * VEC; float* a3 = acc + (size_t)k3 * W + t * VEC;
                 if (VEC == 4) {
-                    float4 o = *reinterpret_cast<float4*>(a);
-                    o.x += v[u][0]; o.y += v[u][1 % VEC]; o.z += v[u][2 % VEC]; o.w += v[u][3 % VEC];
-                    *reinterpret_cast<float4*>(a) = o;
+                    float4 o0 = *reinterpret_cast<float4*>(a0), o1 = *reinterpret_cast<float4*>(a1);
+                    float4 o2 = *reinterpret_cast<float4*>(a2), o3 = *reinterpret_cast<float4*>(a3);
+                    o0.x += v[u][0]; o0.y += v[u][1 % VEC]; o0.z += v[u][2 % VEC]; o0.w += v[u][3 % VEC];
+                    o1.x += v[u + 1][0]; o1.y += v[u + 1][1 % VEC]; o1.z += v[u + 1][2 % VEC]; o1.w += v[u + 1][3 % VEC];
+                    o2.x += v[u + 2][0]; o2.y += v[u + 2][1 % VEC]; o2.z += v[u + 2][2 % VEC]; o2.w += v[u + 2][3 % VEC];
+                    o3.x += v[u + 3][0]; o3.y += v[u + 3][1 % VEC]; o3.z += v[u + 3][2 % VEC]; o3.w += v[u + 3][3 % VEC];
+                    *reinterpret_cast<float4*>(a0) = o0; *reinterpret_cast<float4*>(a1) = o1;
+                    *reinterpret_cast<float4*>(a2) = o2; *reinterpret_cast<float4*>(a3) = o3;
                 } else if (VEC == 2) {
-                    float2 o = *reinterpret_cast<float2*>(a);
-                    o.x += v[u][0]; o.y += v[u][1 % VEC];
-                    *reinterpret_cast<float2*>(a) = o;
+                    float2 o0 = *reinterpret_cast<float2*>(a0), o1 = *reinterpret_cast<float2*>(a1);
+                    float2 o2 = *reinterpret_cast<float2*>(a2), o3 = *reinterpret_cast<float2*>(a3);
+                    o0.x += v[u][0]; o0.y += v[u][1 % VEC]; o1.x += v[u + 1][0]; o1.y += v[u + 1][1 % VEC];
+                    o2.x += v[u + 2][0]; o2.y += v[u + 2][1 % VEC]; o3.x += v[u + 3][0]; o3.y += v[u + 3][1 % VEC];
+                    *reinterpret_cast<float2*>(a0) = o0; *reinterpret_cast<float2*>(a1) = o1;
+                    *reinterpret_cast<float2*>(a2) = o2; *reinterpret_cast<float2*>(a3) = o3;
                 } else {
-                    a[0] += v[u][0];
+                    const float o0 = a0[0] + v[u][0], o1 = a1[0] + v[u + 1][0], o2 = a2[0] + v[u + 2][0], o3 = a3[0] + v[u + 3][0];
+                    a0[0] = o0; a1[0] = o1; a2[0] = o2; a3[0] = o3;
                 }
-                if (t == 0 && cs == 0) cnt[k] += 1;
+                if (t == 0 && cs == 0) { cnt[k0] += 1; cnt[k1] += 1; cnt[k2] += 1; cnt[k3] += 1; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = kb[u + e];
+                    if (k >= 0) {
+                        rmw(k, v[u + e]);
+                        if (t == 0 && cs == 0) cnt[k] += 1;
+                    }
+                }
             }
         }
     };
     float va[U][VEC], vb[U][VEC];
-    keys[t] = key_of(r0 + t);                    // SEG_THREADS == SEG2_KBLK: thread t computes the key of row t of a block
+    if (t < SEG2_KBLK) keys[t] = key_of(r0 + t);  // thread t < 128 computes the key of row t of a block
     load_group(r0, va);
     __syncthreads();
     int cur = 0;
     for (int64_t blk = r0; blk < r1; blk += SEG2_KBLK) {
-        const int knext = key_of(blk + SEG2_KBLK + t);           // next block's keys: in flight under this block
+        const int knext = t < SEG2_KBLK ? key_of(blk + SEG2_KBLK + t) : -1;      // next block's keys: in flight under this block
         const int* kb = keys + cur * SEG2_KBLK;
 #pragma unroll 1
         for (int g = 0; g < SEG2_KBLK; g += 2 * U) {
@@ -304,18 +342,18 @@ segsum2_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labe
             load_group(r + 2 * U, va);
             add_group(kb + g + U, vb);
         }
-        keys[(cur ^ 1) * SEG2_KBLK + t] = knext;
+        if (t < SEG2_KBLK) keys[(cur ^ 1) * SEG2_KBLK + t] = knext;
         __syncthreads();
         cur ^= 1;
     }
     // per-CTA partial: [chunk][K][512], this CTA's columns
     float* out = part_sums + ((size_t)chunk * K) * D + (size_t)cs * W;
-    for (int i = t; i < K * (W / VEC); i += SEG_THREADS) {
+    for (int i = t; i < K * (W / VEC); i += NT) {
         const int k = i / (W / VEC), c = (i - k * (W / VEC)) * VEC;
 #pragma unroll
         for (int q = 0; q < VEC; ++q) out[(size_t)k * D + c + q] = acc[(size_t)k * W + c + q];
     }
-    if (cs == 0) for (int i = t; i < K; i += SEG_THREADS) part_counts[(size_t)chunk * K + i] = cnt[i];
+    if (cs == 0) for (int i = t; i < K; i += NT) part_counts[(size_t)chunk * K + i] = cnt[i];
 }
 
 // pass 2: fixed-order sum over clusters.  grid = K, 512 threads = 128 float4 columns x 4 lanes
@@ -412,16 +450,16 @@ static void seg_plan(int64_t n_rows, int64_t K, int* n_clusters, int* n_slabs, i
     *rows_per_cta = rpc;
 }
 
-// second generation: VEC floats per thread, n_chunks row chunks; returns false when the first generation must run
-static bool seg2_plan(int64_t n_rows, int64_t K, bool norm, int* vec, int* n_chunks, int64_t* rows_per_cta) {
+// second generation: columns per CTA (128 x 4 floats for K <= 100, 256 x 1 for K <= 200, 128 x 1 for K <= 400), n_chunks row
+// chunks; returns false when the first generation must run
+static bool seg2_plan(int64_t n_rows, int64_t K, bool norm, int* width, int* n_chunks, int64_t* rows_per_cta) {
     if (getenv("TEAM_SEGSUM_V1") != nullptr || K > 400 || (norm && K > 100)) return false;
-    const int v = K <= 100 ? 4 : (K <= 200 ? 2 : 1);
-    const size_t smem = (size_t)K * v * SEG_THREADS * sizeof(float) + 8192;
+    const int w = K <= 100 ? 512 : (K <= 200 ? 256 : 128);
+    const size_t smem = (size_t)K * w * sizeof(float) + 8192;
     int occ = (int)((size_t)(220 * 1024) / smem);
     if (occ < 1) occ = 1;
-    const int reg_occ = v == 4 ? 4 : 6;                 // ~100 registers x 128 threads per CTA
-    if (occ > reg_occ) occ = reg_occ;
-    const int ncol = 4 / v;
+    if (occ > 4) occ = 4;                                // ~100 registers x 128 threads per CTA
+    const int ncol = 512 / w;
     int64_t chunks = (int64_t)NUM_SMS * occ / ncol;
     const int64_t by_rows = (n_rows + 4 * SEG2_KBLK - 1) / (4 * SEG2_KBLK);      // at least 512 rows per chunk
     if (chunks > by_rows) chunks = by_rows;
@@ -430,20 +468,20 @@ static bool seg2_plan(int64_t n_rows, int64_t K, bool norm, int* vec, int* n_chu
     rpc = (rpc + SEG2_KBLK - 1) / SEG2_KBLK * SEG2_KBLK;
     if (rpc < SEG2_KBLK) rpc = SEG2_KBLK;
     chunks = n_rows > 0 ? (n_rows + rpc - 1) / rpc : 1;
-    *vec = v; *n_chunks = (int)chunks; *rows_per_cta = rpc;
+    *width = w; *n_chunks = (int)chunks; *rows_per_cta = rpc;
     return true;
 }
 
-template <typename T, int VEC, int U, bool NORM>
+template <typename T, int VEC, int U, bool NORM, int NT>
 static int seg2_launch(const void* x, const int64_t* labels, const int64_t* states, int64_t n_rows, int64_t class_base,
                        int num_classes, int num_states, int K, int n_chunks, int64_t rows_per_cta, float* part_sums,
                        long long* part_counts, cudaStream_t st) {
-    const size_t smem = (size_t)K * VEC * SEG_THREADS * sizeof(float) + (size_t)K * sizeof(int) + 2 * SEG2_KBLK * sizeof(int) +
-                        2 * 4 * U * sizeof(float);
-    auto kern = segsum2_partial_kernel<T, VEC, U, NORM>;
+    const size_t smem = (size_t)K * VEC * NT * sizeof(float) + (size_t)K * sizeof(int) + 2 * SEG2_KBLK * sizeof(int) +
+                        2 * (NT / 32) * U * sizeof(float);
+    auto kern = segsum2_partial_kernel<T, VEC, U, NORM, NT>;
     TEAM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_chunks * (4 / VEC), SEG_THREADS, smem, st>>>(reinterpret_cast<const T*>(x), labels, states, n_rows, rows_per_cta,
-                                                          class_base, num_classes, num_states, K, part_sums, part_counts);
+    kern<<<n_chunks * (D / (VEC * NT)), NT, smem, st>>>(reinterpret_cast<const T*>(x), labels, states, n_rows, rows_per_cta,
+                                                        class_base, num_classes, num_states, K, part_sums, part_counts);
     count_launch();
     TEAM_LAUNCH_CHECK("segsum2_partial_kernel");
     return TEAM_OK;
@@ -516,13 +554,13 @@ extern "C" int team_segsum(const void* x, int x_dtype, const int64_t* labels, co
         long long* pc = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + align_up((size_t)chunks2 * K * D * sizeof(float), 256));
         TEAM_REQUIRE(align_up((size_t)chunks2 * K * D * sizeof(float), 256) + (size_t)chunks2 * K * sizeof(long long) <= workspace_bytes, "team_segsum: workspace too small");
         int rc2;
-#define SEG2_GO(T, VEC, U, NORM) seg2_launch<T, VEC, U, NORM>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, chunks2, rpc2, part_sums, pc, st)
+#define SEG2_GO(T, VEC, U, NORM, NT) seg2_launch<T, VEC, U, NORM, NT>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, chunks2, rpc2, part_sums, pc, st)
         if (x_dtype == TEAM_DTYPE_F32) {
-            rc2 = vec2 == 4 ? (normalize_rows ? SEG2_GO(float, 4, 8, true) : SEG2_GO(float, 4, 8, false))
-                            : (vec2 == 2 ? SEG2_GO(float, 2, 16, false) : SEG2_GO(float, 1, 16, false));
+            rc2 = vec2 == 512 ? (normalize_rows ? SEG2_GO(float, 4, 8, true, 128) : SEG2_GO(float, 4, 8, false, 128))
+                              : (vec2 == 256 ? SEG2_GO(float, 1, 32, false, 256) : SEG2_GO(float, 1, 32, false, 128));
         } else {
-            rc2 = vec2 == 4 ? (normalize_rows ? SEG2_GO(__nv_bfloat16, 4, 8, true) : SEG2_GO(__nv_bfloat16, 4, 8, false))
-                            : (vec2 == 2 ? SEG2_GO(__nv_bfloat16, 2, 16, false) : SEG2_GO(__nv_bfloat16, 1, 16, false));
+            rc2 = vec2 == 512 ? (normalize_rows ? SEG2_GO(__nv_bfloat16, 4, 8, true, 128) : SEG2_GO(__nv_bfloat16, 4, 8, false, 128))
+                              : (vec2 == 256 ? SEG2_GO(__nv_bfloat16, 1, 32, false, 256) : SEG2_GO(__nv_bfloat16, 1, 32, false, 128));
         }
 #undef SEG2_GO
         if (rc2 != TEAM_OK) return rc2;
