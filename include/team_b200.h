@@ -199,6 +199,13 @@ int team_head_encode(const team_head_weights* w, int mode, int which, const void
 int team_head_encode_bwd(const team_head_weights* w, int mode, int which, const float* x, int64_t n_rows,
                          int normalize, const float* g_out, float* g_w, float* g_b,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* The same for which = 0 | 1 | 2 (2 = state: x = the gathered embedding rows E[state_ids], fp32) with the optional
+ * gradient w.r.t. the input rows g_x[n_rows,512] = dz Wsum (NULL = not needed): autograd of encode_state
+ * (utils/inc_net.py:518-526; the caller folds g_x by state id into the embedding table, models/state_evolution.py:45-47)
+ * and of encode_prototpyes (:417-422) in the differentiable PROOF / class-text forms. */
+int team_head_encode_rows_bwd(const team_head_weights* w, int mode, int which, const float* x, int64_t n_rows,
+                              int normalize, const float* g_out, float* g_w, float* g_b, float* g_x,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* PROOF fusion forward.
  * Replaces: Proof_Net.forward                     utils/inc_net.py:436-463
@@ -223,6 +230,33 @@ int team_head_tri_classtext_fwd(const team_head_weights* w, int mode, int64_t ba
                                 const float* text_feat, int64_t num_text, const int64_t* state_ids,
                                 float* out_image, float* out_text, float* out_state, float* out_proto,
                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ standalone MultiHeadAttention
+ * Replaces: MultiHeadAttention.forward (+ ScaledDotProductAttention)   convs/projections.py:64-87, :31-38
+ *           (n_head = 1, d_model = d_k = d_v = 512; eval mode / dropout p = 0) and its autograd backward.
+ * out[B,Lq,512] = LayerNorm(fc(softmax(Q K^T / sqrt(512)) V) + q_in), Q = q_in Wq^T, K = k_in Wk^T, V = v_in Wv^T.
+ * q_in [B,Lq,512], k_in / v_in [B,Lk,512] fp32 row-major; weights as nn.Linear stores them ([out,in]).
+ * The forward saves what the backward needs in `workspace` (team_mha_workspace_bytes), which must be handed to
+ * the matching team_mha_bwd unchanged.  The dense projections run on the mode's GEMM engine (tcgen05 in
+ * TEAM_MODE_BF16), the per-sample attention core in fp32.  team_mha_bwd: g_q_in / g_k_in / g_v_in may be NULL; when
+ * q_in, k_in, v_in are one tensor (self-attention) the caller adds the three input gradients.
+ * Used by the differentiable PROOF fusion (utils/inc_net.py:436-492) and the class-text form of forward_tri_modal
+ * (:544-547, :573-576); the learner's per-batch path runs the factorised kernels of team_head_tri_fwd instead. */
+size_t team_mha_workspace_bytes(int64_t batch, int64_t len_q, int64_t len_k);
+int team_mha_fwd(int mode, int64_t batch, int64_t len_q, int64_t len_k, const float* q_in, const float* k_in,
+                 const float* v_in, const float* w_q, const float* w_k, const float* w_v, const float* w_fc,
+                 const float* b_fc, const float* ln_g, const float* ln_b, float* out, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int team_mha_bwd(int mode, int64_t batch, int64_t len_q, int64_t len_k, const float* q_in, const float* k_in,
+                 const float* v_in, const float* w_q, const float* w_k, const float* w_v, const float* w_fc,
+                 const float* ln_g, const float* g_out, float* g_q_in, float* g_k_in, float* g_v_in,
+                 float* g_w_q, float* g_w_k, float* g_w_v, float* g_w_fc, float* g_b_fc, float* g_ln_g,
+                 float* g_ln_b, void* workspace, size_t workspace_bytes, void* stream);
+/* torch.mean over the middle dimension of x[outer][red][inner] -> out[outer][inner] (serial fixed-order sums: the batch
+ * means of Proof_Net.forward, utils/inc_net.py:458-459, and the row means of forward_tri_modal, :573-576) and its
+ * backward dx[o][r][i] = g[o][i] / red. */
+int team_mean_mid(const float* x, float* out, int64_t outer, int64_t red, int64_t inner, void* stream);
+int team_mean_mid_bwd(const float* g, float* dx, int64_t outer, int64_t red, int64_t inner, void* stream);
 
 /* ------------------------------------------------------------------ losses of the training step (SURVEY 8f "next")
  * Replaces: unicl_loss                                     models/proof.py:21-191, called at :434-441

@@ -21,6 +21,10 @@ CASES: Dict[str, dict] = {
     "head_T10_B4": {"kind": "head", "T": 10, "B": 4, "seed": 45, "step": 3},
     # Proof_Net.forward (PROOF fusion)
     "proof_T2_B5": {"kind": "proof_forward", "T": 2, "B": 5, "seed": 46, "step": 4},
+    # Proof_Net.forward WITH autograd (cotangents on image / text / proto outputs, gradients of every trainable parameter)
+    "proof_T2_B5_grad": {"kind": "proof_grad", "T": 2, "B": 5, "seed": 49, "step": 5},
+    # MultiHeadAttention.forward(q, k, v) standalone (cross-attention shapes), outputs + input / parameter gradients
+    "mha_cross": {"kind": "mha", "B": 3, "Lq": 5, "Lk": 7, "seed": 50},
     # CosineLinear
     "cosine_linear": {"kind": "cosine_linear", "N": 96, "num_classes": 20, "seed": 3000, "sigma": 1.0},
     # cal_prototype / replace_fc
@@ -54,7 +58,13 @@ def grad_subsample(g: torch.Tensor) -> torch.Tensor:
 
 def case_inputs(case: dict) -> dict:
     kind = case["kind"]
-    if kind in ("head", "proof_forward"):
+    if kind == "mha":
+        g = torch.Generator(device="cpu").manual_seed(case["seed"])
+        B, Lq, Lk = case["B"], case["Lq"], case["Lk"]
+        return {"params": synth.make_params(1, seed=case["seed"]),
+                "q": torch.randn((B, Lq, 512), generator=g), "k": torch.randn((B, Lk, 512), generator=g),
+                "v": torch.randn((B, Lk, 512), generator=g), "cot": torch.randn((B, Lq, 512), generator=g)}
+    if kind in ("head", "proof_forward", "proof_grad"):
         T, B = case["T"], case["B"]
         C = synth.CLASSES_PER_TASK * T
         return {"params": synth.make_params(T, seed=case["seed"]),

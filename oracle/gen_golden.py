@@ -68,6 +68,46 @@ def gen_proof_forward(case):
     return {"image": _np(img), "text": _np(txt), "proto": _np(pr), "logit_scale_exp": _np(ls)}
 
 
+def gen_proof_grad(case):
+    """Proof_Net.forward with autograd: cotangents = the first C rows of the synthetic cotangent set."""
+    ci = case_inputs(case)
+    net = ref_loader.build_reference_net(ci["params"], ci["protos"])
+    b = ci["batch"]
+    img, txt, ls, pr = net.forward(b["image"], b["text_cls"])
+    C = ci["C"]
+    cots = [ci["cots"][0], ci["cots"][2][:txt.shape[0]], ci["cots"][3][:C]]
+    names = O.trainable_names(ci["params"])
+    sd = dict(net.named_parameters())
+    grads = torch.autograd.grad([img, txt, pr], [sd[n] for n in names], grad_outputs=cots, allow_unused=True)
+    res = {"image": _np(img), "text": _np(txt), "proto": _np(pr)}
+    for n, g in zip(names, grads):
+        res["grad:" + n] = _np(grad_subsample(g))
+    return res
+
+
+def gen_mha(case):
+    """The reference MultiHeadAttention module itself (convs/projections.py:41-87), eval mode, q != k != v."""
+    ref_loader.install_stubs()
+    from convs.projections import MultiHeadAttention
+    ci = case_inputs(case)
+    m = MultiHeadAttention(1, 512, 512, 512, dropout=0.1)
+    p = ci["params"]
+    with torch.no_grad():
+        m.w_qs.weight.copy_(p["sel_attn.w_qs.weight"]); m.w_ks.weight.copy_(p["sel_attn.w_ks.weight"])
+        m.w_vs.weight.copy_(p["sel_attn.w_vs.weight"]); m.fc.weight.copy_(p["sel_attn.fc.weight"])
+        m.fc.bias.copy_(p["sel_attn.fc.bias"]); m.layer_norm.weight.copy_(p["sel_attn.layer_norm.weight"])
+        m.layer_norm.bias.copy_(p["sel_attn.layer_norm.bias"])
+    m.eval()
+    q, k, v = (ci[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+    out = m(q, k, v)
+    par = [m.w_qs.weight, m.w_ks.weight, m.w_vs.weight, m.fc.weight, m.fc.bias, m.layer_norm.weight, m.layer_norm.bias]
+    grads = torch.autograd.grad(out, [q, k, v] + par, grad_outputs=ci["cot"])
+    res = {"out": _np(out)}
+    for n, g in zip(("q", "k", "v", "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b"), grads):
+        res["grad:" + n] = _np(grad_subsample(g))
+    return res
+
+
 def gen_cosine_linear(case):
     ref_loader.install_stubs()
     from convs.linears import CosineLinear
@@ -252,7 +292,7 @@ def gen_learner(case):
         return learner_harness.run(torch.device("cpu"), swap=False, tasks=case["tasks"], epochs=case["epochs"], seed=case["seed"])
 
 
-GENERATORS = {"head": gen_head, "learner": gen_learner, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward,
+GENERATORS = {"head": gen_head, "learner": gen_learner, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward, "proof_grad": gen_proof_grad, "mha": gen_mha,
               "cosine_linear": gen_cosine_linear, "cal_prototype": gen_cal_prototype,
               "simplecil": gen_simplecil, "evolve": gen_evolve,
               "state_distance_forward": gen_state_distance_forward,

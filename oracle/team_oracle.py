@@ -85,20 +85,25 @@ def context_prompts(p: Params) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- a6
-def sel_attn(x: torch.Tensor, p: Params) -> torch.Tensor:
-    """MultiHeadAttention(n_head=1).forward(x,x,x) in eval mode:
+def mha(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, p: Params) -> torch.Tensor:
+    """MultiHeadAttention(n_head=1).forward(q, k, v) in eval mode:
     convs/projections.py:64-87 with ScaledDotProductAttention :31-38
     (temperature sqrt(512) :57; the discarded log_softmax :34 is omitted)."""
-    d = x.shape[-1]
-    q = F.linear(x, p["sel_attn.w_qs.weight"])
-    k = F.linear(x, p["sel_attn.w_ks.weight"])
-    v = F.linear(x, p["sel_attn.w_vs.weight"])
+    d = q_in.shape[-1]
+    q = F.linear(q_in, p["sel_attn.w_qs.weight"])
+    k = F.linear(k_in, p["sel_attn.w_ks.weight"])
+    v = F.linear(v_in, p["sel_attn.w_vs.weight"])
     attn = torch.bmm(q, k.transpose(1, 2)) / float(d ** 0.5)
     attn = torch.softmax(attn, dim=2)
     out = torch.bmm(attn, v)
     out = F.linear(out, p["sel_attn.fc.weight"], p["sel_attn.fc.bias"])
-    return F.layer_norm(out + x, (d,), p["sel_attn.layer_norm.weight"],
+    return F.layer_norm(out + q_in, (d,), p["sel_attn.layer_norm.weight"],
                         p["sel_attn.layer_norm.bias"], LN_EPS)
+
+
+def sel_attn(x: torch.Tensor, p: Params) -> torch.Tensor:
+    """sel_attn(features, features, features) as Proof_Net calls it (utils/inc_net.py:453, :559)."""
+    return mha(x, x, x, p)
 
 
 # --------------------------------------------------------------------------- a7

@@ -156,6 +156,18 @@ def _declare(lib):
         lib.team_head_tri_classtext_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]
         lib.team_head_proof_fwd.restype = i32
         lib.team_head_proof_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, i32, vp, vp, vp, vp, sz, vp]
+        lib.team_head_encode_rows_bwd.restype = i32
+        lib.team_head_encode_rows_bwd.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, vp, vp, vp, sz, vp]
+        lib.team_mha_workspace_bytes.restype = sz
+        lib.team_mha_workspace_bytes.argtypes = [i64, i64, i64]
+        lib.team_mha_fwd.restype = i32
+        lib.team_mha_fwd.argtypes = [i32, i64, i64, i64] + [vp] * 11 + [vp, sz, vp]
+        lib.team_mha_bwd.restype = i32
+        lib.team_mha_bwd.argtypes = [i32, i64, i64, i64] + [vp] * 19 + [vp, sz, vp]
+        lib.team_mean_mid.restype = i32
+        lib.team_mean_mid.argtypes = [vp, vp, i64, i64, i64, vp]
+        lib.team_mean_mid_bwd.restype = i32
+        lib.team_mean_mid_bwd.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.team_head_encode_bwd.restype = i32
         lib.team_head_encode_bwd.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, vp, vp, sz, vp]
 

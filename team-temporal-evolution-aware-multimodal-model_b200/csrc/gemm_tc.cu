@@ -72,6 +72,7 @@ struct TcGroup {
     int stages;
     int cluster;                 // CTAs per cluster (1, 2, 4 or 8) = largest split count of the group
     unsigned long long* dbg;     // optional [cta][16] globaltimer stamps (tools/gemm_probe.py), else null
+    int diag;                    // TEAM_GEMM_DIAG (timing experiments only, results invalid): 1 = no global stores, 2 = no k-loop
 };
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -196,7 +197,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     const int nkb0 = P.s[0].nkb;
     const int nkb = nkb0 + P.s[1].nkb;
     const int kb_begin = split * P.kb_per_split;
-    const int kb_end = min(nkb, kb_begin + P.kb_per_split);
+    const int kb_end = (g.diag & 2) ? kb_begin : min(nkb, kb_begin + P.kb_per_split);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -323,8 +324,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     if (threadIdx.x == 64) TC_STAMP(9);
     {
         const int M = P.M, N = P.N;
-        float* const C = P.C;
-        __nv_bfloat16* const Cb = P.Cb;
+        float* const C = (g.diag & 1) ? nullptr : P.C;
+        __nv_bfloat16* const Cb = (g.diag & 1) ? nullptr : P.Cb;
         const long long ldc = P.ldc, ldcb = P.ldcb;
         const bool vec_ok = (N % 4 == 0) && (C == nullptr || ((ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0))) &&
                             (Cb == nullptr || ((ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(Cb) & 7) == 0)));
@@ -1157,6 +1158,7 @@ int gemm_bf16_group(cudaStream_t st, const TcGemm* ops, int n, void* ws, size_t 
         grp.cluster = cluster;
         grp.stages = cta <= NUM_SMS ? TC_MAX_STAGES : TC_STAGES;
         grp.dbg = g_dbg != nullptr ? g_dbg + (size_t)(g_dbg_launch++ % 32) * 1024 * 16 : nullptr;
+        { const char* dg = getenv("TEAM_GEMM_DIAG"); grp.diag = dg != nullptr ? atoi(dg) : 0; }
         if ((rc = tc_launch(st, grp, cta, flops, bytes))) return rc;
     }
     return TEAM_OK;

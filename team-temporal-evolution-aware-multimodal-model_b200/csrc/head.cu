@@ -889,8 +889,18 @@ extern "C" int team_head_encode(const team_head_weights* hw, int mode, int which
 extern "C" int team_head_encode_bwd(const team_head_weights* hw, int mode, int which, const float* x, int64_t n_rows,
                                     int normalize, const float* g_out, float* g_w, float* g_b, void* workspace,
                                     size_t workspace_bytes, void* stream) {
+    TEAM_REQUIRE(which == 0 || which == 1, "head encode bwd: which must be 0 (image) or 1 (text)");
+    return team_head_encode_rows_bwd(hw, mode, which, x, n_rows, normalize, g_out, g_w, g_b, nullptr, workspace, workspace_bytes, stream);
+}
+
+// The same with the state modality (which = 2: x = the gathered embedding rows E[state_ids], fp32) and an optional
+// gradient w.r.t. the input rows g_x = dz Wsum (state embedding table: the caller sums g_x by state id; prototype rows
+// pushed through projs_img: which = 0, g_x unused).
+extern "C" int team_head_encode_rows_bwd(const team_head_weights* hw, int mode, int which, const float* x, int64_t n_rows,
+                                         int normalize, const float* g_out, float* g_w, float* g_b, float* g_x,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
     HeadCtx cx;
-    TEAM_REQUIRE((which == 0 || which == 1) && x != nullptr && g_out != nullptr && g_w != nullptr && g_b != nullptr && n_rows >= 1,
+    TEAM_REQUIRE(which >= 0 && which <= 2 && x != nullptr && g_out != nullptr && g_w != nullptr && g_b != nullptr && n_rows >= 1,
                  "head encode bwd: bad args");
     int rc = setup(cx, hw, mode, n_rows, 0, workspace, workspace_bytes, stream);
     if (rc) return rc;
@@ -926,6 +936,7 @@ extern "C" int team_head_encode_bwd(const team_head_weights* hw, int mode, int w
     const int nblk = (int)((n_rows + rpb - 1) / rpb);
     TEAM_LAUNCH(nrm_bwd_kernel, nblk, 256, 0, cx.st, nl);
     seg(wv.add(D, D, 0.f, fonly(g_w, D)), true, sub(w.dXo, 0, 0), true, w.img, n_rows);
+    if (g_x != nullptr) seg(wv.add(n_rows, D, 0.f, fonly(g_x, D)), false, sub(w.dXo, 0, 0), true, w.Wsum[which], D);
     RUN(wv);
     FinishArgs fa;
     memset(&fa, 0, sizeof(fa));

@@ -21,10 +21,10 @@ def _stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _check_state_ids(sid: torch.Tensor) -> torch.Tensor:
+def _check_state_ids(sid: torch.Tensor, num_states: int = capi.NUM_STATES) -> torch.Tensor:
     """nn.Embedding(10, 512) raises on an id outside [0, 10) (models/state_evolution.py:16, :45-47); the kernels
     would clamp it silently.  Device-side assert, no host synchronisation."""
-    torch._assert_async(((sid >= 0) & (sid < capi.NUM_STATES)).all(), "state id outside [0, 10)")
+    torch._assert_async(((sid >= 0) & (sid < num_states)).all(), "state id outside [0, num_states)")
     return sid
 
 
@@ -252,8 +252,10 @@ def forward_tri_modal_class_text(pack: HeadParamPack, image: torch.Tensor, text:
 
 
 class _EncodeFn(torch.autograd.Function):
-    """encode_image / encode_text with autograd to the projections (the ClipLoss branch of the training
-    step, models/proof.py:428-431).  No gradient flows into the (frozen-backbone) features."""
+    """encode_image / encode_text / encode_state / encode_prototpyes with autograd to the projections (and, for the
+    state modality, to the embedding table): the ClipLoss branch of the training step (models/proof.py:428-431) and the
+    differentiable PROOF / class-text forms.  idx: 0 image (also prototype rows, which go through projs_img), 1 text,
+    2 state (x = int64 state ids).  No gradient flows into the (frozen-backbone) features."""
 
     @staticmethod
     def forward(ctx, x, idx, normalize, mode, T, ppt, *params):
@@ -261,9 +263,12 @@ class _EncodeFn(torch.autograd.Function):
         if not x.is_cuda:
             raise capi.TeamB200Error("encode needs CUDA tensors (no CPU fallback)")
         dev = x.device
-        x = _f32c(x, dev)
         flat = [_f32c(p, dev) for p in params]
         hw = _fill_weights(T, ppt, flat, torch.zeros((1, capi.D), device=dev))
+        if idx == 2:
+            x = _check_state_ids(x.detach().to(device=dev, dtype=torch.int64).contiguous())
+        else:
+            x = _f32c(x, dev)
         n = x.shape[0]
         L = capi.lib()
         nbytes = L.team_head_workspace_bytes(max(n, 1), 1, T * ppt, 0, mode)
@@ -285,11 +290,23 @@ class _EncodeFn(torch.autograd.Function):
         gb = torch.empty((capi.D,), dtype=torch.float32, device=dev)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         g = _f32c(g_out, dev)
-        capi.check(capi.lib().team_head_encode_bwd(C.byref(hw), mode, idx, x.data_ptr(), n, normalize, g.data_ptr(),
-                                                   gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()),
-                   "team_head_encode_bwd")
         need = ctx.needs_input_grad[6:]
         out: List[Optional[torch.Tensor]] = [None] * len(need)
+        if idx == 2:
+            # rows = E[state_ids] (a gather: data movement); dE = the input-row gradients summed by state id
+            # (the library's deterministic keyed sum)
+            from . import ops
+            rows = flat[7 * T].index_select(0, x).contiguous()
+            gx = torch.empty((n, capi.D), dtype=torch.float32, device=dev) if need[7 * T] else None
+            capi.check(capi.lib().team_head_encode_rows_bwd(C.byref(hw), mode, 2, rows.data_ptr(), n, normalize, g.data_ptr(),
+                                                            gw.data_ptr(), gb.data_ptr(), gx.data_ptr() if gx is not None else None,
+                                                            ws.data_ptr(), nbytes, _stream_ptr()), "team_head_encode_rows_bwd")
+            if gx is not None:
+                out[7 * T] = ops.keyed_sums(gx, x, num_classes=capi.NUM_STATES)[0]
+        else:
+            capi.check(capi.lib().team_head_encode_bwd(C.byref(hw), mode, idx, x.data_ptr(), n, normalize, g.data_ptr(),
+                                                       gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()),
+                       "team_head_encode_bwd")
         for t in range(T):                       # W = sum_t W_t  =>  dW_t = dW for every unfrozen t
             if need[2 * idx * T + t]:
                 out[2 * idx * T + t] = gw
@@ -299,11 +316,116 @@ class _EncodeFn(torch.autograd.Function):
 
 
 def encode_grad(pack: HeadParamPack, which: str, x: torch.Tensor, normalize: bool = False, mode: int = MODE_F32):
-    """Differentiable encode_image / encode_text (utils/inc_net.py:401-415)."""
-    idx = {"image": 0, "text": 1}[which]
+    """Differentiable encode_image / encode_text / encode_state / encode_prototpyes (utils/inc_net.py:401-422, :518-526;
+    ``which='prototypes'``: ``x`` = img_prototypes, pushed through projs_img)."""
+    idx = {"image": 0, "text": 1, "state": 2, "prototypes": 0}[which]
     if x.shape[0] == 0:
         return torch.empty((0, capi.D), dtype=torch.float32, device=x.device)
     return _EncodeFn.apply(x, idx, normalize, mode, pack.T, pack.ppt, *pack.flat)
+
+
+class _MhaFn(torch.autograd.Function):
+    """MultiHeadAttention.forward (convs/projections.py:64-87) on arbitrary [B, L, 512] tokens: team_mha_fwd / team_mha_bwd."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, mode, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b):
+        capi.require_device()
+        if not q.is_cuda:
+            raise capi.TeamB200Error("sel_attn needs CUDA tensors (no CPU fallback)")
+        dev = q.device
+        same = (k is q, v is q)
+        q = _f32c(q, dev)
+        k = q if same[0] else _f32c(k, dev)
+        v = q if same[1] else _f32c(v, dev)
+        if q.dim() != 3 or k.dim() != 3 or q.shape[2] != capi.D or k.shape[2] != capi.D or k.shape != v.shape or k.shape[0] != q.shape[0]:
+            raise ValueError("sel_attn: q [B,Lq,512], k / v [B,Lk,512]")
+        B, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+        par = [_f32c(p, dev) for p in (w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b)]
+        L = capi.lib()
+        nbytes = L.team_mha_workspace_bytes(B, Lq, Lk)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        out = torch.empty((B, Lq, capi.D), dtype=torch.float32, device=dev)
+        capi.check(L.team_mha_fwd(mode, B, Lq, Lk, q.data_ptr(), k.data_ptr(), v.data_ptr(), *[p.data_ptr() for p in par],
+                                  out.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()), "team_mha_fwd")
+        ctx.hold = (q, k, v, par, ws)
+        ctx.meta = (mode, B, Lq, Lk, nbytes)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        q, k, v, par, ws = ctx.hold
+        mode, B, Lq, Lk, nbytes = ctx.meta
+        dev = q.device
+        g = _f32c(g_out, dev)
+        need = ctx.needs_input_grad
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        gq = mk(B, Lq, capi.D) if need[0] else None
+        gk = mk(B, Lk, capi.D) if need[1] else None
+        gv = mk(B, Lk, capi.D) if need[2] else None
+        gw = [mk(capi.D, capi.D) for _ in range(4)] + [mk(capi.D) for _ in range(3)]
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b = par
+        capi.check(capi.lib().team_mha_bwd(mode, B, Lq, Lk, q.data_ptr(), k.data_ptr(), v.data_ptr(), w_q.data_ptr(), w_k.data_ptr(),
+                                           w_v.data_ptr(), w_fc.data_ptr(), ln_g.data_ptr(), g.data_ptr(), ptr(gq), ptr(gk), ptr(gv),
+                                           *[t.data_ptr() for t in gw], ws.data_ptr(), nbytes, _stream_ptr()), "team_mha_bwd")
+        return (gq, gk, gv, None) + tuple(t if need[4 + i] else None for i, t in enumerate(gw))
+
+
+def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b, mode: int = MODE_F32):
+    """Standalone ``sel_attn(q, k, v)`` (convs/projections.py:64-87; eval mode / dropout p = 0), differentiable."""
+    return _MhaFn.apply(q, k, v, mode, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b)
+
+
+class _MeanFn(torch.autograd.Function):
+    """torch.mean(x, dim) for the batch / row means of the PROOF and class-text forms (utils/inc_net.py:458-459, :573-576)."""
+
+    @staticmethod
+    def forward(ctx, x, dim):
+        capi.require_device()
+        x = _f32c(x, x.device)
+        dim = dim % x.dim()
+        outer = int(torch.tensor(x.shape[:dim]).prod()) if dim > 0 else 1
+        red = x.shape[dim]
+        inner = int(torch.tensor(x.shape[dim + 1:]).prod()) if dim + 1 < x.dim() else 1
+        out = torch.empty(x.shape[:dim] + x.shape[dim + 1:], dtype=torch.float32, device=x.device)
+        capi.check(capi.lib().team_mean_mid(x.data_ptr(), out.data_ptr(), outer, red, inner, _stream_ptr()), "team_mean_mid")
+        ctx.meta = (tuple(x.shape), outer, red, inner)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, outer, red, inner = ctx.meta
+        g = _f32c(g, g.device)
+        dx = torch.empty(shape, dtype=torch.float32, device=g.device)
+        capi.check(capi.lib().team_mean_mid_bwd(g.data_ptr(), dx.data_ptr(), outer, red, inner, _stream_ptr()), "team_mean_mid_bwd")
+        return dx, None
+
+
+def mean_dim(x: torch.Tensor, dim: int) -> torch.Tensor:
+    return _MeanFn.apply(x, dim)
+
+
+class _EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding lookup of InsectLifecycleModel.get_state_embeddings (models/state_evolution.py:45-47): the forward is
+    a row gather, the backward the library's deterministic keyed sum of the row gradients by state id."""
+
+    @staticmethod
+    def forward(ctx, weight, ids):
+        ids = _check_state_ids(ids.detach().to(device=weight.device, dtype=torch.int64).contiguous().reshape(-1), weight.shape[0])
+        ctx.hold = (ids,)
+        ctx.meta = (weight.shape[0],)
+        return weight.detach().index_select(0, ids)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        (ids,) = ctx.hold
+        return ops.keyed_sums(_f32c(g, g.device), ids, num_classes=ctx.meta[0])[0], None
+
+
+def embedding(weight: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    shape = tuple(ids.shape)
+    return _EmbeddingFn.apply(weight, ids).reshape(shape + (weight.shape[1],))
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:

@@ -72,8 +72,14 @@ class MultiHeadAttention(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, q, k, v):
-        raise NotImplementedError("sel_attn is evaluated inside Proof_Net.forward_tri_modal by the fused "
-                                  "kernels (team_head_tri_fwd); it has no standalone CUDA entry point")
+        """Standalone call on arbitrary [B, L, 512] tokens (convs/projections.py:64-87): ``team_mha_fwd`` / ``team_mha_bwd``,
+        differentiable.  Inside ``Proof_Net.forward_tri_modal`` the learner's path runs the factorised kernels instead.
+        Dropout is not implemented: p must be 0 in train mode (see ``Proof_Net._check_dropout``)."""
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("team_b200 evaluates sel_attn without dropout: set dropout.p = 0.0 or call .eval() "
+                                      "(INTEGRATION.md, 'Dropout')")
+        return head.mha(q, k, v, self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight, self.fc.bias,
+                        self.layer_norm.weight, self.layer_norm.bias, mode=getattr(self, "team_mode", head.MODE_F32))
 
 
 class TemporalGCNBlock(nn.Module):
@@ -118,8 +124,9 @@ class InsectLifecycleModel(nn.Module):
                                                 nn.ReLU(), nn.Linear(hidden_dim, 3), nn.Softmax(dim=1))
 
     def get_state_embeddings(self, state_ids):
-        raise NotImplementedError("the embedding lookup is fused into Proof_Net.encode_state / forward_tri_modal "
-                                  "(10-row table projected once per step, then gathered)")
+        """models/state_evolution.py:45-47 on its own (differentiable).  Inside ``Proof_Net.encode_state`` /
+        ``forward_tri_modal`` the lookup is fused: the 10-row table is projected once per step, then gathered."""
+        return head.embedding(self.state_embeddings.weight, state_ids)
 
     def _detect_evolution_type(self, class_id, state_ids):
         t = graph.detect_evolution_type(list(state_ids))
@@ -288,10 +295,13 @@ class Proof_Net(nn.Module):
         return head.encode_grad(self._pack(), "text", feats, normalize=normalize, mode=self.team_mode)
 
     def encode_state(self, state_ids, normalize: bool = False):
-        return head.encode(self._pack(), "state", state_ids.to(self._device), normalize=normalize, mode=self.team_mode)
+        return head.encode_grad(self._pack(), "state", state_ids.to(self._device), normalize=normalize, mode=self.team_mode)
 
     def encode_prototpyes(self, normalize: bool = False):        # (sic) utils/inc_net.py:417
-        return head.encode(self._pack(), "prototypes", None, self._protos(), normalize=normalize, mode=self.team_mode)
+        return head.encode_grad(self._pack(), "prototypes", self._protos(), normalize=normalize, mode=self.team_mode)
+
+    def _wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def forward_tri_modal(self, image, text, state_ids):
         """(image [B,512], text [B,1,512], state [B,512], proto [B,512], exp(logit_scale)); per-sample text
@@ -302,13 +312,49 @@ class Proof_Net(nn.Module):
             text = self.tokenizer(text)
             text = text.to(self._device) if torch.is_tensor(text) else text
         txt = self.convnet.encode_text(text)
-        if txt.shape[0] != img.shape[0]:          # class texts shared by all samples: text output = mean over them (forward only)
+        if txt.shape[0] != img.shape[0]:          # class texts shared by all samples: text output = mean over them
+            if self._wants_grad():
+                return self._tri_modal_class_text_grad(img, txt, state_ids.to(self._device))
             with torch.no_grad():
                 o = head.forward_tri_modal_class_text(self._pack(), img, txt, state_ids.to(self._device), self._protos(),
                                                       mode=self.team_mode)
             return o[0], o[1], o[2], o[3], self.convnet.logit_scale.exp()
         o = head.forward_tri_modal(self._pack(), img, txt, state_ids.to(self._device), self._protos(), mode=self.team_mode)
         return o[0], o[1], o[2], o[3], self.convnet.logit_scale.exp()
+
+    def _tri_modal_class_text_grad(self, img, txt, state_ids):
+        """Differentiable class-text form (utils/inc_net.py:544-547, :573-576): tokens = [image | Tn class texts | state |
+        C prototypes | P prompts]; the fused forward-only kernel (team_head_tri_classtext_fwd) serves the no-grad case."""
+        pack = self._pack()
+        xi = head.encode_grad(pack, "image", img, normalize=True, mode=self.team_mode)
+        xt = head.encode_grad(pack, "text", txt, normalize=True, mode=self.team_mode)
+        xs = head.encode_grad(pack, "state", state_ids, normalize=True, mode=self.team_mode)
+        xp = head.encode_grad(pack, "prototypes", self._protos(), normalize=True, mode=self.team_mode)
+        B, Tn, Cn = xi.shape[0], xt.shape[0], xp.shape[0]
+        toks = torch.cat([xi.view(B, 1, FEATURE_DIM), xt.view(1, Tn, FEATURE_DIM).expand(B, Tn, FEATURE_DIM),
+                          xs.view(B, 1, FEATURE_DIM), xp.view(1, Cn, FEATURE_DIM).expand(B, Cn, FEATURE_DIM),
+                          self.get_context_prompts().view(1, -1, FEATURE_DIM).expand(B, -1, FEATURE_DIM)], dim=1).contiguous()
+        self.sel_attn.team_mode = self.team_mode
+        f = self.sel_attn(toks, toks, toks)
+        o_txt = f[:, 1:1 + Tn]
+        o_pro = f[:, 2 + Tn:2 + Tn + Cn]
+        o_txt = head.mean_dim(o_txt.contiguous(), 1) if Tn > 1 else o_txt
+        o_pro = head.mean_dim(o_pro.contiguous(), 1) if Cn > 1 else o_pro
+        return f[:, 0], o_txt, f[:, 1 + Tn], o_pro, self.convnet.logit_scale.exp()
+
+    def _proof_grad(self, xi, xt):
+        """Differentiable PROOF fusion (utils/inc_net.py:447-462) on encoded rows: tokens = [image | Tn texts | C prototypes |
+        P prompts], text / prototype outputs = means over the batch."""
+        xp = self.encode_prototpyes(normalize=True)
+        B, Tn, Cn = xi.shape[0], xt.shape[0], xp.shape[0]
+        toks = torch.cat([xi.view(B, 1, FEATURE_DIM), xt.view(1, Tn, FEATURE_DIM).expand(B, Tn, FEATURE_DIM),
+                          xp.view(1, Cn, FEATURE_DIM).expand(B, Cn, FEATURE_DIM),
+                          self.get_context_prompts().view(1, -1, FEATURE_DIM).expand(B, -1, FEATURE_DIM)], dim=1).contiguous()
+        self.sel_attn.team_mode = self.team_mode
+        f = self.sel_attn(toks, toks, toks)
+        o_txt = head.mean_dim(f[:, 1:1 + Tn].contiguous(), 0)
+        o_pro = head.mean_dim(f[:, 1 + Tn:1 + Tn + Cn].contiguous(), 0)
+        return f[:, 0], o_txt, self.convnet.logit_scale.exp(), o_pro
 
     def forward_for_classification(self, image, text_cls):
         """Learner.forward_for_classification (models/proof.py:519-536): cosine logits of the projected image
@@ -325,11 +371,17 @@ class Proof_Net(nn.Module):
 
     def forward(self, image, text):
         """PROOF fusion (utils/inc_net.py:436-463): (image [B,512], text [Tn,512] batch mean, exp(logit_scale),
-        proto [C,512] batch mean).  Forward only - the TEAM learner never trains through this path."""
+        proto [C,512] batch mean).  Without autograd: one fused forward (team_head_proof_fwd); with autograd (a trainable
+        parameter under enable_grad): the same function through the differentiable encode + standalone attention ops."""
+        self._check_dropout()
         img = self.convnet.encode_image(image.to(self._device))
         if isinstance(text, list):
             text = self.tokenizer(text)
         txt = self.convnet.encode_text(text.to(self._device) if torch.is_tensor(text) else text)
+        if self._wants_grad():
+            pack = self._pack()
+            return self._proof_grad(head.encode_grad(pack, "image", img, normalize=True, mode=self.team_mode),
+                                    head.encode_grad(pack, "text", txt, normalize=True, mode=self.team_mode))
         with torch.no_grad():
             o = head.forward_proof(self._pack(), img, txt, self._protos(), mode=self.team_mode)
         return o[0], o[1], self.convnet.logit_scale.exp(), o[2]
@@ -339,6 +391,9 @@ class Proof_Net(nn.Module):
         encode_text with normalize=True); transformer=False returns the inputs and the encoded prototypes."""
         if not transformer:
             return image_features, text_features, self.convnet.logit_scale.exp(), self.encode_prototpyes(normalize=True)
+        self._check_dropout()
+        if self._wants_grad():
+            return self._proof_grad(image_features.to(self._device), text_features.to(self._device))
         with torch.no_grad():
             o = head.forward_proof(self._pack(), image_features.to(self._device), text_features.to(self._device),
                                    self._protos(), inputs_encoded=True, mode=self.team_mode)

@@ -64,6 +64,42 @@ def test_proof_forward(golden):
         assert rel_err(o, g[key]) < 2e-6, key
 
 
+def test_proof_forward_grads(golden):
+    """Proof_Net.forward with autograd (real reference): outputs and the gradient of every trainable parameter."""
+    from oracle.cases import grad_subsample
+    case, g = CASES["proof_T2_B5_grad"], golden("proof_T2_B5_grad")
+    ci = case_inputs(case)
+    b = ci["batch"]
+    p = {k: v.clone().requires_grad_(v.dim() > 0) for k, v in ci["params"].items()}
+    img, txt, ls, pr = O.forward_proof(p, b["image"], b["text_cls"], ci["protos"])
+    cots = [ci["cots"][0], ci["cots"][2][:txt.shape[0]], ci["cots"][3][:ci["C"]]]
+    names = O.trainable_names(ci["params"])
+    grads = torch.autograd.grad([img, txt, pr], [p[n] for n in names], grad_outputs=cots, allow_unused=True)
+    for key, o in (("image", img), ("text", txt), ("proto", pr)):
+        assert rel_err(o, g[key]) < 2e-6, key
+    for n, gr in zip(names, grads):
+        want = g["grad:" + n]
+        if gr is None:
+            assert want.size == 0 or not np.any(want), n
+        else:
+            assert rel_err(grad_subsample(gr), want) < 1e-5, n
+
+
+def test_mha_cross_attention(golden):
+    """The reference MultiHeadAttention module on q != k != v (convs/projections.py:64-87): output, input and parameter grads."""
+    from oracle.cases import grad_subsample
+    case, g = CASES["mha_cross"], golden("mha_cross")
+    ci = case_inputs(case)
+    p = {k: v.clone().requires_grad_(True) for k, v in ci["params"].items() if k.startswith("sel_attn.")}
+    q, k, v = (ci[n].clone().requires_grad_(True) for n in ("q", "k", "v"))
+    out = O.mha(q, k, v, p)
+    assert rel_err(out, g["out"]) < 2e-6
+    par = [p["sel_attn." + n] for n in ("w_qs.weight", "w_ks.weight", "w_vs.weight", "fc.weight", "fc.bias", "layer_norm.weight", "layer_norm.bias")]
+    grads = torch.autograd.grad(out, [q, k, v] + par, grad_outputs=ci["cot"])
+    for n, gr in zip(("q", "k", "v", "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b"), grads):
+        assert rel_err(grad_subsample(gr), g["grad:" + n]) < 1e-5, n
+
+
 def test_cosine_linear(golden):
     case, g = CASES["cosine_linear"], golden("cosine_linear")
     ci = case_inputs(case)
