@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scale", action="store_true", help="skip the larger-batch points (at_scale)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch samples per GPU (headline); strong: --global-batch samples in total, split over the GPUs "
+                         "(BASELINE configs[3]: 4096 over 8 GPUs).  For N > 1 the weak line also carries the strong point "
+                         "(`strong_scaling`) and an untimed check of the gradient exchange (`grad_exchange_check`).")
+    ap.add_argument("--global-batch", type=int, default=4096)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl", "nccl-buckets"],
                     help="N>1 gradient exchange: own NVLink peer-memory kernel inside the step graph (default), one NCCL "
                          "all-reduce after the step, or three NCCL buckets overlapped with the backward")
@@ -254,6 +259,10 @@ def run_team(a):
     L = capi.lib()
     mode = head.MODE_BF16 if a.mode == "bf16" else head.MODE_F32
     T, B = a.tasks, a.batch
+    if a.scaling == "strong":
+        if a.global_batch % world:
+            raise SystemExit(f"--global-batch {a.global_batch} is not a multiple of {world} GPUs")
+        B = a.global_batch // world
     C = synth.CLASSES_PER_TASK * T
     warmup = max(a.warmup, 3)
 
@@ -444,6 +453,84 @@ def run_team(a):
                       "stream (2 slots) -> graph replay of fwd+bwd -> D2H of the predictions; wall clock over all steps "
                       "incl. drain; cotangents device-resident (the loss is the caller's)"}
 
+    # ---- N > 1: (i) untimed check that the in-graph peer exchange leaves the SUM of the per-rank gradients in every
+    # rank's buffer (against an NCCL all-reduce of gradients computed without the exchange); (ii) the strong-scaling
+    # point of BASELINE configs[3]: 4096 samples in total, split over the GPUs, same graph-replayed step.
+    grad_check, strong = None, None
+    if world > 1:
+        try:
+            with torch.cuda.stream(stream):
+                local = head.HeadStepRunner(pack, protos, B, C, mode)
+                local.step(imgs[0], txts[0], sids[0], text_cls, cots[0])
+                want = local.flat_grads.clone()
+                dist.all_reduce(want)
+                mine = local.flat_grads.clone()
+                eager_step(0)                                   # the runner of the timed region (exchange inside the backward)
+                if peer is None:
+                    runner.allreduce_grads()
+                torch.cuda.synchronize()
+                got = runner.flat_grads
+                err = float((got.double() - want.double()).norm() / want.double().norm().clamp_min(1e-30))
+                changed = float((got.double() - mine.double()).norm() / want.double().norm().clamp_min(1e-30))
+                worst = torch.tensor([err], device=dev)
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+                same = got.clone()
+                dist.broadcast(same, 0)
+                ident = torch.tensor([1 if torch.equal(same, got) else 0], device=dev)
+                dist.all_reduce(ident, op=dist.ReduceOp.MIN)
+                grad_check = {"ok": bool(float(worst.item()) <= 1e-5), "max_rel_err_over_ranks": float(worst.item()), "tolerance": 1e-5,
+                              "bit_identical_on_all_ranks": bool(int(ident.item())),
+                              "rel_change_vs_local_gradient": changed,
+                              "what": "flat gradient buffer after one step with the exchange vs NCCL all-reduce(sum) of the per-rank "
+                                      "gradients of the same step computed without it (norm-wise relative, fp32)"}
+                del local
+        except Exception as exc:
+            grad_check = {"ok": False, "error": str(exc)[:300]}
+        try:
+            if a.scaling == "weak" and a.global_batch % world == 0 and a.global_batch // world >= 8:
+                Bs = a.global_batch // world
+                peer_s = parallel.PeerAllReduce(head.HeadStepRunner.grad_numel(pack), dev) if peer is not None else None
+                rs = head.HeadStepRunner(pack, protos, Bs, C, mode, peer=peer_s)
+                nset = min(rot, 32)
+                sets = []
+                for i in range(nset):
+                    bb = synth.make_batch(Bs, C, step=5000 + rank * 1000 + i)
+                    cc = synth.make_cotangents(Bs, step=5000 + rank * 1000 + i)
+                    sets.append((bb["image"].to(dev), bb["text"].to(dev), bb["state"].to(dev),
+                                 [cc[0].to(dev), cc[1].reshape(Bs, 512).to(dev), cc[2].to(dev), cc[3].to(dev)]))
+                with torch.cuda.stream(stream):
+                    rs.step(sets[0][0], sets[0][1], sets[0][2], text_cls, sets[0][3])
+                    torch.cuda.synchronize()
+                    gs = []
+                    for q in sets:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=stream):
+                            rs.step(q[0], q[1], q[2], text_cls, q[3])
+                        gs.append(g)
+
+                    def sstep(i):
+                        gs[i % nset].replay()
+                        if peer_s is None:
+                            rs.allreduce_grads()
+                    for i in range(warmup):
+                        sstep(i)
+                    barrier()
+                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record(stream)
+                    for i in range(a.steps):
+                        sstep(warmup + i)
+                    s1.record(stream)
+                    barrier()
+                    sms = torch.tensor([s0.elapsed_time(s1)], device=dev)
+                    dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+                sms = float(sms.item()) / a.steps
+                strong = {"scaling": "strong", "global_batch": a.global_batch, "batch_per_gpu": Bs, "ms_per_step": sms,
+                          "samples_per_s": a.global_batch / sms * 1e3,
+                          "timing": f"CUDA events, {a.steps} graph replays, max over ranks, {nset} rotating input sets"}
+                del rs, gs, sets
+        except Exception as exc:
+            strong = {"error": str(exc)[:300]}
+
     # ---- the same step at larger per-GPU batches (BASELINE configs[4] sweep), N = 1 only: where the launch-latency
     # floor of the 26-launch chain no longer hides the kernels, i.e. what the kernels themselves sustain
     at_scale = None
@@ -625,12 +712,13 @@ def run_team(a):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": a.mode, "data": "synthetic",
                 "config": workload_config(T, B, world),
                 "run": {"grad_exchange": comm, "cuda_graphs": graphs is not None,
                         "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2"},
                 "roofline": roof, "at_scale": at_scale, "train_step": train_step, "proto_build": proto_build, "graph": graph_path, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
+                "grad_exchange_check": grad_check, "strong_scaling": strong,
                 "gpu_launches": int(launches_per_step) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
         print(json.dumps(line), flush=True)

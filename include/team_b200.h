@@ -231,6 +231,19 @@ int team_head_tri_classtext_fwd(const team_head_weights* w, int mode, int64_t ba
                                 float* out_image, float* out_text, float* out_state, float* out_proto,
                                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ exemplar herding
+ * Replaces: the selection loop of BaseLearner._construct_exemplar   models/base.py:284-311 and the exemplar mean :335-341.
+ * feats [n_rows,512] fp32 = extract_vector outputs, rows grouped by class: group g owns rows [group_ptr[g], group_ptr[g+1])
+ * (group_ptr: n_groups + 1 int64 on the device).  For every group: rows are L2-normalised (v / (||v|| + 1e-8)), the class mean
+ * taken, and m exemplars picked greedily so that the running exemplar mean stays closest to the class mean (first index
+ * on ties).  out_idx [n_groups,m] int64 = picked rows, relative to the group's first row, in pick order (-1 where a group has
+ * fewer than m rows); out_mean [n_groups,512] = normalised mean of the picked normalised rows (the _class_means row);
+ * out_class_mean (optional) [n_groups,512] = mean of all normalised rows.  One CTA per group. */
+size_t team_herding_workspace_bytes(int64_t n_rows);
+int team_herding_select(const float* feats, const int64_t* group_ptr, int32_t n_groups, int32_t m, int64_t n_rows,
+                        int64_t* out_idx, float* out_mean, float* out_class_mean, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ standalone MultiHeadAttention
  * Replaces: MultiHeadAttention.forward (+ ScaledDotProductAttention)   convs/projections.py:64-87, :31-38
  *           (n_head = 1, d_model = d_k = d_v = 512; eval mode / dropout p = 0) and its autograd backward.

@@ -25,6 +25,8 @@ CASES: Dict[str, dict] = {
     "proof_T2_B5_grad": {"kind": "proof_grad", "T": 2, "B": 5, "seed": 49, "step": 5},
     # MultiHeadAttention.forward(q, k, v) standalone (cross-attention shapes), outputs + input / parameter gradients
     "mha_cross": {"kind": "mha", "B": 3, "Lq": 5, "Lk": 7, "seed": 50},
+    # BaseLearner._construct_exemplar (herding) of the real reference: 3 classes x 150 rows, 12 exemplars per class
+    "herding": {"kind": "herding", "n_classes": 3, "n_train": 150, "m": 12, "seed": 4321},
     # CosineLinear
     "cosine_linear": {"kind": "cosine_linear", "N": 96, "num_classes": 20, "seed": 3000, "sigma": 1.0},
     # cal_prototype / replace_fc
@@ -58,6 +60,9 @@ def grad_subsample(g: torch.Tensor) -> torch.Tensor:
 
 def case_inputs(case: dict) -> dict:
     kind = case["kind"]
+    if kind == "herding":
+        from oracle import learner_harness
+        return {"data": learner_harness.FakeData(n_classes=case["n_classes"], n_train=case["n_train"], n_test=2, seed=case["seed"])}
     if kind == "mha":
         g = torch.Generator(device="cpu").manual_seed(case["seed"])
         B, Lq, Lk = case["B"], case["Lq"], case["Lk"]

@@ -108,6 +108,29 @@ def gen_mha(case):
     return res
 
 
+def gen_herding(case):
+    """The real BaseLearner._construct_exemplar (models/base.py:274-343) on the synthetic DataManager (features ARE the
+    vectors: extract_vector = identity): picked rows per class and the exemplar class means."""
+    ref_loader.install_stubs()
+    from oracle import learner_harness
+    import models.base as ref_base
+    from torch.utils.data import DataLoader as _DL
+    ref_base.DataLoader = lambda *a, **k: _DL(*a, **{**k, "num_workers": 0})
+    ci = case_inputs(case)
+    dm = learner_harness.FakeDataManager(ci["data"])
+    nc = case["n_classes"]
+    net = types.SimpleNamespace(eval=lambda: None, extract_vector=lambda x: x)
+    fake = types.SimpleNamespace(_network=net, _device=torch.device("cpu"), _known_classes=0, _total_classes=nc,
+                                 _data_memory=np.array([]), _targets_memory=np.array([]), feature_dim=512,
+                                 _class_means=np.zeros((nc, 512)))
+    fake._extract_vectors = types.MethodType(ref_base.BaseLearner._extract_vectors, fake)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        ref_base.BaseLearner._construct_exemplar(fake, dm, case["m"])
+    mem = np.asarray(fake._data_memory, dtype=np.int64).reshape(nc, case["m"], 2)      # (split, row in the train split)
+    first = np.array([np.where(ci["data"].y["train"] == c)[0][0] for c in range(nc)])
+    return {"picked": mem[:, :, 1] - first[:, None], "class_means": np.asarray(fake._class_means, dtype=np.float64)}
+
+
 def gen_cosine_linear(case):
     ref_loader.install_stubs()
     from convs.linears import CosineLinear
@@ -292,7 +315,7 @@ def gen_learner(case):
         return learner_harness.run(torch.device("cpu"), swap=False, tasks=case["tasks"], epochs=case["epochs"], seed=case["seed"])
 
 
-GENERATORS = {"head": gen_head, "learner": gen_learner, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward, "proof_grad": gen_proof_grad, "mha": gen_mha,
+GENERATORS = {"head": gen_head, "learner": gen_learner, "unicl": gen_unicl, "clip": gen_clip, "proof_forward": gen_proof_forward, "proof_grad": gen_proof_grad, "mha": gen_mha, "herding": gen_herding,
               "cosine_linear": gen_cosine_linear, "cal_prototype": gen_cal_prototype,
               "simplecil": gen_simplecil, "evolve": gen_evolve,
               "state_distance_forward": gen_state_distance_forward,

@@ -132,7 +132,8 @@ def _reseed_by_name(module: nn.Module, seed: int):
             p.copy_((torch.randn(p.shape, generator=g) * std).to(p.device))
 
 
-def run(device: torch.device, swap: bool, tasks: int = 2, epochs: int = 2, seed: int = 7, team_mode: str = "f32"):
+def run(device: torch.device, swap: bool, tasks: int = 2, epochs: int = 2, seed: int = 7, team_mode: str = "f32",
+        swap_herding: bool = False):
     """Returns a dict of numpy arrays: accuracy after every task, prototypes, per-state prototypes, distance factors
     and the trained parameters."""
     ref_loader.install_stubs()
@@ -150,6 +151,10 @@ def run(device: torch.device, swap: bool, tasks: int = 2, epochs: int = 2, seed:
     ref_proof.num_workers = 0
     ref_base.DataLoader = loader0
     orig = (ref_proof.Proof_Net, ref_sd.AdaptiveStateDistanceMatrix)
+    orig_herd = ref_base.BaseLearner._construct_exemplar
+    if swap_herding:                        # third optional line of INTEGRATION.md: exemplar herding on the GPU
+        from team_b200 import exemplars
+        ref_base.BaseLearner._construct_exemplar = exemplars.construct_exemplar
     if swap:                                # the two lines of INTEGRATION.md
         from team_b200 import inc_net as team_net
         ref_proof.Proof_Net = team_net.Proof_Net
@@ -197,4 +202,5 @@ def run(device: torch.device, swap: bool, tasks: int = 2, epochs: int = 2, seed:
                 out["param/" + name] = v[::16] if v.ndim == 2 and v.shape[0] == 512 else v
     finally:
         ref_proof.Proof_Net, ref_sd.AdaptiveStateDistanceMatrix = orig
+        ref_base.BaseLearner._construct_exemplar = orig_herd
     return out

@@ -165,6 +165,33 @@ def forward_proof(p: Params, image, text, img_prototypes):
     return img_o.view(B, -1), txt_o.view(nt, -1), p["convnet.logit_scale"].exp(), pr_o.view(npr, -1)
 
 
+# --------------------------------------------------------------------------- 8f: exemplar herding
+def herding_select(features, m: int):
+    """Selection loop and exemplar mean of BaseLearner._construct_exemplar for ONE class: models/base.py:284-311 (normalise
+    with EPSILON = 1e-8 :12, class mean, greedy argmin with np.delete) and :335-341 (exemplar mean).  ``features`` =
+    extract_vector outputs [n,512] (numpy float32, as tensor2numpy returns them).  Returns (indices into the ORIGINAL rows
+    in pick order, normalised exemplar mean, class mean)."""
+    import numpy as np
+    vectors = np.asarray(features, dtype=np.float32)
+    vectors = (vectors.T / (np.linalg.norm(vectors.T, axis=0) + 1e-8)).T
+    all_vectors = vectors
+    class_mean = np.mean(vectors, axis=0)
+    alive = np.arange(vectors.shape[0])
+    picked, exemplar_vectors = [], []
+    for k in range(1, m + 1):
+        S = np.sum(exemplar_vectors, axis=0)
+        mu_p = (vectors + S) / k
+        i = int(np.argmin(np.sqrt(np.sum((class_mean - mu_p) ** 2, axis=1))))
+        picked.append(int(alive[i]))
+        exemplar_vectors.append(np.array(vectors[i]))
+        vectors = np.delete(vectors, i, axis=0)
+        alive = np.delete(alive, i)
+    sel = all_vectors[picked]
+    mean = np.mean(sel, axis=0)
+    mean = mean / np.linalg.norm(mean)
+    return np.asarray(picked, dtype=np.int64), mean, class_mean
+
+
 # --------------------------------------------------------------------------- 8f: losses of the training step
 def unicl_loss(image_features, text_features, state_features, labels, temperature=0.07, epoch=None, max_epoch=None,
                state_ids=None, evolution_features=None):

@@ -158,6 +158,10 @@ def _declare(lib):
         lib.team_head_proof_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, i64, i32, vp, vp, vp, vp, sz, vp]
         lib.team_head_encode_rows_bwd.restype = i32
         lib.team_head_encode_rows_bwd.argtypes = [C.POINTER(HeadWeights), i32, i32, vp, i64, i32, vp, vp, vp, vp, vp, sz, vp]
+        lib.team_herding_workspace_bytes.restype = sz
+        lib.team_herding_workspace_bytes.argtypes = [i64]
+        lib.team_herding_select.restype = i32
+        lib.team_herding_select.argtypes = [vp, vp, i32, i32, i64, vp, vp, vp, vp, sz, vp]
         lib.team_mha_workspace_bytes.restype = sz
         lib.team_mha_workspace_bytes.argtypes = [i64, i64, i64]
         lib.team_mha_fwd.restype = i32

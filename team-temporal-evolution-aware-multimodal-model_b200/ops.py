@@ -5,8 +5,9 @@ torch is used only for device memory and the current stream; all arithmetic happ
 ``libteam_b200.so``.  Inputs must be CUDA tensors - there is no CPU fallback."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import capi
@@ -107,6 +108,33 @@ def cosine_logits(x: torch.Tensor, weight: torch.Tensor, sigma: Optional[torch.T
     if want_logits and want_argmax:
         return logits, amax
     return logits if want_logits else amax
+
+
+def herding_select(features: torch.Tensor, m: int, group_sizes: Optional[Sequence[int]] = None):
+    """Exemplar herding of ``BaseLearner._construct_exemplar`` (models/base.py:284-311, :335-341) for one class
+    (``features`` [n,512]) or several (rows grouped by class, ``group_sizes`` = rows per class).  Returns
+    (picked row indices within each class [G,m] int64 in pick order, exemplar means [G,512], class means [G,512]);
+    G = 1 for a single class.  Every class needs at least ``m`` rows (the reference raises on fewer)."""
+    capi.require_device()
+    _chk_rows(features, "features")
+    if features.dtype != torch.float32:
+        raise TypeError("herding_select: fp32 features")
+    n = features.shape[0]
+    sizes = [n] if group_sizes is None else [int(v) for v in group_sizes]
+    if sum(sizes) != n or any(v < m for v in sizes) or m < 1:
+        raise ValueError(f"herding_select: every class needs >= m = {m} rows and the sizes must add up to {n} (got {sizes})")
+    dev = features.device
+    ptr = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int64).to(dev)
+    G = len(sizes)
+    L = capi.lib()
+    nbytes = L.team_herding_workspace_bytes(n)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    idx = torch.empty((G, m), dtype=torch.int64, device=dev)
+    emean = torch.empty((G, capi.D), dtype=torch.float32, device=dev)
+    cmean = torch.empty((G, capi.D), dtype=torch.float32, device=dev)
+    capi.check(L.team_herding_select(features.data_ptr(), ptr.data_ptr(), G, m, n, idx.data_ptr(), emean.data_ptr(),
+                                     cmean.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()), "team_herding_select")
+    return idx, emean, cmean
 
 
 def dynamic_temperature(temperature: float = 0.07, epoch=None, max_epoch=None) -> float:

@@ -100,6 +100,17 @@ def test_mha_cross_attention(golden):
         assert rel_err(grad_subsample(gr), g["grad:" + n]) < 1e-5, n
 
 
+def test_herding(golden):
+    """Exemplar herding restatement vs the real BaseLearner._construct_exemplar (models/base.py:274-343): picks exact."""
+    case, g = CASES["herding"], golden("herding")
+    data = case_inputs(case)["data"]
+    for c in range(case["n_classes"]):
+        x = data.x["train"][data.y["train"] == c].numpy()
+        picked, mean, _ = O.herding_select(x, case["m"])
+        assert np.array_equal(picked, g["picked"][c]), c
+        assert rel_err(torch.from_numpy(mean), g["class_means"][c]) < 1e-6
+
+
 def test_cosine_linear(golden):
     case, g = CASES["cosine_linear"], golden("cosine_linear")
     ci = case_inputs(case)
