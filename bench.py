@@ -64,7 +64,7 @@ def ncu_dram_bytes_per_launch(kernel_prefix: str):
     """Average DRAM bytes (read + write) per launch of a kernel from the committed `ncu --set full` summary of this
     workload (profiles/, written by tools/ncu_summary.py); None if the file is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1i_ncu_full_B1024_T10_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r2s_ncu_full_gemm_waves_B1024_T10_summary.csv")
     if not os.path.exists(path):
         return None, None
     rows = list(csv.reader(open(path)))

@@ -69,7 +69,37 @@ table_rows_fwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
         TableRowW mine;
         mine.c_w = mine.a_i = mine.a_t = mine.a_s = 0.f; mine.r = 0;
         if (lane <= d.C) mine = table_row_weights(d, b, lane, srow, SK, TT, mt, Zt);
-        for (int k = 0; k <= d.C; ++k) {
+        // Prototype rows two at a time: a row is one dependent chain (shared-memory loads -> 512-wide sums -> five shuffle
+        // rounds -> rsqrt -> accumulate) and at 1 024 samples a warp owns one sample, so the kernel's time is C + 1 of
+        // those chains back to back; two independent rows in flight overlap their shuffle / load latencies.
+        int k = 0;
+        for (; k + 1 < d.C; k += 2) {
+            const TableRowW rwa = shfl_row_weights(mine, k), rwb = shfl_row_weights(mine, k + 1);
+            float4 ua[4], ta[4], ub[4], tb[4];
+            ld_row(tabN + (size_t)k * D, lane, ua);
+            ld_row(tabS + (size_t)k * D, lane, ta);
+            ld_row(tabN + (size_t)(k + 1) * D, lane, ub);
+            ld_row(tabS + (size_t)(k + 1) * D, lane, tb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ua[i] = fma4s(rwa.c_w, ua[i], fma4s(rwa.a_i, vi[i], fma4s(rwa.a_t, vt[i], fma4s(rwa.a_s, vs[i], ta[i]))));
+                ub[i] = fma4s(rwb.c_w, ub[i], fma4s(rwb.a_i, vi[i], fma4s(rwb.a_t, vt[i], fma4s(rwb.a_s, vs[i], tb[i]))));
+            }
+            float a1 = sum_part(ua), a2 = dot_part(ua, ua), b1 = sum_part(ub), b2 = dot_part(ub, ub);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+            }
+            const float ma = a1 * (1.0f / D), mb = b1 * (1.0f / D);
+            const float ra = 1.0f / sqrtf(fmaxf(a2 * (1.0f / D) - ma * ma, 0.f) + LN_EPS);
+            const float rb = 1.0f / sqrtf(fmaxf(b2 * (1.0f / D) - mb * mb, 0.f) + LN_EPS);
+            shift_row(ua, -ma);
+            axpy_row(acc, ra, ua);                 // same order as one row at a time: bit-identical results
+            shift_row(ub, -mb);
+            axpy_row(acc, rb, ub);
+        }
+        for (; k <= d.C; ++k) {
             const TableRowW rw = shfl_row_weights(mine, k);
             const int tr = k < d.C ? k : d.C + sid;
             float4 u[4], t[4];

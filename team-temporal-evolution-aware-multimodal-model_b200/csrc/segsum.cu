@@ -356,6 +356,235 @@ segsum2_partial_kernel(const T* __restrict__ x, const int64_t* __restrict__ labe
     if (cs == 0) for (int i = t; i < K; i += NT) part_counts[(size_t)chunk * K + i] = cnt[i];
 }
 
+// ------------------------------------------------------------------ third generation of pass 1 (many keys: K > 100)
+// With K = 200 (class x state) keys the accumulators of all keys no longer fit beside each other at full row width:
+// the second generation then gives every thread ONE column (4-byte loads, a shared-memory read-modify-write per 4 bytes)
+// and measured 32 % of the HBM copy peak.  Here the rows are first PARTITIONED by key, which costs a few bytes per row,
+// and then summed straight from HBM into registers - no shared-memory accumulators at all:
+//   A  sg_rank_kernel     per block of 1024 rows: key of every row, its stable rank among the block's rows of that key
+//                         (warp match + per-warp counts), per-block key counts                       reads 16 B / row
+//   B  sg_scan_kernel     per key: exclusive scan of the block counts (a row's position = key start + blocks before +
+//                         rank); sg_table_kernel: key starts and the segment table (runs of <= seg_len rows of one key)
+//   C  sg_scatter_kernel  row index -> its position in the key-sorted order                            8 B / row
+//   D  sg_gather_kernel   one warp per segment: streams its rows (whole 2 KB rows, 4 in flight, 128-bit loads) and adds
+//                         them in index order in registers; one partial row per segment
+//   E  sg_fold_kernel     per key: partials in segment order
+// Everything is a pure function of the input: ranks come from ballots, not from atomics' arrival order - bit-reproducible.
+constexpr int SG_BLK = 1024;           // rows per ranking block (one thread per row)
+constexpr int SG_SEG_MAX = 512;        // rows per gather segment (fewer for small inputs: >= ~32 warps per SM wanted)
+constexpr int SG_GW = 8;               // warps per gather CTA
+
+__device__ __forceinline__ int sg_key(const int64_t* __restrict__ labels, const int64_t* __restrict__ states, int64_t row,
+                                      int64_t n_rows, int64_t class_base, int num_classes, int num_states, int K) {
+    if (row >= n_rows) return -1;
+    const int64_t c = __ldg(labels + row) - class_base;
+    if (c < 0 || c >= num_classes) return K;                       // bucket K = rows that belong to no key
+    if (states == nullptr) return (int)c;
+    const int64_t st = __ldg(states + row);
+    return (st >= 0 && st < num_states) ? (int)(c * num_states + st) : K;
+}
+
+// packed[row] = key << 10 | rank within (block, key);  blk_counts[key][block]
+__global__ void __launch_bounds__(SG_BLK)
+sg_rank_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ states, int64_t n_rows, int64_t class_base,
+               int num_classes, int num_states, int K, int nblk, int* __restrict__ packed, int* __restrict__ blk_counts) {
+    extern __shared__ int sg_cnt[];                                // [32 warps][K + 1]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, K1 = K + 1;
+    for (int i = t; i < 32 * K1; i += SG_BLK) sg_cnt[i] = 0;
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * SG_BLK + t;
+    const int key = sg_key(labels, states, row, n_rows, class_base, num_classes, num_states, K);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int wrank = __popc(peers & ((1u << lane) - 1u));
+    if (key >= 0 && wrank == 0) sg_cnt[warp * K1 + key] = __popc(peers);      // one writer per (warp, key)
+    __syncthreads();
+    for (int k = t; k < K1; k += SG_BLK) {                         // exclusive scan over the warps, per key
+        int run = 0;
+        for (int w = 0; w < 32; ++w) { const int c = sg_cnt[w * K1 + k]; sg_cnt[w * K1 + k] = run; run += c; }
+        blk_counts[(size_t)k * nblk + blockIdx.x] = run;
+    }
+    __syncthreads();
+    if (key >= 0) packed[row] = (key << 10) | (sg_cnt[warp * K1 + key] + wrank);
+}
+
+// one CTA per key: blk_counts[key][:] -> exclusive scan in place, totals[key]
+__global__ void __launch_bounds__(1024)
+sg_scan_kernel(int* __restrict__ blk_counts, int nblk, long long* __restrict__ totals) {
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    int* c = blk_counts + (size_t)blockIdx.x * nblk;
+    const int per = (nblk + 1023) / 1024;
+    const int b0 = t * per, b1 = min(nblk, b0 + per);
+    long long s = 0;
+    for (int b = b0; b < b1; ++b) s += c[b];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        long long run = 0;
+        for (int i = 0; i < 1024; ++i) { const long long v = part[i]; part[i] = run; run += v; }
+        totals[blockIdx.x] = run;
+    }
+    __syncthreads();
+    long long run = part[t];
+    for (int b = b0; b < b1; ++b) { const int v = c[b]; c[b] = (int)run; run += v; }
+}
+
+// key_start[k] (exclusive scan of the totals) and seg_base[k] (segments before key k); single CTA
+__global__ void __launch_bounds__(32)
+sg_table_kernel(const long long* __restrict__ totals, int K, int seg_len, long long* __restrict__ key_start, int* __restrict__ seg_base) {
+    if (threadIdx.x != 0) return;
+    long long run = 0;
+    int segs = 0;
+    for (int k = 0; k <= K; ++k) {
+        key_start[k] = run;
+        seg_base[k] = segs;
+        run += totals[k];
+        if (k < K) segs += (int)((totals[k] + seg_len - 1) / seg_len);
+    }
+    seg_base[K] = segs;            // total number of segments (bucket K is never gathered)
+}
+
+__global__ void __launch_bounds__(256)
+sg_scatter_kernel(const int* __restrict__ packed, const int* __restrict__ blk_excl, const long long* __restrict__ key_start,
+                  int64_t n_rows, int nblk, int* __restrict__ order) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= n_rows) return;
+    const int p = packed[row];
+    const int key = p >> 10, rank = p & 1023;
+    const int blk = (int)(row / SG_BLK);
+    order[key_start[key] + blk_excl[(size_t)key * nblk + blk] + rank] = (int)row;
+}
+
+template <typename T, bool NORM>
+__global__ void __launch_bounds__(SG_GW * 32)
+sg_gather_kernel(const T* __restrict__ x, const int* __restrict__ order, const long long* __restrict__ key_start,
+                 const long long* __restrict__ totals, const int* __restrict__ seg_base, int K, int seg_len, float* __restrict__ partials) {
+    const int lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * SG_GW + (threadIdx.x >> 5);
+    if (seg >= seg_base[K]) return;
+    int lo = 0, hi = K;                                            // last key with seg_base[key] <= seg
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_base[mid] <= seg) lo = mid; else hi = mid; }
+    const int key = lo;
+    const long long first = key_start[key] + (long long)(seg - seg_base[key]) * seg_len;
+    const long long last = min(key_start[key] + totals[key], first + seg_len);
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = 4;
+    for (long long p = first; p < last; p += U) {
+        int r[U];
+        float4 v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = p + u < last ? __ldg(order + p + u) : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[u][j] = r[u] >= 0 ? RowLoad<T>::load(x + (size_t)r[u] * D, lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float inv = 1.f;
+            if (NORM) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ss += v[u][j].x * v[u][j].x + v[u][j].y * v[u][j].y + v[u][j].z * v[u][j].z + v[u][j].w * v[u][j].w;
+                inv = 1.0f / fmaxf(sqrtf(warp_sum(ss)), NORM_EPS);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[j].x = fmaf(v[u][j].x, inv, acc[j].x); acc[j].y = fmaf(v[u][j].y, inv, acc[j].y);
+                acc[j].z = fmaf(v[u][j].z, inv, acc[j].z); acc[j].w = fmaf(v[u][j].w, inv, acc[j].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(partials + (size_t)seg * D)[lane + 32 * j] = acc[j];
+}
+
+__global__ void __launch_bounds__(128)
+sg_fold_kernel(const float* __restrict__ partials, const int* __restrict__ seg_base, const long long* __restrict__ totals,
+               float* __restrict__ sums, int64_t* __restrict__ counts) {
+    const int k = blockIdx.x, c4 = threadIdx.x;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int s0 = seg_base[k], s1 = seg_base[k + 1];
+    int q = s0;
+    for (; q + 4 <= s1; q += 4) {
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = reinterpret_cast<const float4*>(partials + (size_t)(q + u) * D)[c4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s.x += a[u].x; s.y += a[u].y; s.z += a[u].z; s.w += a[u].w; }
+    }
+    for (; q < s1; ++q) {
+        const float4 a = reinterpret_cast<const float4*>(partials + (size_t)q * D)[c4];
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+    reinterpret_cast<float4*>(sums)[(size_t)k * (D / 4) + c4] = s;
+    if (c4 == 0) counts[k] = totals[k];
+}
+
+struct SgPlan {
+    int nblk, seg_len;
+    int64_t max_segs;
+    size_t off_packed, off_order, off_blk, off_totals, off_kstart, off_segbase, off_partials, total;
+};
+static SgPlan sg_plan(int64_t n_rows, int64_t K) {
+    SgPlan p;
+    p.nblk = (int)((n_rows + SG_BLK - 1) / SG_BLK);
+    if (p.nblk < 1) p.nblk = 1;
+    p.seg_len = SG_SEG_MAX;                                        // ~4 700 warp-segments fill the machine (148 SMs x 32 warps)
+    while (p.seg_len > 64 && n_rows / p.seg_len < 4736) p.seg_len >>= 1;
+    p.max_segs = n_rows / p.seg_len + K + 1;
+    size_t off = 0;
+    auto take = [&](size_t b) { const size_t r = off; off += align_up(b, 256); return r; };
+    p.off_packed = take((size_t)p.nblk * SG_BLK * sizeof(int));
+    p.off_order = take((size_t)(n_rows > 0 ? n_rows : 1) * sizeof(int));
+    p.off_blk = take((size_t)(K + 1) * p.nblk * sizeof(int));
+    p.off_totals = take((size_t)(K + 2) * sizeof(long long));
+    p.off_kstart = take((size_t)(K + 2) * sizeof(long long));
+    p.off_segbase = take((size_t)(K + 2) * sizeof(int));
+    p.off_partials = take((size_t)p.max_segs * D * sizeof(float));
+    p.total = off;
+    return p;
+}
+// the sorted path serves many-key problems (K > 100) of any size up to 2^31 rows and K < 2^20
+static bool sg_wanted(int64_t n_rows, int64_t K) {
+    if (getenv("TEAM_SEGSUM_V2") != nullptr || getenv("TEAM_SEGSUM_V1") != nullptr) return false;
+    return K > 100 && K < (1 << 20) && n_rows >= 4096 && n_rows < (1ll << 31) && (size_t)(K + 1) * 32 * sizeof(int) <= 200 * 1024;
+}
+
+template <typename T>
+static int sg_run(const void* x, const int64_t* labels, const int64_t* states, int64_t n_rows, int64_t class_base, int num_classes,
+                  int num_states, int K, bool norm, float* sums, int64_t* counts, void* ws, cudaStream_t st) {
+    const SgPlan p = sg_plan(n_rows, K);
+    char* b = reinterpret_cast<char*>(ws);
+    int* packed = reinterpret_cast<int*>(b + p.off_packed);
+    int* order = reinterpret_cast<int*>(b + p.off_order);
+    int* blk = reinterpret_cast<int*>(b + p.off_blk);
+    long long* totals = reinterpret_cast<long long*>(b + p.off_totals);
+    long long* kstart = reinterpret_cast<long long*>(b + p.off_kstart);
+    int* segbase = reinterpret_cast<int*>(b + p.off_segbase);
+    float* partials = reinterpret_cast<float*>(b + p.off_partials);
+    const size_t smem = (size_t)32 * (K + 1) * sizeof(int);
+    TEAM_CUDA_CHECK(cudaFuncSetAttribute(sg_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sg_rank_kernel<<<p.nblk, SG_BLK, smem, st>>>(labels, states, n_rows, class_base, num_classes, num_states, K, p.nblk, packed, blk);
+    TEAM_LAUNCH_CHECK("sg_rank_kernel");
+    sg_scan_kernel<<<K + 1, 1024, 0, st>>>(blk, p.nblk, totals);
+    TEAM_LAUNCH_CHECK("sg_scan_kernel");
+    sg_table_kernel<<<1, 32, 0, st>>>(totals, K, p.seg_len, kstart, segbase);
+    TEAM_LAUNCH_CHECK("sg_table_kernel");
+    sg_scatter_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(packed, blk, kstart, n_rows, p.nblk, order);
+    TEAM_LAUNCH_CHECK("sg_scatter_kernel");
+    const unsigned gblocks = (unsigned)((p.max_segs + SG_GW - 1) / SG_GW);
+    const T* xp = reinterpret_cast<const T*>(x);
+    if (norm) sg_gather_kernel<T, true><<<gblocks, SG_GW * 32, 0, st>>>(xp, order, kstart, totals, segbase, K, p.seg_len, partials);
+    else sg_gather_kernel<T, false><<<gblocks, SG_GW * 32, 0, st>>>(xp, order, kstart, totals, segbase, K, p.seg_len, partials);
+    TEAM_LAUNCH_CHECK("sg_gather_kernel");
+    sg_fold_kernel<<<K, 128, 0, st>>>(partials, segbase, totals, sums, counts);
+    TEAM_LAUNCH_CHECK("sg_fold_kernel");
+    return TEAM_OK;
+}
+
 // pass 2: fixed-order sum over clusters.  grid = K, 512 threads = 128 float4 columns x 4 lanes
 // of cluster partials; lane g sums clusters g, g+4, ... then the 4 lanes fold in order.
 __global__ void __launch_bounds__(512)
@@ -525,7 +754,9 @@ extern "C" size_t team_segsum_workspace_bytes(int64_t n_rows, int64_t num_keys) 
     seg_plan(n_rows, num_keys, &ncl, &nsl, &sk, &rpc);
     int vec, chunks;
     if (seg2_plan(n_rows, num_keys, false, &vec, &chunks, &rpc) && chunks > ncl) ncl = chunks;      // partial records of either generation
-    return align_up((size_t)ncl * num_keys * D * sizeof(float), 256) + align_up((size_t)ncl * num_keys * sizeof(long long), 256);
+    size_t need = align_up((size_t)ncl * num_keys * D * sizeof(float), 256) + align_up((size_t)ncl * num_keys * sizeof(long long), 256);
+    if (sg_wanted(n_rows, num_keys)) { const size_t s3 = sg_plan(n_rows, num_keys).total; if (s3 > need) need = s3; }
+    return need;
 }
 
 extern "C" int team_segsum(const void* x, int x_dtype, const int64_t* labels, const int64_t* states,
@@ -547,6 +778,12 @@ extern "C" int team_segsum(const void* x, int x_dtype, const int64_t* labels, co
         return TEAM_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (sg_wanted(n_rows, K)) {            // many keys: partition the rows by key, then sum them straight from HBM
+        TEAM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "team_segsum: workspace must be 256-byte aligned");
+        return x_dtype == TEAM_DTYPE_F32
+                   ? sg_run<float>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, normalize_rows != 0, sums, counts, workspace, st)
+                   : sg_run<__nv_bfloat16>(x, labels, states, n_rows, class_base, (int)num_classes, (int)num_states, K, normalize_rows != 0, sums, counts, workspace, st);
+    }
     float* part_sums = reinterpret_cast<float*>(workspace);
     int vec2 = 0, chunks2 = 0;
     int64_t rpc2 = 0;

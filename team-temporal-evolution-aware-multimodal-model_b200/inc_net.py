@@ -26,7 +26,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
-from . import capi, graph, head, ops
+from . import capi, feature_cache, graph, head, ops
 
 FEATURE_DIM = capi.D
 
@@ -221,6 +221,16 @@ class Proof_Net(nn.Module):
         self.img_prototypes_by_state: Dict[int, Dict[int, torch.Tensor]] = {}
         self.evolution_embeddings = None
         self.team_mode = _mode_of(args)
+        # frozen-tower feature cache (feature_cache.py): args["team_feature_cache"] = False switches it off
+        self._towers = feature_cache.TowerCache(convnet) if args.get("team_feature_cache", True) else None
+
+    def _img_feats(self, x):
+        x = x.to(self._device)
+        return self._towers.image(x) if self._towers is not None else self.convnet.encode_image(x)
+
+    def _txt_feats(self, t):
+        t = t.to(self._device) if torch.is_tensor(t) else t
+        return self._towers.text(t) if self._towers is not None else self.convnet.encode_text(t)
 
     # ------------------------------------------------------------------ incremental bookkeeping
     def update_prototype(self, nb_classes):
@@ -287,11 +297,11 @@ class Proof_Net(nn.Module):
                 "'Dropout') or call the head in eval() mode; the reference default is p = 0.1 in train mode")
 
     def encode_image(self, x, normalize: bool = False):
-        feats = self.convnet.encode_image(x.to(self._device))
+        feats = self._img_feats(x)
         return head.encode_grad(self._pack(), "image", feats, normalize=normalize, mode=self.team_mode)
 
     def encode_text(self, x, normalize: bool = False):
-        feats = self.convnet.encode_text(x.to(self._device) if torch.is_tensor(x) else x)
+        feats = self._txt_feats(x)
         return head.encode_grad(self._pack(), "text", feats, normalize=normalize, mode=self.team_mode)
 
     def encode_state(self, state_ids, normalize: bool = False):
@@ -307,11 +317,10 @@ class Proof_Net(nn.Module):
         """(image [B,512], text [B,1,512], state [B,512], proto [B,512], exp(logit_scale)); per-sample text
         (``len(text) == B``, the only form the learner uses, models/proof.py:421-425)."""
         self._check_dropout()
-        img = self.convnet.encode_image(image.to(self._device))
+        img = self._img_feats(image)
         if isinstance(text, list):
             text = self.tokenizer(text)
-            text = text.to(self._device) if torch.is_tensor(text) else text
-        txt = self.convnet.encode_text(text)
+        txt = self._txt_feats(text)
         if txt.shape[0] != img.shape[0]:          # class texts shared by all samples: text output = mean over them
             if self._wants_grad():
                 return self._tri_modal_class_text_grad(img, txt, state_ids.to(self._device))
@@ -359,11 +368,10 @@ class Proof_Net(nn.Module):
     def forward_for_classification(self, image, text_cls):
         """Learner.forward_for_classification (models/proof.py:519-536): cosine logits of the projected image
         against the projected class texts, no scale.  Returns (logits [B,C], argmax [B])."""
-        img = self.convnet.encode_image(image.to(self._device))
+        img = self._img_feats(image)
         if isinstance(text_cls, list):
             text_cls = self.tokenizer(text_cls)
-            text_cls = text_cls.to(self._device) if torch.is_tensor(text_cls) else text_cls
-        tc = self.convnet.encode_text(text_cls)
+        tc = self._txt_feats(text_cls)
         with torch.no_grad():
             xi = head.encode(self._pack(), "image", img, normalize=True, mode=self.team_mode)
             ti = head.encode(self._pack(), "text", tc, normalize=True, mode=self.team_mode)
@@ -374,10 +382,10 @@ class Proof_Net(nn.Module):
         proto [C,512] batch mean).  Without autograd: one fused forward (team_head_proof_fwd); with autograd (a trainable
         parameter under enable_grad): the same function through the differentiable encode + standalone attention ops."""
         self._check_dropout()
-        img = self.convnet.encode_image(image.to(self._device))
+        img = self._img_feats(image)
         if isinstance(text, list):
             text = self.tokenizer(text)
-        txt = self.convnet.encode_text(text.to(self._device) if torch.is_tensor(text) else text)
+        txt = self._txt_feats(text)
         if self._wants_grad():
             pack = self._pack()
             return self._proof_grad(head.encode_grad(pack, "image", img, normalize=True, mode=self.team_mode),

@@ -109,6 +109,36 @@ def test_keyed_sums_empty_and_out_of_range():
     assert counts0.cpu().tolist() == [0, 0, 0, 0] and float(sums0.abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("n", [4096, 10007, 300000])
+def test_keyed_sums_many_keys_foreign_rows(n):
+    """The key-partitioned path (K > 100: rows sorted by key, then summed from HBM): labels outside the class window, states
+    outside [0, 10), keys that own no row, a key that owns nearly every row; equals the shared-memory path bit for bit in
+    the counts and to round-off in the sums."""
+    import os
+    from team_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 512, generator=g)
+    y = torch.randint(-2, 26, (n,), generator=g)
+    s = torch.randint(-1, 12, (n,), generator=g)
+    y[: n // 2] = 7; s[: n // 2] = 4                        # one heavy key
+    y[y == 11] = 12                                          # class 11 owns nothing
+    sums, counts = ops.keyed_sums(x.cuda(), y.cuda(), s.cuda(), class_base=3, num_classes=20, num_states=10)
+    ok = (y >= 3) & (y < 23) & (s >= 0) & (s < 10)
+    key = ((y - 3) * 10 + s)[ok]
+    ref = torch.zeros(200, 512, dtype=torch.float64).index_add_(0, key, x[ok].double())
+    assert torch.equal(counts.cpu(), torch.bincount(key, minlength=200))
+    assert rel(sums, ref) < 1e-5
+    assert int(counts[80:90].sum()) == 0 and float(sums[80:90].abs().sum()) == 0.0
+    again, _ = ops.keyed_sums(x.cuda(), y.cuda(), s.cuda(), class_base=3, num_classes=20, num_states=10)
+    assert torch.equal(sums, again)
+    os.environ["TEAM_SEGSUM_V2"] = "1"                       # the column-partitioned shared-memory path
+    try:
+        old, cold = ops.keyed_sums(x.cuda(), y.cuda(), s.cuda(), class_base=3, num_classes=20, num_states=10)
+    finally:
+        del os.environ["TEAM_SEGSUM_V2"]
+    assert torch.equal(cold, counts) and rel(old, ref) < 1e-5
+
+
 @pytest.mark.parametrize("n,C,dtype", [(1, 2, torch.float32), (1025, 20, torch.float32),
                                        (4096, 32, torch.float32), (999, 50, torch.float32),
                                        (2048, 20, torch.bfloat16)])

@@ -13,12 +13,19 @@ METRICS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__wa
            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a .ncu-rep report, or the `ncu -i rep --page raw --csv` dump of one (what a GPU box sends back when the report is too large)
+if sys.argv[1].endswith(".csv"):
+    raw = open(sys.argv[1]).read()
+else:
+    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
 w = csv.writer(sys.stdout)
 w.writerow(["id", "kernel", "grid", "block"] + [f"{m} [{units[idx[m]]}]" for m in METRICS if m in idx])
+only_team = len(sys.argv) > 2 and sys.argv[2] == "--team-only"
 for r in data:
+    if only_team and "team::" not in r[idx["Kernel Name"]]:
+        continue
     name = r[idx["Kernel Name"]].split("(")[0].replace("team::", "").replace("void ", "")
     w.writerow([r[idx["ID"]], name, r[idx["Grid Size"]], r[idx["Block Size"]]] + [r[idx[m]] for m in METRICS if m in idx])
