@@ -618,8 +618,9 @@ def run_team(a):
                     lossv = ts.step(epoch=0).cpu()            # D2H of the step's losses (and the sync a logging loop has)
                     last = lossv
                 dt = time.perf_counter() - t0
-            train_step = {"what": "cls logits + forward_tri_modal + ClipLoss branch + unicl_loss (evolution features) + backward "
-                                  "+ fused AdamW as one CUDA graph (team_b200.train.TrainStep)",
+            train_step = {"what": "cls logits + forward_tri_modal + ClipLoss on the head's own normalised rows (gradient joins the head "
+                                  "backward: team_head_grads.g_own_rows) + unicl_loss (evolution features) + backward + fused AdamW "
+                                  "as one CUDA graph (team_b200.train.TrainStep)",
                           "batch": B, "ms_per_step": tms_dev, "samples_per_s": B / tms_dev * 1e3, "library_launches_per_step": int(tl),
                           "e2e": {"ms_per_step": dt / a.steps * 1e3, "samples_per_s": B * a.steps / dt,
                                   "h2d_bytes_per_step": B * (512 * 4 * 2 + 16), "d2h_bytes_per_step": 20,

@@ -155,9 +155,19 @@ typedef struct team_head_grads {            /* all OVERWRITTEN by team_head_tri_
     void* ev_w_fc;
     void* ev_w_qkv;
     const team_peer_comm* comm;              /* NULL: no exchange inside the call */
+    /* Optional INPUT: an extra cotangent [2B,512] on the normalised projected own rows themselves (image rows, then text
+     * rows: what encode_image / encode_text(normalize=True) return and team_head_own_rows_offset exposes).  The
+     * learner's ClipLoss branch (models/proof.py:428-431) consumes exactly these rows, so its gradient joins the
+     * head's backward here instead of running the two projections and their backward a second time.  NULL = none. */
+    const float* g_own_rows;
 } team_head_grads;
 
 size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, int32_t num_prompts,
+                                 int32_t num_text_cls, int mode);
+/* Byte offset, inside the workspace of team_head_tri_fwd (same arguments as team_head_workspace_bytes), of the
+ * [2B,512] fp32 rows normalize(encode_image(x)) | normalize(encode_text(t)) the forward leaves there (valid until the
+ * matching team_head_tri_bwd): the inputs of the ClipLoss branch, models/proof.py:428-430. */
+size_t team_head_own_rows_offset(int64_t batch, int32_t num_classes, int32_t num_prompts,
                                  int32_t num_text_cls, int mode);
 
 /* image_feat/text_feat [B,512] fp32 (post-CLIP features; per-sample text), state_ids [B] int64.

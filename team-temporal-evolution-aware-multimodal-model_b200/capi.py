@@ -48,7 +48,8 @@ class PeerComm(C.Structure):
 class HeadGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts", "state_emb",
-                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "ev_w_fc", "ev_w_qkv")] + [("comm", C.POINTER(PeerComm))]
+                 "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "ev_w_fc", "ev_w_qkv")] + [("comm", C.POINTER(PeerComm)),
+                                                                                                  ("g_own_rows", C.c_void_p)]
 
 
 class TgcnBlock(C.Structure):
@@ -122,6 +123,8 @@ def _declare(lib):
     if hasattr(lib, "team_head_workspace_bytes"):
         lib.team_head_workspace_bytes.restype = sz
         lib.team_head_workspace_bytes.argtypes = [i64, C.c_int32, C.c_int32, C.c_int32, i32]
+        lib.team_head_own_rows_offset.restype = sz
+        lib.team_head_own_rows_offset.argtypes = [i64, C.c_int32, C.c_int32, C.c_int32, i32]
         lib.team_head_tri_fwd.restype = i32
         lib.team_head_tri_fwd.argtypes = [C.POINTER(HeadWeights), i32, i64, vp, vp, vp, vp, i64,
                                           vp, vp, vp, vp, vp, vp, vp, sz, vp]

@@ -72,7 +72,7 @@ struct TcGroup {
     int stages;
     int cluster;                 // CTAs per cluster (1, 2, 4 or 8) = largest split count of the group
     unsigned long long* dbg;     // optional [cta][16] globaltimer stamps (tools/gemm_probe.py), else null
-    int diag;                    // TEAM_GEMM_DIAG (timing experiments only, results invalid): 1 = no global stores, 2 = no k-loop
+    int diag;                    // TEAM_GEMM_DIAG (timing experiments only, results invalid): 1 = no global stores, 2 = no k-loop, 4 = no epilogue loop, 8 = no TMEM -> smem copy
 };
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
@@ -284,7 +284,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
     // TMEM -> padded smem tile (the operand ring is idle now); thread = one accumulator row
     float* stg = reinterpret_cast<float*>(smem);
     const int sld = bn + 4;
-    {
+    if (!(g.diag & 8)) {
         float* my = stg + (size_t)(warp * 32 + lane) * sld;
         const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16);
         int c = 0;
@@ -322,7 +322,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TcGroup g) {
         __syncthreads();
     }
     if (threadIdx.x == 64) TC_STAMP(9);
-    {
+    if (!(g.diag & 4)) {
         const int M = P.M, N = P.N;
         float* const C = (g.diag & 1) ? nullptr : P.C;
         __nv_bfloat16* const Cb = (g.diag & 1) ? nullptr : P.Cb;

@@ -354,6 +354,14 @@ extern "C" size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, 
     return w.total_bytes;
 }
 
+// byte offset of the normalised projected own rows Xo ([2B,512] fp32: image rows, then text rows) inside the workspace
+extern "C" size_t team_head_own_rows_offset(int64_t batch, int32_t num_classes, int32_t num_prompts, int32_t num_text_cls, int mode) {
+    HeadDims d = head_dims(batch, num_classes, num_prompts, num_text_cls);
+    HeadWS w;
+    head_plan(d, mode, reinterpret_cast<void*>(uintptr_t(256)), &w);          // a non-null fake base: only the offsets are used
+    return (size_t)(reinterpret_cast<uintptr_t>(w.Xo.f) - 256);
+}
+
 #define RUN(wave)                                     \
     do {                                              \
         int _rc = run_wave(cx, wave);                 \
@@ -494,7 +502,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     SideStream* own_side = nullptr;
     {
         const cudaStream_t ost = fork_side(cx.st, &own_side);
-        TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, ost, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo_own, (__nv_bfloat16*)nullptr, w.own_partials);
+        TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, ost, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo_own, (__nv_bfloat16*)nullptr, w.own_partials, gr->g_own_rows);
         // own x own score gradients: initial values of the dQ / dK rows (the GEMMs of waves 5 and 7 accumulate on top)
         TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, ost, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, (__nv_bfloat16*)nullptr);
     }

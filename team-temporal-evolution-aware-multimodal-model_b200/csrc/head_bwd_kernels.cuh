@@ -373,7 +373,8 @@ ln_own_bwd_kernel(HeadDims d, const float* __restrict__ Ybo, const float* __rest
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ g_image,
                   const float* __restrict__ g_text, float* __restrict__ dYo, __nv_bfloat16* __restrict__ dYoh,
                   float* __restrict__ dXo, float* __restrict__ rowdot, float* __restrict__ dsown,
-                  float* __restrict__ dVFo, __nv_bfloat16* __restrict__ dVFoh, float* __restrict__ partials) {
+                  float* __restrict__ dVFo, __nv_bfloat16* __restrict__ dVFoh, float* __restrict__ partials,
+                  const float* __restrict__ g_own) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) float fold[3][8][D];        // 48 KB
@@ -410,7 +411,14 @@ ln_own_bwd_kernel(HeadDims d, const float* __restrict__ Ybo, const float* __rest
             add_row(dbf, du);
             st_row(dYo + (size_t)row * D, lane, du);
             st_row_h(dYoh != nullptr ? dYoh + (size_t)row * D : nullptr, lane, du);
-            st_row(dXo + (size_t)row * D, lane, du);
+            if (g_own != nullptr) {       // extra cotangent on the normalised own rows themselves (the ClipLoss branch, head.cuh)
+                float4 gx[4];
+                ld_row(g_own + (size_t)row * D, lane, gx);
+                add_row(gx, du);
+                st_row(dXo + (size_t)row * D, lane, gx);
+            } else {
+                st_row(dXo + (size_t)row * D, lane, du);
+            }
             const float rd = warp_sum(dot_part(du, ybar));
             const float da_i = warp_sum(dot_part(du, vi));
             const float da_t = warp_sum(dot_part(du, vt));

@@ -560,8 +560,19 @@ class HeadStepRunner:
             self.logits.data_ptr() if n_cls else None, self.argmax.data_ptr() if n_cls else None,
             self.ws.data_ptr(), self.nbytes, _stream_ptr()), "team_head_tri_fwd")
 
-    def backward(self, image, text, sid, cots):
-        """``cots[3]`` (cotangent of the prototype output) may be None: the prototype rows are then skipped."""
+    def own_rows(self) -> torch.Tensor:
+        """[2B,512] view of normalize(encode_image(x)) | normalize(encode_text(t)) as the last ``forward`` left them in the
+        workspace (``team_head_own_rows_offset``): the inputs of the ClipLoss branch (models/proof.py:428-430)."""
+        off = capi.lib().team_head_own_rows_offset(self.B, self.hw.num_classes, self.pack.T * self.pack.ppt, self.n_cls, self.mode)
+        return self.ws[off:off + 2 * self.B * capi.D * 4].view(torch.float32).view(2 * self.B, capi.D)
+
+    def backward(self, image, text, sid, cots, g_own_rows: Optional[torch.Tensor] = None):
+        """``cots[3]`` (cotangent of the prototype output) may be None: the prototype rows are then skipped.
+        ``g_own_rows``: optional extra cotangent [2B,512] (or [2,B,512]) on ``own_rows()`` (``team_head_grads.g_own_rows``)."""
+        if g_own_rows is not None and (g_own_rows.numel() != 2 * self.B * capi.D or g_own_rows.dtype != torch.float32
+                                       or not g_own_rows.is_contiguous()):
+            raise ValueError("g_own_rows must be a contiguous fp32 [2B,512] tensor")
+        self.hg.g_own_rows = g_own_rows.data_ptr() if g_own_rows is not None else None
         capi.check(capi.lib().team_head_tri_bwd(
             C.byref(self.hw), self.mode, self.B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),
             cots[0].data_ptr(), cots[1].data_ptr(), cots[2].data_ptr(), cots[3].data_ptr() if cots[3] is not None else None,

@@ -207,8 +207,10 @@ def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, lab
 
 
 def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, grad_scale: float = 1.0,
-              mode: int = capi.MODE_F32):
-    """ClipLoss.forward (utils/toolkit.py:128-141, world_size 1) forward + gradient: (loss [1], (g_image, g_text))."""
+              mode: int = capi.MODE_F32, grads_out: Optional[torch.Tensor] = None):
+    """ClipLoss.forward (utils/toolkit.py:128-141, world_size 1) forward + gradient: (loss [1], (g_image, g_text)).
+    ``grads_out``: optional contiguous fp32 [2,B,512] buffer the two gradients are written to (image rows, then text rows -
+    the layout of ``team_head_grads.g_own_rows``)."""
     capi.require_device()
     B = image.shape[0]
     xi, xt = _chk_rows(image.detach().float(), "image"), _chk_rows(text.detach().float(), "text")
@@ -219,7 +221,9 @@ def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, gr
     dev = xi.device
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     loss = torch.empty((1,), dtype=torch.float32, device=dev)
-    grads = torch.empty((2, B, capi.D), dtype=torch.float32, device=dev)
+    grads = grads_out if grads_out is not None else torch.empty((2, B, capi.D), dtype=torch.float32, device=dev)
+    if grads.shape != (2, B, capi.D) or grads.dtype != torch.float32 or not grads.is_contiguous() or grads.device != dev:
+        raise ValueError("clip_loss: grads_out must be a contiguous fp32 [2,B,512] tensor on the inputs' device")
     capi.check(L.team_clip_loss(mode, xi.data_ptr(), xt.data_ptr(), B, float(logit_scale), float(grad_scale),
                                 loss.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(), ws.data_ptr(), nbytes,
                                 _stream_ptr()), "team_clip_loss")

@@ -6,7 +6,7 @@
 
 `Learner._train_proj_with_replay` keeps working unchanged on `inc_net.Proof_Net` (tests/test_gpu_learner_dropin.py);
 `TrainStep` is the fast form of the same loop body for callers that can hand over pre-extracted features: every
-launch of the step - 60-odd library kernels - is captured once per epoch (the learner's cosine learning-rate schedule
+launch of the step - 50-odd library kernels - is captured once per epoch (the learner's cosine learning-rate schedule
 and unicl's dynamic temperature change per epoch, :111-116, :363) and replayed per batch.  The Adam step count lives
 on the device (`team_adamw_step_graph`).  Not captured (and not trained here): `convnet.logit_scale` - the captured
 ClipLoss launch bakes its value in; pass the current value when an epoch's graph is captured.
@@ -62,6 +62,7 @@ class TrainStep:
         self.image, self.text = mk(batch, D), mk(batch, D)
         self.state, self.labels = mk(batch, dt=torch.int64), mk(batch, dt=torch.int64)
         self.losses = torch.zeros((5,), dtype=torch.float32, device=dev)     # total, ce, clip, unicl total, unicl instance
+        self.g_own = torch.zeros((2, batch, D), dtype=torch.float32, device=dev)   # ClipLoss gradient w.r.t. the normalised own rows
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self._stream = torch.cuda.Stream(device=dev)
 
@@ -76,15 +77,12 @@ class TrainStep:
         ce = torch.nn.functional.cross_entropy(r.logits, y)                       # value only: the logits carry no gradient (:411-417)
         un, cots = ops.unicl_loss(r.outs[0], r.outs[1], r.outs[2], y, state_ids=sid, evolution_features=self.evo,
                                   epoch=epoch, max_epoch=self.tuned_epoch, grad_scale=0.3, mode=mode)
-        r.backward(img, txt, sid, [cots[0], cots[1], cots[2], None])              # the losses never touch the prototype output
-        ei = head.encode_grad(self.pack, "image", img, normalize=True, mode=mode)
-        et = head.encode_grad(self.pack, "text", txt, normalize=True, mode=mode)
-        cl, (gi, gt) = ops.clip_loss(ei.detach(), et.detach(), self.logit_scale, mode=mode)
-        for p, _ in self.pairs[:4]:
-            p.grad = None
-        torch.autograd.backward([ei, et], [gi, gt])
-        for p, g in self.pairs[:4]:
-            g.add_(p.grad.reshape(g.shape))
+        # ClipLoss branch (:428-431): its inputs normalize(encode_text(..)) / normalize(encode_image(..)) ARE the normalised
+        # own rows the head's forward just produced, so the loss reads them in place and its gradient joins the head's
+        # backward as an extra cotangent on those rows (team_head_grads.g_own_rows) - no second pass through the projections
+        xo = r.own_rows()
+        cl, _ = ops.clip_loss(xo[:self.B], xo[self.B:], self.logit_scale, mode=mode, grads_out=self.g_own)
+        r.backward(img, txt, sid, [cots[0], cots[1], cots[2], None], g_own_rows=self.g_own)   # the losses never touch the prototype output
         self.opt.lr = self.lr_at(epoch)
         self.opt.step_graph([g for _, g in self.pairs])
         self.losses[1] = ce
