@@ -29,15 +29,32 @@ __host__ __device__ inline size_t table2_bwd_smem_floats(const HeadDims& d) {
 // tabN[tr] = NF_r, tabS[tr] = S_r + bfc;  tr < C: r = tr (prototype row), tr >= C: r = M + tr - C (state-table row)
 __device__ __forceinline__ void table2_load(const HeadDims& d, const float* __restrict__ NFt, const float* __restrict__ S,
                                             const float* __restrict__ bfc, float* tabN, float* tabS) {
+    // Six float4 pairs in flight per thread: with a plain loop every iteration is one dependent L2 round trip (all CTAs read
+    // the same 120 KB at the same moment), 15 of them back to back before the first row can start.
     const int n4 = d.Rt * (D / 4);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const int tr = i >> 7, c = i & 127;
-        const int r = tr < d.C ? tr : d.M + tr - d.C;
-        reinterpret_cast<float4*>(tabN)[i] = reinterpret_cast<const float4*>(NFt + (size_t)r * D)[c];
-        float4 s = reinterpret_cast<const float4*>(S + (size_t)r * D)[c];
-        const float4 b = reinterpret_cast<const float4*>(bfc)[c];
-        s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-        reinterpret_cast<float4*>(tabS)[i] = s;
+    constexpr int UB = 6;
+    const float4 bias = reinterpret_cast<const float4*>(bfc)[threadIdx.x & 127];      // column of i = tid + k * blockDim.x (blockDim.x % 128 == 0)
+    for (int i0 = threadIdx.x; i0 < n4; i0 += UB * blockDim.x) {
+        float4 a[UB], s[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            if (i < n4) {
+                const int tr = i >> 7, c = i & 127;
+                const int r = tr < d.C ? tr : d.M + tr - d.C;
+                a[u] = __ldg(reinterpret_cast<const float4*>(NFt + (size_t)r * D) + c);
+                s[u] = __ldg(reinterpret_cast<const float4*>(S + (size_t)r * D) + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            if (i < n4) {
+                s[u].x += bias.x; s[u].y += bias.y; s[u].z += bias.z; s[u].w += bias.w;
+                reinterpret_cast<float4*>(tabN)[i] = a[u];
+                reinterpret_cast<float4*>(tabS)[i] = s[u];
+            }
+        }
     }
 }
 
