@@ -122,8 +122,18 @@ typedef struct team_head_weights {
     const float* ln_b;
     const float* prototypes;                 /* img_prototypes [C,512] */
     int32_t num_classes;                     /* C */
-    int32_t reserved;
+    /* Optional: the projections of the first num_frozen tasks are frozen (utils/inc_net.py:392-393, :494-502), so their
+     * sums are constants of the task: w_frozen[k] [512,512] / b_frozen[k] [512] (k = 0 image, 1 text, 2 state) hold
+     * sum_{t < num_frozen} W_t as written by team_head_frozen_sums, and the step prologue adds only the remaining tasks
+     * (same left-to-right order, bit-identical to summing all T).  num_frozen = 0: every task is summed per call. */
+    int32_t num_frozen;
+    const float* w_frozen[3];
+    const float* b_frozen[3];
 } team_head_weights;
+
+/* w_sums [3][512*512], b_sums [3][512]: sum over tasks t < num_frozen of the image / text / state projections
+ * (1 <= num_frozen <= T), for team_head_weights.w_frozen / b_frozen.  Call again whenever those parameters change. */
+int team_head_frozen_sums(const team_head_weights* w, int32_t num_frozen, float* w_sums, float* b_sums, void* stream);
 
 /* Peer-memory gradient exchange folded into the backward (optional, see team_peer_allreduce_f32 for the meaning of
  * the pointer tables): the gradient pointers of team_head_grads must then lie inside bufs[rank][0, n_total) with

@@ -37,7 +37,8 @@ class HeadWeights(C.Structure):
                  ("w_img", "b_img", "w_text", "b_text", "w_state", "b_state", "prompts")] +
                 [(n, C.c_void_p) for n in
                  ("state_emb", "w_q", "w_k", "w_v", "w_fc", "b_fc", "ln_g", "ln_b", "prototypes")] +
-                [("num_classes", C.c_int32), ("reserved", C.c_int32)])
+                [("num_classes", C.c_int32), ("num_frozen", C.c_int32),
+                 ("w_frozen", C.c_void_p * 3), ("b_frozen", C.c_void_p * 3)])
 
 
 class PeerComm(C.Structure):
@@ -123,6 +124,8 @@ def _declare(lib):
     if hasattr(lib, "team_head_workspace_bytes"):
         lib.team_head_workspace_bytes.restype = sz
         lib.team_head_workspace_bytes.argtypes = [i64, C.c_int32, C.c_int32, C.c_int32, i32]
+        lib.team_head_frozen_sums.restype = i32
+        lib.team_head_frozen_sums.argtypes = [C.POINTER(HeadWeights), i32, vp, vp, vp]
         lib.team_head_own_rows_offset.restype = sz
         lib.team_head_own_rows_offset.argtypes = [i64, C.c_int32, C.c_int32, C.c_int32, i32]
         lib.team_head_tri_fwd.restype = i32

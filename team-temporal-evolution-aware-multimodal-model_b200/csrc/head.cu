@@ -195,8 +195,19 @@ static int prologue(HeadCtx& cx, const team_head_weights* hw, int nsum, const fl
     memset(&ps, 0, sizeof(ps));
     const float* const* Ws[3] = {hw->w_img, hw->w_text, hw->w_state};
     const float* const* Bs[3] = {hw->b_img, hw->b_text, hw->b_state};
+    const int nf = hw->num_frozen;
     for (int k = 0; k < 3; ++k) {
-        ps.W[k] = plist(Ws[k], T); ps.Bv[k] = plist(Bs[k], T);
+        if (nf > 0 && nf <= T && hw->w_frozen[k] != nullptr && hw->b_frozen[k] != nullptr) {
+            // frozen tasks enter as ONE precomputed term (team_head_frozen_sums): ((W_0 + W_1) + ...) + W_nf + ... as before
+            PtrList lw, lb;
+            memset(&lw, 0, sizeof(lw)); memset(&lb, 0, sizeof(lb));
+            lw.p[0] = hw->w_frozen[k]; lb.p[0] = hw->b_frozen[k];
+            for (int t = nf; t < T; ++t) { lw.p[1 + t - nf] = Ws[k][t]; lb.p[1 + t - nf] = Bs[k][t]; }
+            lw.n = lb.n = 1 + T - nf;
+            ps.W[k] = lw; ps.Bv[k] = lb;
+        } else {
+            ps.W[k] = plist(Ws[k], T); ps.Bv[k] = plist(Bs[k], T);
+        }
         ps.Wout[k] = w.Wsum[k].f; ps.Wh[k] = w.Wsum[k].h; ps.bout[k] = w.bsum[k];
     }
     ps.n = nsum;
@@ -352,6 +363,26 @@ extern "C" size_t team_head_workspace_bytes(int64_t batch, int32_t num_classes, 
     HeadWS w;
     head_plan(d, mode, nullptr, &w);
     return w.total_bytes;
+}
+
+extern "C" int team_head_frozen_sums(const team_head_weights* hw, int32_t num_frozen, float* w_sums, float* b_sums, void* stream) {
+    TEAM_REQUIRE(hw != nullptr && w_sums != nullptr && b_sums != nullptr, "head frozen sums: null pointer");
+    TEAM_REQUIRE(num_frozen >= 1 && num_frozen <= hw->num_tasks && hw->num_tasks <= TEAM_MAX_TASKS, "head frozen sums: num_frozen %d out of [1, %d]", num_frozen, hw->num_tasks);
+    PrepSum ps;
+    memset(&ps, 0, sizeof(ps));
+    const float* const* Ws[3] = {hw->w_img, hw->w_text, hw->w_state};
+    const float* const* Bs[3] = {hw->b_img, hw->b_text, hw->b_state};
+    for (int k = 0; k < 3; ++k) {
+        for (int t = 0; t < num_frozen; ++t) TEAM_REQUIRE(Ws[k][t] != nullptr && Bs[k][t] != nullptr, "head frozen sums: null projection %d of task %d", k, t);
+        ps.W[k] = plist(Ws[k], num_frozen); ps.Bv[k] = plist(Bs[k], num_frozen);
+        ps.Wout[k] = w_sums + (size_t)k * D * D; ps.Wh[k] = nullptr; ps.bout[k] = b_sums + (size_t)k * D;
+    }
+    ps.n = 3;
+    ConvList cl;
+    memset(&cl, 0, sizeof(cl));
+    cl.sum_blocks = 3 * PREP_SUM_BLOCKS_PER_W;
+    TEAM_LAUNCH(prep_kernel, cl.sum_blocks, 256, 0, (cudaStream_t)stream, ps, cl);
+    return TEAM_OK;
 }
 
 // byte offset of the normalised projected own rows Xo ([2B,512] fp32: image rows, then text rows) inside the workspace

@@ -484,6 +484,8 @@ class HeadStepRunner:
         self.protos = _f32c(img_prototypes, dev)
         self.hw = _fill_weights(pack.T, pack.ppt, self.flat, self.protos)
         L = capi.lib()
+        self._frozen = None
+        self.refresh_frozen()
         self.nbytes = L.team_head_workspace_bytes(batch, self.hw.num_classes, pack.T * pack.ppt, num_text_cls, mode)
         self.ws = torch.empty((self.nbytes,), dtype=torch.uint8, device=dev)
         self.outs = torch.empty((4, batch, capi.D), dtype=torch.float32, device=dev)
@@ -524,6 +526,29 @@ class HeadStepRunner:
             self.hg.ev_w_qkv = self.ready_events[1].cuda_event
             self.comm_stream = torch.cuda.Stream(device=dev)
 
+    def refresh_frozen(self):
+        """The projections of the old tasks are frozen (utils/inc_net.py:392-393, :494-502; requires_grad False on every
+        one of them): their sums are computed ONCE here (``team_head_frozen_sums``) and the step prologue adds only the
+        newest task (``team_head_weights.num_frozen``).  Call again after loading other values into those parameters."""
+        T = self.pack.T
+        old = [p for k in range(6) for p in self.pack.flat[k * T:k * T + T - 1]]
+        self._frozen_src = old
+        self._frozen_ver = [p._version for p in old]
+        if T < 2 or any(p.requires_grad for p in old):
+            self.hw.num_frozen = 0
+            return
+        if self._frozen is None:
+            self._frozen = (torch.empty((3, capi.D, capi.D), dtype=torch.float32, device=self.dev),
+                            torch.empty((3, capi.D), dtype=torch.float32, device=self.dev))
+        fw, fb = self._frozen
+        self.hw.num_frozen = 0
+        capi.check(capi.lib().team_head_frozen_sums(C.byref(self.hw), T - 1, fw.data_ptr(), fb.data_ptr(), _stream_ptr()),
+                   "team_head_frozen_sums")
+        for k in range(3):
+            self.hw.w_frozen[k] = fw[k].data_ptr()
+            self.hw.b_frozen[k] = fb[k].data_ptr()
+        self.hw.num_frozen = T - 1
+
     @staticmethod
     def grad_numel(pack: HeadParamPack) -> int:
         return sum(sz for _, sz in GRAD_LAYOUT) + max(pack.T * pack.ppt, 1) * capi.D
@@ -552,6 +577,8 @@ class HeadStepRunner:
         cur.wait_stream(self.comm_stream)
 
     def forward(self, image, text, sid, text_cls=None):
+        if self.hw.num_frozen and any(p._version != v for p, v in zip(self._frozen_src, self._frozen_ver)):
+            self.refresh_frozen()              # an old task's projection was written to (load_state_dict, ...): re-sum
         n_cls = self.n_cls if text_cls is not None else 0
         capi.check(capi.lib().team_head_tri_fwd(
             C.byref(self.hw), self.mode, self.B, image.data_ptr(), text.data_ptr(), sid.data_ptr(),

@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PAIRS = [  # (C struct, ctypes class name, fields to compare: C field -> ctypes field)
-    ("team_head_weights", "HeadWeights", ["num_tasks", "prompts_per_task", "w_img", "prompts", "state_emb", "w_q", "w_fc", "ln_b", "prototypes", "num_classes"]),
+    ("team_head_weights", "HeadWeights", ["num_tasks", "prompts_per_task", "w_img", "prompts", "state_emb", "w_q", "w_fc", "ln_b", "prototypes", "num_classes", "num_frozen", "w_frozen", "b_frozen"]),
     ("team_head_grads", "HeadGrads", ["w_img", "prompts", "state_emb", "w_q", "w_fc", "ln_b", "ev_w_fc", "ev_w_qkv", "comm", "g_own_rows"]),
     ("team_peer_comm", "PeerComm", ["bufs", "flags", "multicast", "rank", "world", "n_total", "split_at"]),
     ("team_tgcn_block", "TgcnBlock", ["msg_w", "gate_b"]),

@@ -358,3 +358,37 @@ def test_null_proto_cotangent_equals_zero_cotangent(mode_name):
         if key is not None:
             lo = (view.data_ptr() - r.flat_grads.data_ptr()) // 4
             assert rel(got[key].reshape(-1), want[lo:lo + view.numel()]) < 1e-6, name
+
+
+def test_frozen_projection_sums_are_bit_identical():
+    """team_head_weights.num_frozen / team_head_frozen_sums: the old tasks' projections enter the step prologue as one
+    precomputed term (they are frozen, utils/inc_net.py:392-393).  Outputs and gradients must equal the all-tasks sum bit for
+    bit (same left-to-right order), and an in-place change of an old projection must be picked up."""
+    from team_b200 import head
+    dev = torch.device("cuda")
+    T, B = 4, 37
+    C = 2 * T
+    params = {k: v.to(dev) for k, v in synth.make_params(T, seed=91).items()}
+    pack = head.HeadParamPack.from_state_dict(params)
+    protos = synth.make_prototypes(C).to(dev)
+    b = {k: v.to(dev) for k, v in synth.make_batch(B, C, step=5).items()}
+    cots = [c.to(dev).reshape(B, 512) for c in synth.make_cotangents(B, step=5)]
+    tc = synth.make_text_class_features(20)[:C].contiguous().to(dev)
+    for mode in (head.MODE_F32, head.MODE_BF16):
+        cached = head.HeadStepRunner(pack, protos, B, C, mode)
+        assert cached.hw.num_frozen == T - 1
+        plain = head.HeadStepRunner(pack, protos, B, C, mode)
+        plain.hw.num_frozen = 0
+        for r in (cached, plain):
+            r.step(b["image"], b["text"], b["state"], tc, cots)
+        torch.cuda.synchronize()
+        assert torch.equal(cached.outs, plain.outs) and torch.equal(cached.flat_grads, plain.flat_grads)
+        assert torch.equal(cached.logits, plain.logits)
+        params["projs_img.0.MLP.0.weight"].mul_(1.5)          # e.g. load_state_dict into a frozen projection
+        for r in (cached, plain):
+            r.step(b["image"], b["text"], b["state"], tc, cots)
+        torch.cuda.synchronize()
+        assert torch.equal(cached.outs, plain.outs) and torch.equal(cached.flat_grads, plain.flat_grads)
+        params["projs_img.0.MLP.0.weight"].div_(1.5)
+    params["projs_text.1.MLP.0.bias"].requires_grad_(True)     # an old task that is trainable: no caching
+    assert head.HeadStepRunner(pack, protos, B, C, head.MODE_F32).hw.num_frozen == 0
