@@ -272,7 +272,7 @@ struct SideStream {                 // one lane: a stream and its fork / join ev
     cudaEvent_t fork = nullptr, join = nullptr;
 };
 struct SideLanes {
-    SideStream lane[2];             // 0: independent compute kernels, 1: the gradient exchange
+    SideStream lane[3];             // 0: independent compute kernels, 1: the gradient exchange, 2: classification logits
     bool tried = false, ok = false;
 };
 static SideStream* side_stream(int lane) {
@@ -286,7 +286,7 @@ static SideStream* side_stream(int lane) {
     if (!t.tried) {
         t.tried = true;
         t.ok = true;
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             SideStream& s = t.lane[i];
             if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -422,7 +422,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         TEAM_LAUNCH(fill_prompt_rows_kernel, fill_rows, 128, 0, fst, plist(hw->prompts, hw->num_tasks), hw->prompts_per_task > 0 ? hw->prompts_per_task : 1, d.C, d.Ns, d.Nsp, w.S.f, w.S.h);
     }
     if ((rc = prologue(cx, hw, 3, image_feat, text_feat, want_cls ? text_cls : nullptr, batch))) return rc;
-    if ((rc = join_side(cx.st, side))) return rc;
+    SideStream* fill_side = side;        // joined before wave 2 (the first reader of the prompt rows): wave 1 chains straight behind the prologue
     Wave wv;
     const Mat none{nullptr, nullptr, 0};
     auto fonly = [](float* p, int64_t ld) { return Mat{p, nullptr, ld}; };
@@ -445,6 +445,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         norm_add(nl, blocks, w.Xo.f, w.Xo.f, w.Xo.h, w.invo, d.B2);
         TEAM_LAUNCH(rows_normalize_kernel, blocks, 256, 0, cx.st, nl);
     }
+    if ((rc = join_side(cx.st, fill_side))) return rc;
     // ---- wave 2: q/k/v of the step rows and of the own rows against the packed [3D, D] weight
     seg(wv.add(d.Nsp, 3 * D, 0.f, honly(w.QKVs)), false, w.S, false, w.Wqkv, D);
     seg(wv.add(d.B2, 3 * D, 0.f, honly(w.QKVo)), false, w.Xo, false, w.Wqkv, D);
@@ -484,9 +485,15 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     // the own-row outputs and the classification logits do not depend on the table-query rows: side stream
     const cudaStream_t sst = fork_side(cx.st, &side);
     TEAM_LAUNCH(ln_own_fwd_kernel, (d.B2 + 7) / 8, 256, 0, sst, d, w.Ybo, w.aown, w.VFo.f, w.Xo.f, hw->b_fc, hw->ln_g, hw->ln_b, out_image, out_text);
+    // forward_for_classification (models/proof.py:519-536; image rows are already normalised in Xo): a third lane beside the
+    // own-row LayerNorm and the table rows.  Measured alternatives (tools/timeline.py, profiles/r2z_timeline_*): behind
+    // ln_own_fwd on the same lane the pair outlasts the table rows by 5 us; forked right after the normalisation (its inputs
+    // are ready there, 45 us of slack) it slows GEMM waves 2 and 3 by more than it saves (0.194 vs 0.189 ms per step), at the
+    // lowest stream priority as well - the kernels of one step compete for the same SMs and L2 bandwidth.
+    SideStream* cls_side = nullptr;
     if (want_cls) {
-        // forward_for_classification (models/proof.py:519-536): image rows are already normalised in Xo
-        if ((rc = cosine_logits_launch(sst, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
+        const cudaStream_t cst = fork_side(cx.st, &cls_side, 2);
+        if ((rc = cosine_logits_launch(cst, w.Xo.f, d.B, w.Zc, d.Tc, nullptr, cls_logits, cls_argmax))) return rc;
     }
     if (use_table_gram(d)) {      // Gram formulation: scalar LayerNorm algebra per (sample, row), vector outputs as coefficient sums
         if ((rc = join_side(cx.st, gram_side))) return rc;          // table_gram_prep_kernel
@@ -504,6 +511,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         TEAM_LAUNCH(table_rows_fwd_kernel, tgrid, TQ_WARPS * 32, 0, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
     }
     if ((rc = join_side(cx.st, side))) return rc;
+    if ((rc = join_side(cx.st, cls_side))) return rc;
     (void)none;
     return TEAM_OK;
 }
@@ -531,12 +539,13 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
     int ogrid = (d.B + 7) / 8;
     if (ogrid > NUM_SMS) ogrid = NUM_SMS;
     SideStream* own_side = nullptr;
-    {
-        const cudaStream_t ost = fork_side(cx.st, &own_side);
-        TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, ost, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo_own, (__nv_bfloat16*)nullptr, w.own_partials, gr->g_own_rows);
-        // own x own score gradients: initial values of the dQ / dK rows (the GEMMs of waves 5 and 7 accumulate on top)
-        TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, ost, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, (__nv_bfloat16*)nullptr);
-    }
+    // (Enqueueing the table-row kernel first - it needs a whole register file per CTA and cannot share an SM with these two -
+    // was measured: it then runs alone in 26 us, but the own-row kernels are squeezed onto the 20 remaining SMs and finish
+    // later than before: 0.1948 vs 0.1885 ms per step, tools/timeline.py.)
+    const cudaStream_t ost = fork_side(cx.st, &own_side);
+    TEAM_LAUNCH(ln_own_bwd_kernel, ogrid, 256, 0, ost, d, w.Ybo, w.Xo.f, w.VFo.f, w.aown, hw->b_fc, hw->ln_g, hw->ln_b, g_image, g_text, w.dYo.f, w.dYo.h, w.dXo.f, w.rowdot, w.dsown, w.dVFo_own, (__nv_bfloat16*)nullptr, w.own_partials, gr->g_own_rows);
+    // own x own score gradients: initial values of the dQ / dK rows (the GEMMs of waves 5 and 7 accumulate on top)
+    TEAM_LAUNCH(own_own_bwd_kernel, (d.B + 7) / 8, 256, 0, ost, d, w.QKVo.f, bf ? w.QKVo.h : nullptr, w.dsown, w.dQKVo.f, (__nv_bfloat16*)nullptr);
     // ---- table-query rows (prototype / state outputs)
     int tgrid;
     if (use_table_gram(d)) {      // Gram formulation (head_table_gram.cuh); needs W0 / GT / xs / xst / RS of the matching forward
