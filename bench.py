@@ -408,6 +408,44 @@ def run_team(a):
                 "how": f"CUDA events around each launch of the kernel on the launching stream, {nprof} extra eager steps "
                        "after the timed region"}
 
+    # ---- the same kernel INSIDE a graph replay: in-kernel globaltimer stamps (team_gemm_debug_stamps) of a graph captured
+    # with the stamp buffer attached.  Span of a launch = first CTA past its dependency wait -> last CTA done, i.e. without the
+    # launch latency and the broken PDL overlap that the event pair around an eager launch adds.  Reported beside the event
+    # numbers (which stay the contract's `achieved`), not instead of them.
+    if roof is not None and dom == 1 and graphs is not None:
+        try:
+            L.team_gemm_debug_stamps.argtypes = [ctypes.c_void_p]
+            dbg = torch.zeros((32, 1024, 16), dtype=torch.int64, device=dev)
+            with torch.cuda.stream(stream):
+                L.team_gemm_debug_stamps(dbg.data_ptr())
+                gs = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gs, stream=stream):
+                    runner.step(imgs[0], txts[0], sids[0], text_cls, cots[0])
+                L.team_gemm_debug_stamps(None)
+                spans = []
+                for rep in range(5):
+                    for j in range(3):
+                        step(j + 1)                     # ordinary replays around it, as in the timed region
+                    dbg.zero_()
+                    gs.replay()
+                    torch.cuda.synchronize()
+                    dcpu = dbg.cpu()
+                    for l in range(32):
+                        x = dcpu[l]
+                        x = x[(x[:, 7] > 0) & (x[:, 2] > 0)]          # CTAs that ran a tile (cluster padding CTAs leave no end stamp)
+                        if x.shape[0]:
+                            spans.append(float(int(x[:, 7].max()) - int(x[:, 2].min())) * 1e-3)
+                del gs
+            if spans and world == 1:
+                us = sum(spans) / len(spans)
+                fl = roof["algorithmic_flops_per_launch"]
+                roof["in_graph"] = {"avg_launch_us": us, "launches_timed": len(spans), "achieved": fl / us / 1e6, "frac": fl / us / 1e6 / roof["peak"],
+                                    "share_of_step": us * (len(spans) / 5) / 1e3 / ms_per_step,
+                                    "how": "in-kernel globaltimer stamps of a graph replay: first CTA past griddepcontrol.wait -> last CTA "
+                                           "done, mean over the GEMM launches of 5 replays"}
+        except Exception as exc:
+            roof["in_graph"] = {"error": str(exc)[:200]}
+
     # ---- end to end through the public API (head.HostBatchPipeline): every step copies its batch from pinned
     # host memory (copy stream, double-buffered), replays the fwd+bwd graph, all-reduces the gradient bucket
     # (N > 1) and copies the step's predictions back to the host, where they are compared with the labels
