@@ -266,7 +266,7 @@ int team_herding_select(const float* feats, const int64_t* group_ptr, int32_t n_
 
 /* ------------------------------------------------------------------ standalone MultiHeadAttention
  * Replaces: MultiHeadAttention.forward (+ ScaledDotProductAttention)   convs/projections.py:64-87, :31-38
- *           (n_head = 1, d_model = d_k = d_v = 512; eval mode / dropout p = 0) and its autograd backward.
+ *           (n_head = 1, d_model = d_k = d_v = 512; eval mode and train mode with dropout) and its autograd backward.
  * out[B,Lq,512] = LayerNorm(fc(softmax(Q K^T / sqrt(512)) V) + q_in), Q = q_in Wq^T, K = k_in Wk^T, V = v_in Wv^T.
  * q_in [B,Lq,512], k_in / v_in [B,Lk,512] fp32 row-major; weights as nn.Linear stores them ([out,in]).
  * The forward saves what the backward needs in `workspace` (team_mha_workspace_bytes), which must be handed to
@@ -276,15 +276,22 @@ int team_herding_select(const float* feats, const int64_t* group_ptr, int32_t n_
  * Used by the differentiable PROOF fusion (utils/inc_net.py:436-492) and the class-text form of forward_tri_modal
  * (:544-547, :573-576); the learner's per-batch path runs the factorised kernels of team_head_tri_fwd instead. */
 size_t team_mha_workspace_bytes(int64_t batch, int64_t len_q, int64_t len_k);
+/* Train mode: dropout_p > 0 applies the block's two dropouts (attention probabilities, fc output; nn.Dropout(0.1) in the
+ * reference, convs/projections.py:28, :62, :84) with counter-based Philox4x32-10 masks: element i of the probabilities is
+ * kept iff philox(key = seed, counter = (i / 4, offset))[i % 4] >= p * 2^32, the fc output uses offset + 1; kept values are
+ * scaled by 1 / (1 - p).  The backward regenerates the masks from the same (dropout_p, seed, offset).  A caller advances
+ * `offset` by 2 per forward call.  dropout_p = 0: eval mode.  team_dropout_keep_mask writes the 0 / 1 mask of n elements. */
 int team_mha_fwd(int mode, int64_t batch, int64_t len_q, int64_t len_k, const float* q_in, const float* k_in,
                  const float* v_in, const float* w_q, const float* w_k, const float* w_v, const float* w_fc,
-                 const float* b_fc, const float* ln_g, const float* ln_b, float* out, void* workspace,
-                 size_t workspace_bytes, void* stream);
+                 const float* b_fc, const float* ln_g, const float* ln_b, float dropout_p, uint64_t seed,
+                 uint64_t offset, float* out, void* workspace, size_t workspace_bytes, void* stream);
 int team_mha_bwd(int mode, int64_t batch, int64_t len_q, int64_t len_k, const float* q_in, const float* k_in,
                  const float* v_in, const float* w_q, const float* w_k, const float* w_v, const float* w_fc,
-                 const float* ln_g, const float* g_out, float* g_q_in, float* g_k_in, float* g_v_in,
-                 float* g_w_q, float* g_w_k, float* g_w_v, float* g_w_fc, float* g_b_fc, float* g_ln_g,
-                 float* g_ln_b, void* workspace, size_t workspace_bytes, void* stream);
+                 const float* ln_g, float dropout_p, uint64_t seed, uint64_t offset, const float* g_out,
+                 float* g_q_in, float* g_k_in, float* g_v_in, float* g_w_q, float* g_w_k, float* g_w_v,
+                 float* g_w_fc, float* g_b_fc, float* g_ln_g, float* g_ln_b, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int team_dropout_keep_mask(unsigned char* keep, int64_t n, float dropout_p, uint64_t seed, uint64_t offset, void* stream);
 /* torch.mean over the middle dimension of x[outer][red][inner] -> out[outer][inner] (serial fixed-order sums: the batch
  * means of Proof_Net.forward, utils/inc_net.py:458-459, and the row means of forward_tri_modal, :573-576) and its
  * backward dx[o][r][i] = g[o][i] / red. */

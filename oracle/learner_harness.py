@@ -133,7 +133,7 @@ def _reseed_by_name(module: nn.Module, seed: int):
 
 
 def run(device: torch.device, swap: bool, tasks: int = 2, epochs: int = 2, seed: int = 7, team_mode: str = "f32",
-        swap_herding: bool = False):
+        swap_herding: bool = False, keep_dropout: bool = False):
     """Returns a dict of numpy arrays: accuracy after every task, prototypes, per-state prototypes, distance factors
     and the trained parameters."""
     ref_loader.install_stubs()
@@ -182,7 +182,7 @@ def run(device: torch.device, swap: bool, tasks: int = 2, epochs: int = 2, seed:
             for t in range(tasks):
                 torch.manual_seed(seed + 100 * (t + 1))
                 for m in learner._network.modules():       # dropout off in both runs (see module docstring)
-                    if isinstance(m, nn.Dropout):
+                    if isinstance(m, nn.Dropout) and not keep_dropout:
                         m.p = 0.0
                 learner.incremental_train(dm)
                 accs.append(float(learner._compute_accuracy(learner._network, learner.test_loader)))

@@ -85,18 +85,56 @@ def context_prompts(p: Params) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- a6
-def mha(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, p: Params) -> torch.Tensor:
-    """MultiHeadAttention(n_head=1).forward(q, k, v) in eval mode:
-    convs/projections.py:64-87 with ScaledDotProductAttention :31-38
-    (temperature sqrt(512) :57; the discarded log_softmax :34 is omitted)."""
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123):
+    multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key increments 0x9E3779B9 / 0xBB67AE85, ten rounds.  Counter words as numpy
+    uint64 arrays holding 32-bit values; returns the four output words.  Pinned by the Random123 known-answer vectors
+    (tests/test_oracle_golden.py)."""
+    import numpy as np
+    M32 = np.uint64(0xFFFFFFFF)
+    c = [np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0 & 0xFFFFFFFF), np.uint64(k1 & 0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & M32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & M32]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & M32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & M32
+    return c
+
+
+def philox_keep_mask(n: int, dropout_p: float, seed: int, offset: int):
+    """0 / 1 keep mask of n elements as the library defines it (include/team_b200.h: team_mha_fwd): element i is kept iff
+    philox4x32_10(counter = (i // 4 low, i // 4 high, offset low, offset high), key = (seed low, seed high))[i % 4]
+    >= dropout_p * 2**32."""
+    import numpy as np
+    nb = (n + 3) // 4
+    blk = np.arange(nb, dtype=np.uint64)
+    c = philox4x32_10(blk & np.uint64(0xFFFFFFFF), blk >> np.uint64(32), np.full(nb, offset & 0xFFFFFFFF, np.uint64),
+                      np.full(nb, (offset >> 32) & 0xFFFFFFFF, np.uint64), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    out = np.stack(c, axis=1).reshape(-1)[:n]
+    thr = min(int(dropout_p * 4294967296.0), 4294967295)
+    return torch.from_numpy((out >= np.uint64(thr)).astype(np.float64))
+
+
+def mha(q_in: torch.Tensor, k_in: torch.Tensor, v_in: torch.Tensor, p: Params, drop=None) -> torch.Tensor:
+    """MultiHeadAttention(n_head=1).forward(q, k, v): convs/projections.py:64-87 with ScaledDotProductAttention :31-38
+    (temperature sqrt(512) :57; the discarded log_softmax :34 is omitted).  ``drop`` = None: eval mode (both nn.Dropout
+    are the identity); ``drop`` = (p, seed, offset): train mode - the reference's two dropouts (attention probabilities
+    :35, fc output :84) with EXPLICIT masks (philox_keep_mask; torch's own mask stream is not reproducible)."""
     d = q_in.shape[-1]
     q = F.linear(q_in, p["sel_attn.w_qs.weight"])
     k = F.linear(k_in, p["sel_attn.w_ks.weight"])
     v = F.linear(v_in, p["sel_attn.w_vs.weight"])
     attn = torch.bmm(q, k.transpose(1, 2)) / float(d ** 0.5)
     attn = torch.softmax(attn, dim=2)
+    if drop is not None:
+        pd, seed, offset = drop
+        attn = attn * philox_keep_mask(attn.numel(), pd, seed, offset).reshape(attn.shape).to(attn.dtype) / (1.0 - pd)
     out = torch.bmm(attn, v)
     out = F.linear(out, p["sel_attn.fc.weight"], p["sel_attn.fc.bias"])
+    if drop is not None:
+        out = out * philox_keep_mask(out.numel(), pd, seed, offset + 1).reshape(out.shape).to(out.dtype) / (1.0 - pd)
     return F.layer_norm(out + q_in, (d,), p["sel_attn.layer_norm.weight"],
                         p["sel_attn.layer_norm.bias"], LN_EPS)
 

@@ -171,9 +171,11 @@ def _declare(lib):
         lib.team_mha_workspace_bytes.restype = sz
         lib.team_mha_workspace_bytes.argtypes = [i64, i64, i64]
         lib.team_mha_fwd.restype = i32
-        lib.team_mha_fwd.argtypes = [i32, i64, i64, i64] + [vp] * 11 + [vp, sz, vp]
+        lib.team_mha_fwd.argtypes = [i32, i64, i64, i64] + [vp] * 10 + [C.c_float, C.c_uint64, C.c_uint64] + [vp, vp, sz, vp]
         lib.team_mha_bwd.restype = i32
-        lib.team_mha_bwd.argtypes = [i32, i64, i64, i64] + [vp] * 19 + [vp, sz, vp]
+        lib.team_mha_bwd.argtypes = [i32, i64, i64, i64] + [vp] * 8 + [C.c_float, C.c_uint64, C.c_uint64] + [vp] * 11 + [vp, sz, vp]
+        lib.team_dropout_keep_mask.restype = i32
+        lib.team_dropout_keep_mask.argtypes = [vp, i64, C.c_float, C.c_uint64, C.c_uint64, vp]
         lib.team_mean_mid.restype = i32
         lib.team_mean_mid.argtypes = [vp, vp, i64, i64, i64, vp]
         lib.team_mean_mid_bwd.restype = i32

@@ -327,14 +327,14 @@ static bool use_table2(const HeadDims& d) {
 }
 
 // Gram formulation of the table-query rows (head_table_gram.cuh) for batches of at least TEAM_TABLE_GRAM_MIN_B samples
-// (default 32768).  Measured (profiles/EXPERIMENTS.md round 2): its kernels are 1.5 - 1.9x faster than the second
+// (default 16384).  Measured (profiles/EXPERIMENTS.md round 2): its kernels are 1.5 - 1.9x faster than the second
 // generation in isolation at 65 536 samples, but the step gains only 2 % there (both generations fill the register file,
 // so the side-lane kernels no longer overlap) and loses below ~16 384 samples, where its two extra step-level launches
 // sit on the critical path.  TEAM_TABLE_V2 / TEAM_TABLE_V1 force the older kernels.  Read per call (tests flip it).
 static bool use_table_gram(const HeadDims& d) {
     if (getenv("TEAM_TABLE_V2") != nullptr || getenv("TEAM_TABLE_V1") != nullptr) return false;
     const char* e = getenv("TEAM_TABLE_GRAM_MIN_B");
-    const int min_b = e != nullptr ? atoi(e) : 32768;
+    const int min_b = e != nullptr ? atoi(e) : 16384;
     return d.B >= min_b && table_gram_supported(d);
 }
 // warps per CTA of the Gram kernels (TEAM_TG_FW / TEAM_TG_BW override, A/B runs)

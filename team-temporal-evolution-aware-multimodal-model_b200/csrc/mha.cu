@@ -7,7 +7,7 @@
 //   Q = q_in Wq^T, K = k_in Wk^T, V = v_in Wv^T            dense projections: tcgen05 GEMM (mode BF16) / fp32 FFMA GEMM
 //   A = softmax(Q K^T / sqrt(512))  per sample              batched fp32 GEMM + warp-per-row softmax (log_softmax of the
 //   O = A V                                                 reference is discarded by its caller)
-//   out = LayerNorm(O Wfc^T + b_fc + q_in)                  dropout = identity (eval mode / p = 0)
+//   out = LayerNorm(drop(O Wfc^T + b_fc) + q_in)           with A := drop(A) in train mode: counter-based masks, see Philox below
 //
 // The backward is the hand-written VJP; every batch reduction (weight gradients through split-K GEMMs, bias / LayerNorm
 // gradients through per-CTA partials folded in CTA order) has a fixed order, so results are run-to-run reproducible.
@@ -16,6 +16,38 @@
 #include "gemm_tc.cuh"
 
 namespace team {
+
+// ------------------------------------------------------------------------------------------------ dropout masks
+// Train-mode dropout of the block (attention probabilities and fc output, p = 0.1 in the reference: convs/projections.py:28,
+// :62, :84) as COUNTER-BASED masks: element i of a tensor is kept iff philox4x32-10(key = seed, counter = (i / 4, offset))
+// [i % 4] * 2^-32 >= p.  Nothing is stored: the backward regenerates the mask from the same (seed, offset).  The stream is
+// this library's own (torch's Philox offsets depend on its launch geometry and cannot be reproduced), so parity in train
+// mode is checked against the reference math with the SAME masks (oracle/team_oracle.py:philox_keep_mask) and statistically.
+struct Philox {
+    uint32_t k0, k1;
+    uint64_t offset;
+};
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+// the four 32-bit outputs of counter block `blk`
+__host__ __device__ __forceinline__ void philox4(const Philox& g, uint64_t blk, uint32_t (&c)[4]) {
+    c[0] = (uint32_t)blk; c[1] = (uint32_t)(blk >> 32); c[2] = (uint32_t)g.offset; c[3] = (uint32_t)(g.offset >> 32);
+    uint32_t k0 = g.k0, k1 = g.k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// keep-scale of element idx: 0 (dropped) or 1 / (1 - p); thr = p * 2^32
+__device__ __forceinline__ float drop_scale(const Philox& g, uint64_t idx, uint32_t thr, float inv_keep) {
+    uint32_t c[4];
+    philox4(g, idx >> 2, c);
+    return c[idx & 3] >= thr ? inv_keep : 0.f;
+}
 
 // ------------------------------------------------------------------------------------------------ batched fp32 GEMM
 // C_b[M,N] = alpha * op(A_b) op(B_b) (+ beta * C_b), b = blockIdx.z; TA: A stored [K,M]; TB: B stored [N,K].
@@ -120,7 +152,9 @@ static int bgemm(cudaStream_t st, bool ta, bool tb, int64_t batch, int M, int N,
 
 // ------------------------------------------------------------------------------------------------ row kernels
 // softmax over the last dimension, in place, warp per row (any row length)
-__global__ void __launch_bounds__(256) mha_softmax_kernel(float* __restrict__ S, int64_t rows, int len) {
+// Ad (optional): the probabilities after attention dropout (what multiplies V); S keeps the softmax itself (its backward needs it)
+__global__ void __launch_bounds__(256) mha_softmax_kernel(float* __restrict__ S, int64_t rows, int len, float* __restrict__ Ad,
+                                                         Philox rng, uint32_t thr, float inv_keep) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -134,10 +168,16 @@ __global__ void __launch_bounds__(256) mha_softmax_kernel(float* __restrict__ S,
     for (int i = lane; i < len; i += 32) { const float e = __expf(p[i] - m); p[i] = e; z += e; }
     z = warp_sum(z);
     const float inv = 1.f / z;
-    for (int i = lane; i < len; i += 32) p[i] *= inv;
+    for (int i = lane; i < len; i += 32) {
+        const float a = p[i] * inv;
+        p[i] = a;
+        if (Ad != nullptr) Ad[row * len + i] = a * drop_scale(rng, (uint64_t)(row * len + i), thr, inv_keep);
+    }
 }
 // dS = A .* (dA - sum_j dA_j A_j) * scale, in place on dA
-__global__ void __launch_bounds__(256) mha_softmax_bwd_kernel(const float* __restrict__ A, float* __restrict__ dA, int64_t rows, int len, float scale) {
+// (with attention dropout dA arrives as the gradient of the DROPPED probabilities: the mask is regenerated and applied first)
+__global__ void __launch_bounds__(256) mha_softmax_bwd_kernel(const float* __restrict__ A, float* __restrict__ dA, int64_t rows, int len, float scale,
+                                                             int drop, Philox rng, uint32_t thr, float inv_keep) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -146,7 +186,11 @@ __global__ void __launch_bounds__(256) mha_softmax_bwd_kernel(const float* __res
     const float* a = A + row * len;
     float* g = dA + row * len;
     float dot = 0.f;
-    for (int i = lane; i < len; i += 32) dot = fmaf(a[i], g[i], dot);
+    for (int i = lane; i < len; i += 32) {
+        float gi = g[i];
+        if (drop) { gi *= drop_scale(rng, (uint64_t)(row * len + i), thr, inv_keep); g[i] = gi; }
+        dot = fmaf(a[i], gi, dot);
+    }
     dot = warp_sum(dot);
     for (int i = lane; i < len; i += 32) g[i] = a[i] * (g[i] - dot) * scale;
 }
@@ -154,7 +198,7 @@ __global__ void __launch_bounds__(256) mha_softmax_bwd_kernel(const float* __res
 // out = LayerNorm(Y + R) * gamma + beta; Y is overwritten with xhat (what the backward needs), rstd per row
 __global__ void __launch_bounds__(256)
 mha_add_ln_fwd_kernel(float* __restrict__ Y, const float* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float* __restrict__ out, float* __restrict__ rstd, int64_t rows) {
+                      float* __restrict__ out, float* __restrict__ rstd, int64_t rows, int drop, Philox rng, uint32_t thr, float inv_keep) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -165,7 +209,14 @@ mha_add_ln_fwd_kernel(float* __restrict__ Y, const float* __restrict__ R, const 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int c = 4 * (lane + 32 * i);
-        const float4 y = *reinterpret_cast<const float4*>(Y + row * D + c), r = *reinterpret_cast<const float4*>(R + row * D + c);
+        float4 y = *reinterpret_cast<const float4*>(Y + row * D + c);
+        const float4 r = *reinterpret_cast<const float4*>(R + row * D + c);
+        if (drop) {                                        // dropout(fc(output)), convs/projections.py:84: one counter block per float4
+            uint32_t q[4];
+            philox4(rng, (uint64_t)(row * D + c) >> 2, q);
+            y.x *= q[0] >= thr ? inv_keep : 0.f; y.y *= q[1] >= thr ? inv_keep : 0.f;
+            y.z *= q[2] >= thr ? inv_keep : 0.f; y.w *= q[3] >= thr ? inv_keep : 0.f;
+        }
         v[i] = make_float4(y.x + r.x, y.y + r.y, y.z + r.z, y.w + r.w);
         s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
@@ -193,7 +244,8 @@ mha_add_ln_fwd_kernel(float* __restrict__ Y, const float* __restrict__ R, const 
 constexpr int MHA_LNB_WARPS = 8;
 __global__ void __launch_bounds__(MHA_LNB_WARPS * 32)
 mha_ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ XH, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                  float* __restrict__ dPre, float* __restrict__ partial, int64_t rows, int rows_per_cta) {
+                  float* __restrict__ dPre, float* __restrict__ partial, int64_t rows, int rows_per_cta,
+                  float* __restrict__ dFc, Philox rng, uint32_t thr, float inv_keep) {
     __shared__ float red[MHA_LNB_WARPS][3][D];
     pdl_trigger();
     pdl_wait();
@@ -230,7 +282,15 @@ mha_ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ XH, co
             const float4 o = make_float4(rs * (dy[i].x - s1 - xh[i].x * s2), rs * (dy[i].y - s1 - xh[i].y * s2),
                                          rs * (dy[i].z - s1 - xh[i].z * s2), rs * (dy[i].w - s1 - xh[i].w * s2));
             *reinterpret_cast<float4*>(dPre + row * D + c) = o;
-            ap[i].x += o.x; ap[i].y += o.y; ap[i].z += o.z; ap[i].w += o.w;
+            float4 f = o;
+            if (dFc != nullptr) {                          // gradient of the fc output through its dropout mask (dPre itself is the residual's)
+                uint32_t q[4];
+                philox4(rng, (uint64_t)(row * D + c) >> 2, q);
+                f.x *= q[0] >= thr ? inv_keep : 0.f; f.y *= q[1] >= thr ? inv_keep : 0.f;
+                f.z *= q[2] >= thr ? inv_keep : 0.f; f.w *= q[3] >= thr ? inv_keep : 0.f;
+                *reinterpret_cast<float4*>(dFc + row * D + c) = f;
+            }
+            ap[i].x += f.x; ap[i].y += f.y; ap[i].z += f.z; ap[i].w += f.w;
         }
     }
 #pragma unroll
@@ -320,8 +380,8 @@ static int dense(const Dense& e, bool ta, bool tb, int64_t M, int64_t N, int64_t
 
 struct MhaPlan {
     int64_t Rq, Rk;
-    float *Q, *K, *V, *A, *O, *XH, *rstd;                 // saved by the forward
-    float *dPre, *dO, *dA, *dQ, *dK, *dV, *partial;       // backward scratch
+    float *Q, *K, *V, *A, *Ad, *O, *XH, *rstd;            // saved by the forward (Ad: probabilities after attention dropout)
+    float *dPre, *dFc, *dO, *dA, *dQ, *dK, *dV, *partial; // backward scratch (dFc: dPre through the fc-output dropout mask)
     __nv_bfloat16 *ha, *hb;
     void* gws; size_t gws_bytes;
     int ln_ctas, ln_rows_per_cta;
@@ -334,8 +394,8 @@ static MhaPlan mha_plan(int64_t B, int64_t Lq, int64_t Lk, void* base) {
     auto take = [&](size_t bytes) { void* r = base ? (char*)base + off : nullptr; off += align_up(bytes, 256); return r; };
     const size_t fq = (size_t)p.Rq * D * 4, fk = (size_t)p.Rk * D * 4, fa = (size_t)B * Lq * Lk * 4;
     p.Q = (float*)take(fq); p.K = (float*)take(fk); p.V = (float*)take(fk);
-    p.A = (float*)take(fa); p.O = (float*)take(fq); p.XH = (float*)take(fq); p.rstd = (float*)take((size_t)p.Rq * 4);
-    p.dPre = (float*)take(fq); p.dO = (float*)take(fq); p.dA = (float*)take(fa);
+    p.A = (float*)take(fa); p.Ad = (float*)take(fa); p.O = (float*)take(fq); p.XH = (float*)take(fq); p.rstd = (float*)take((size_t)p.Rq * 4);
+    p.dPre = (float*)take(fq); p.dFc = (float*)take(fq); p.dO = (float*)take(fq); p.dA = (float*)take(fa);
     p.dQ = (float*)take(fq); p.dK = (float*)take(fk); p.dV = (float*)take(fk);
     int64_t ctas = (p.Rq + 63) / 64;
     if (ctas > 4 * NUM_SMS) ctas = 4 * NUM_SMS;
@@ -353,6 +413,23 @@ static MhaPlan mha_plan(int64_t B, int64_t Lq, int64_t Lk, void* base) {
     p.gws = take(p.gws_bytes);
     p.total = off;
     return p;
+}
+
+struct MhaDrop {
+    bool on;
+    Philox attn, fc;
+    uint32_t thr;
+    float inv_keep;
+};
+static MhaDrop mha_drop(float p, uint64_t seed, uint64_t offset) {
+    MhaDrop d;
+    d.on = p > 0.f;
+    d.attn = Philox{(uint32_t)seed, (uint32_t)(seed >> 32), offset};
+    d.fc = Philox{(uint32_t)seed, (uint32_t)(seed >> 32), offset + 1};
+    const double t = (double)p * 4294967296.0;
+    d.thr = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    d.inv_keep = p < 1.f ? 1.f / (1.f - p) : 0.f;
+    return d;
 }
 
 static int mha_check(int mode, int64_t B, int64_t Lq, int64_t Lk) {
@@ -373,11 +450,13 @@ extern "C" size_t team_mha_workspace_bytes(int64_t batch, int64_t len_q, int64_t
 
 extern "C" int team_mha_fwd(int mode, int64_t batch, int64_t len_q, int64_t len_k, const float* q_in, const float* k_in,
                             const float* v_in, const float* w_q, const float* w_k, const float* w_v, const float* w_fc,
-                            const float* b_fc, const float* ln_g, const float* ln_b, float* out, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            const float* b_fc, const float* ln_g, const float* ln_b, float dropout_p, uint64_t seed,
+                            uint64_t offset, float* out, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = mha_check(mode, batch, len_q, len_k);
     if (rc) return rc;
     TEAM_REQUIRE(q_in && k_in && v_in && w_q && w_k && w_v && w_fc && b_fc && ln_g && ln_b && out, "mha fwd: null pointer");
+    TEAM_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mha fwd: dropout_p %g outside [0, 1)", (double)dropout_p);
+    const MhaDrop dr = mha_drop(dropout_p, seed, offset);
     TEAM_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mha: workspace must be 256-byte aligned");
     const MhaPlan p = mha_plan(batch, len_q, len_k, workspace);
     if (workspace_bytes < p.total) { set_error("mha fwd: workspace %zu < %zu bytes", workspace_bytes, p.total); return TEAM_EWORKSPACE; }
@@ -390,21 +469,25 @@ extern "C" int team_mha_fwd(int mode, int64_t batch, int64_t len_q, int64_t len_
     if ((rc = dense(e, false, true, p.Rk, D, D, v_in, D, w_v, D, 0.f, p.V, D, nullptr))) return rc;
     // scores / temperature (temperature = sqrt(d_k), convs/projections.py:53), softmax over the keys, A V
     if ((rc = bgemm(st, false, true, batch, Lq, Lk, D, 1.f / sqrtf((float)D), p.Q, D, (int64_t)Lq * D, p.K, D, (int64_t)Lk * D, 0.f, p.A, Lk, (int64_t)Lq * Lk))) return rc;
-    TEAM_LAUNCH(mha_softmax_kernel, (p.Rq + 7) / 8, 256, 0, st, p.A, p.Rq, Lk);
-    if ((rc = bgemm(st, false, false, batch, Lq, D, Lk, 1.f, p.A, Lk, (int64_t)Lq * Lk, p.V, D, (int64_t)Lk * D, 0.f, p.O, D, (int64_t)Lq * D))) return rc;
+    TEAM_LAUNCH(mha_softmax_kernel, (p.Rq + 7) / 8, 256, 0, st, p.A, p.Rq, Lk, dr.on ? p.Ad : (float*)nullptr, dr.attn, dr.thr, dr.inv_keep);
+    const float* Ause = dr.on ? p.Ad : p.A;
+    if ((rc = bgemm(st, false, false, batch, Lq, D, Lk, 1.f, Ause, Lk, (int64_t)Lq * Lk, p.V, D, (int64_t)Lk * D, 0.f, p.O, D, (int64_t)Lq * D))) return rc;
     if ((rc = dense(e, false, true, p.Rq, D, D, p.O, D, w_fc, D, 0.f, p.XH, D, b_fc))) return rc;
-    TEAM_LAUNCH(mha_add_ln_fwd_kernel, (p.Rq + 7) / 8, 256, 0, st, p.XH, q_in, ln_g, ln_b, out, p.rstd, p.Rq);
+    TEAM_LAUNCH(mha_add_ln_fwd_kernel, (p.Rq + 7) / 8, 256, 0, st, p.XH, q_in, ln_g, ln_b, out, p.rstd, p.Rq, dr.on ? 1 : 0, dr.fc, dr.thr, dr.inv_keep);
     return TEAM_OK;
 }
 
 // g_* of the inputs may be NULL (not needed); when q_in, k_in and v_in are one tensor the caller adds the three.
 extern "C" int team_mha_bwd(int mode, int64_t batch, int64_t len_q, int64_t len_k, const float* q_in, const float* k_in,
                             const float* v_in, const float* w_q, const float* w_k, const float* w_v, const float* w_fc,
-                            const float* ln_g, const float* g_out, float* g_q_in, float* g_k_in, float* g_v_in,
-                            float* g_w_q, float* g_w_k, float* g_w_v, float* g_w_fc, float* g_b_fc, float* g_ln_g,
-                            float* g_ln_b, void* workspace, size_t workspace_bytes, void* stream) {
+                            const float* ln_g, float dropout_p, uint64_t seed, uint64_t offset, const float* g_out,
+                            float* g_q_in, float* g_k_in, float* g_v_in, float* g_w_q, float* g_w_k, float* g_w_v,
+                            float* g_w_fc, float* g_b_fc, float* g_ln_g, float* g_ln_b, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     int rc = mha_check(mode, batch, len_q, len_k);
     if (rc) return rc;
+    TEAM_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mha bwd: dropout_p %g outside [0, 1)", (double)dropout_p);
+    const MhaDrop dr = mha_drop(dropout_p, seed, offset);
     TEAM_REQUIRE(q_in && k_in && v_in && w_q && w_k && w_v && w_fc && ln_g && g_out, "mha bwd: null pointer");
     TEAM_REQUIRE(g_w_q && g_w_k && g_w_v && g_w_fc && g_b_fc && g_ln_g && g_ln_b, "mha bwd: null gradient buffer");
     TEAM_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mha: workspace must be 256-byte aligned");
@@ -415,15 +498,18 @@ extern "C" int team_mha_bwd(int mode, int64_t batch, int64_t len_q, int64_t len_
     if (mode == TEAM_MODE_BF16 && (rc = tc_workspace_init(st, p.gws, p.gws_bytes))) return rc;
     const Dense e{st, mode, p.gws, p.gws_bytes, p.ha, p.hb};
     // LayerNorm backward (+ residual branch), b_fc / gamma / beta gradients
-    TEAM_LAUNCH(mha_ln_bwd_kernel, p.ln_ctas, MHA_LNB_WARPS * 32, 0, st, g_out, p.XH, p.rstd, ln_g, p.dPre, p.partial, p.Rq, p.ln_rows_per_cta);
+    TEAM_LAUNCH(mha_ln_bwd_kernel, p.ln_ctas, MHA_LNB_WARPS * 32, 0, st, g_out, p.XH, p.rstd, ln_g, p.dPre, p.partial, p.Rq, p.ln_rows_per_cta,
+                dr.on ? p.dFc : (float*)nullptr, dr.fc, dr.thr, dr.inv_keep);
     TEAM_LAUNCH(mha_fold_kernel, (3 * D + 255) / 256, 256, 0, st, p.partial, p.ln_ctas, g_ln_g, g_ln_b, g_b_fc);
-    // fc: dWfc = dPre^T O, dO = dPre Wfc
-    if ((rc = dense(e, true, false, D, D, p.Rq, p.dPre, D, p.O, D, 0.f, g_w_fc, D, nullptr))) return rc;
-    if ((rc = dense(e, false, false, p.Rq, D, D, p.dPre, D, w_fc, D, 0.f, p.dO, D, nullptr))) return rc;
+    // fc: dWfc = dFc^T O, dO = dFc Wfc  (dFc = dPre through the fc-output dropout mask; = dPre without dropout)
+    const float* dFc = dr.on ? p.dFc : p.dPre;
+    const float* Ause = dr.on ? p.Ad : p.A;
+    if ((rc = dense(e, true, false, D, D, p.Rq, dFc, D, p.O, D, 0.f, g_w_fc, D, nullptr))) return rc;
+    if ((rc = dense(e, false, false, p.Rq, D, D, dFc, D, w_fc, D, 0.f, p.dO, D, nullptr))) return rc;
     // attention core: dA = dO V^T, dV = A^T dO, dS = softmax', dQ = dS K, dK = dS^T Q  (dS carries 1 / temperature)
     if ((rc = bgemm(st, false, true, batch, Lq, Lk, D, 1.f, p.dO, D, (int64_t)Lq * D, p.V, D, (int64_t)Lk * D, 0.f, p.dA, Lk, (int64_t)Lq * Lk))) return rc;
-    if ((rc = bgemm(st, true, false, batch, Lk, D, Lq, 1.f, p.A, Lk, (int64_t)Lq * Lk, p.dO, D, (int64_t)Lq * D, 0.f, p.dV, D, (int64_t)Lk * D))) return rc;
-    TEAM_LAUNCH(mha_softmax_bwd_kernel, (p.Rq + 7) / 8, 256, 0, st, p.A, p.dA, p.Rq, Lk, 1.f / sqrtf((float)D));
+    if ((rc = bgemm(st, true, false, batch, Lk, D, Lq, 1.f, Ause, Lk, (int64_t)Lq * Lk, p.dO, D, (int64_t)Lq * D, 0.f, p.dV, D, (int64_t)Lk * D))) return rc;
+    TEAM_LAUNCH(mha_softmax_bwd_kernel, (p.Rq + 7) / 8, 256, 0, st, p.A, p.dA, p.Rq, Lk, 1.f / sqrtf((float)D), dr.on ? 1 : 0, dr.attn, dr.thr, dr.inv_keep);
     if ((rc = bgemm(st, false, false, batch, Lq, D, Lk, 1.f, p.dA, Lk, (int64_t)Lq * Lk, p.K, D, (int64_t)Lk * D, 0.f, p.dQ, D, (int64_t)Lq * D))) return rc;
     if ((rc = bgemm(st, true, false, batch, Lk, D, Lq, 1.f, p.dA, Lk, (int64_t)Lq * Lk, p.Q, D, (int64_t)Lq * D, 0.f, p.dK, D, (int64_t)Lk * D))) return rc;
     // projections: dW = dP^T x, dx = dP W
@@ -436,6 +522,24 @@ extern "C" int team_mha_bwd(int mode, int64_t batch, int64_t len_q, int64_t len_
     }
     if (g_k_in != nullptr && (rc = dense(e, false, false, p.Rk, D, D, p.dK, D, w_k, D, 0.f, g_k_in, D, nullptr))) return rc;
     if (g_v_in != nullptr && (rc = dense(e, false, false, p.Rk, D, D, p.dV, D, w_v, D, 0.f, g_v_in, D, nullptr))) return rc;
+    return TEAM_OK;
+}
+
+// keep[i] = 1 / 0 for element i of the tensor masked with (seed, offset) - what the kernels above regenerate on the fly
+// (attention probabilities: offset; fc output: offset + 1).  For the statistical tests of the stream.
+__global__ void __launch_bounds__(256) philox_mask_kernel(unsigned char* __restrict__ keep, int64_t n, Philox rng, uint32_t thr) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c[4];
+    philox4(rng, (uint64_t)i >> 2, c);
+    keep[i] = c[i & 3] >= thr ? 1 : 0;
+}
+extern "C" int team_dropout_keep_mask(unsigned char* keep, int64_t n, float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+    TEAM_REQUIRE(keep != nullptr && n >= 0 && dropout_p >= 0.f && dropout_p < 1.f, "dropout mask: bad arguments");
+    if (n == 0) return TEAM_OK;
+    const MhaDrop dr = mha_drop(dropout_p, seed, offset);
+    philox_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keep, n, dr.attn, dr.thr);
+    TEAM_LAUNCH_CHECK("philox_mask_kernel");
     return TEAM_OK;
 }
 

@@ -328,7 +328,7 @@ class _MhaFn(torch.autograd.Function):
     """MultiHeadAttention.forward (convs/projections.py:64-87) on arbitrary [B, L, 512] tokens: team_mha_fwd / team_mha_bwd."""
 
     @staticmethod
-    def forward(ctx, q, k, v, mode, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b):
+    def forward(ctx, q, k, v, mode, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b, dropout_p=0.0, seed=0, offset=0):
         capi.require_device()
         if not q.is_cuda:
             raise capi.TeamB200Error("sel_attn needs CUDA tensors (no CPU fallback)")
@@ -345,16 +345,17 @@ class _MhaFn(torch.autograd.Function):
         nbytes = L.team_mha_workspace_bytes(B, Lq, Lk)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         out = torch.empty((B, Lq, capi.D), dtype=torch.float32, device=dev)
+        drop = (float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset) & 0xFFFFFFFFFFFFFFFF)
         capi.check(L.team_mha_fwd(mode, B, Lq, Lk, q.data_ptr(), k.data_ptr(), v.data_ptr(), *[p.data_ptr() for p in par],
-                                  out.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()), "team_mha_fwd")
+                                  *drop, out.data_ptr(), ws.data_ptr(), nbytes, _stream_ptr()), "team_mha_fwd")
         ctx.hold = (q, k, v, par, ws)
-        ctx.meta = (mode, B, Lq, Lk, nbytes)
+        ctx.meta = (mode, B, Lq, Lk, nbytes, drop)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         q, k, v, par, ws = ctx.hold
-        mode, B, Lq, Lk, nbytes = ctx.meta
+        mode, B, Lq, Lk, nbytes, drop = ctx.meta
         dev = q.device
         g = _f32c(g_out, dev)
         need = ctx.needs_input_grad
@@ -366,14 +367,25 @@ class _MhaFn(torch.autograd.Function):
         ptr = lambda t: t.data_ptr() if t is not None else None
         w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b = par
         capi.check(capi.lib().team_mha_bwd(mode, B, Lq, Lk, q.data_ptr(), k.data_ptr(), v.data_ptr(), w_q.data_ptr(), w_k.data_ptr(),
-                                           w_v.data_ptr(), w_fc.data_ptr(), ln_g.data_ptr(), g.data_ptr(), ptr(gq), ptr(gk), ptr(gv),
+                                           w_v.data_ptr(), w_fc.data_ptr(), ln_g.data_ptr(), *drop, g.data_ptr(), ptr(gq), ptr(gk), ptr(gv),
                                            *[t.data_ptr() for t in gw], ws.data_ptr(), nbytes, _stream_ptr()), "team_mha_bwd")
-        return (gq, gk, gv, None) + tuple(t if need[4 + i] else None for i, t in enumerate(gw))
+        return (gq, gk, gv, None) + tuple(t if need[4 + i] else None for i, t in enumerate(gw)) + (None, None, None)
 
 
-def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b, mode: int = MODE_F32):
-    """Standalone ``sel_attn(q, k, v)`` (convs/projections.py:64-87; eval mode / dropout p = 0), differentiable."""
-    return _MhaFn.apply(q, k, v, mode, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b)
+def mha(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b, mode: int = MODE_F32,
+        dropout_p: float = 0.0, seed: int = 0, offset: int = 0):
+    """Standalone ``sel_attn(q, k, v)`` (convs/projections.py:64-87), differentiable.  ``dropout_p`` > 0: train mode, the
+    two dropouts of the block with counter-based masks keyed by ``(seed, offset)`` (``offset`` and ``offset + 1`` are used)."""
+    return _MhaFn.apply(q, k, v, mode, w_q, w_k, w_v, w_fc, b_fc, ln_g, ln_b, dropout_p, seed, offset)
+
+
+def dropout_keep_mask(n: int, dropout_p: float, seed: int, offset: int, device="cuda") -> torch.Tensor:
+    """The 0 / 1 keep mask ``team_mha_fwd`` applies to a tensor of ``n`` elements under ``(dropout_p, seed, offset)``."""
+    capi.require_device()
+    keep = torch.empty((n,), dtype=torch.uint8, device=device)
+    capi.check(capi.lib().team_dropout_keep_mask(keep.data_ptr(), n, float(dropout_p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                 int(offset) & 0xFFFFFFFFFFFFFFFF, _stream_ptr()), "team_dropout_keep_mask")
+    return keep
 
 
 class _MeanFn(torch.autograd.Function):

@@ -73,13 +73,18 @@ class MultiHeadAttention(nn.Module):
 
     def forward(self, q, k, v):
         """Standalone call on arbitrary [B, L, 512] tokens (convs/projections.py:64-87): ``team_mha_fwd`` / ``team_mha_bwd``,
-        differentiable.  Inside ``Proof_Net.forward_tri_modal`` the learner's path runs the factorised kernels instead.
-        Dropout is not implemented: p must be 0 in train mode (see ``Proof_Net._check_dropout``)."""
+        differentiable.  Inside ``Proof_Net.forward_tri_modal`` the learner's eval / p = 0 path runs the factorised kernels
+        instead.  Train mode with p > 0: both dropouts of the block (attention probabilities :28, fc output :62, :84) with the
+        library's counter-based masks; seed = torch's seed, offset drawn from torch's CPU generator (so
+        ``torch.manual_seed`` reproduces a run; the stream itself is not torch's)."""
+        p, seed, offset = 0.0, 0, 0
         if self.training and self.dropout.p > 0:
-            raise NotImplementedError("team_b200 evaluates sel_attn without dropout: set dropout.p = 0.0 or call .eval() "
-                                      "(INTEGRATION.md, 'Dropout')")
+            p = float(self.dropout.p)
+            seed = torch.initial_seed()
+            offset = int(torch.randint(0, 2 ** 62, (1,)).item()) * 2
         return head.mha(q, k, v, self.w_qs.weight, self.w_ks.weight, self.w_vs.weight, self.fc.weight, self.fc.bias,
-                        self.layer_norm.weight, self.layer_norm.bias, mode=getattr(self, "team_mode", head.MODE_F32))
+                        self.layer_norm.weight, self.layer_norm.bias, mode=getattr(self, "team_mode", head.MODE_F32),
+                        dropout_p=p, seed=seed, offset=offset)
 
 
 class TemporalGCNBlock(nn.Module):
@@ -286,15 +291,14 @@ class Proof_Net(nn.Module):
         models/base.py:213-238)."""
         return self.convnet.encode_image(x)
 
-    def _check_dropout(self):
+    def _dropout_active(self) -> bool:
         """The reference applies Dropout(0.1) to the attention probabilities and to the fc output in train mode
-        (convs/projections.py:28,62,84; `.train()` at models/proof.py:398).  The fused kernels share the softmax of
-        the step rows between all samples, which a per-(sample, query, key) mask would break, so they implement
-        p = 0 only - and say so instead of silently training without dropout."""
-        if self.training and self.sel_attn.dropout.p > 0:
-            raise NotImplementedError(
-                "team_b200 evaluates sel_attn without dropout: set net.sel_attn.dropout.p = 0.0 (INTEGRATION.md, "
-                "'Dropout') or call the head in eval() mode; the reference default is p = 0.1 in train mode")
+        (convs/projections.py:28,62,84; `.train()` at models/proof.py:398).  The factorised kernels share the softmax of the
+        step rows between all samples, which a per-(sample, query, key) mask would break, so they implement p = 0 only;
+        with dropout active the head runs the token-tensor route instead (encode_* with autograd -> the [B, L, 512] tokens
+        the reference builds -> the stand-alone attention block with its dropout masks, team_mha_fwd / team_mha_bwd): the
+        reference's semantics at the reference's cost model (every token of every sample through q / k / v / fc)."""
+        return self.training and self.sel_attn.dropout.p > 0
 
     def encode_image(self, x, normalize: bool = False):
         feats = self._img_feats(x)
@@ -316,14 +320,15 @@ class Proof_Net(nn.Module):
     def forward_tri_modal(self, image, text, state_ids):
         """(image [B,512], text [B,1,512], state [B,512], proto [B,512], exp(logit_scale)); per-sample text
         (``len(text) == B``, the only form the learner uses, models/proof.py:421-425)."""
-        self._check_dropout()
         img = self._img_feats(image)
         if isinstance(text, list):
             text = self.tokenizer(text)
         txt = self._txt_feats(text)
+        if self._dropout_active():
+            return self._tri_modal_tokens(img, txt, state_ids.to(self._device))
         if txt.shape[0] != img.shape[0]:          # class texts shared by all samples: text output = mean over them
             if self._wants_grad():
-                return self._tri_modal_class_text_grad(img, txt, state_ids.to(self._device))
+                return self._tri_modal_tokens(img, txt, state_ids.to(self._device))
             with torch.no_grad():
                 o = head.forward_tri_modal_class_text(self._pack(), img, txt, state_ids.to(self._device), self._protos(),
                                                       mode=self.team_mode)
@@ -331,25 +336,30 @@ class Proof_Net(nn.Module):
         o = head.forward_tri_modal(self._pack(), img, txt, state_ids.to(self._device), self._protos(), mode=self.team_mode)
         return o[0], o[1], o[2], o[3], self.convnet.logit_scale.exp()
 
-    def _tri_modal_class_text_grad(self, img, txt, state_ids):
-        """Differentiable class-text form (utils/inc_net.py:544-547, :573-576): tokens = [image | Tn class texts | state |
-        C prototypes | P prompts]; the fused forward-only kernel (team_head_tri_classtext_fwd) serves the no-grad case."""
+    def _tri_modal_tokens(self, img, txt, state_ids):
+        """forward_tri_modal through the token tensor the reference builds (utils/inc_net.py:528-580): tokens = [image |
+        text(s) | state | C prototypes | P prompts], sel_attn on them, slices / means as there.  Serves the class-text form
+        with autograd (the fused forward-only kernel team_head_tri_classtext_fwd serves its no-grad case) and BOTH forms in
+        train mode with dropout."""
         pack = self._pack()
         xi = head.encode_grad(pack, "image", img, normalize=True, mode=self.team_mode)
         xt = head.encode_grad(pack, "text", txt, normalize=True, mode=self.team_mode)
         xs = head.encode_grad(pack, "state", state_ids, normalize=True, mode=self.team_mode)
         xp = head.encode_grad(pack, "prototypes", self._protos(), normalize=True, mode=self.team_mode)
         B, Tn, Cn = xi.shape[0], xt.shape[0], xp.shape[0]
-        toks = torch.cat([xi.view(B, 1, FEATURE_DIM), xt.view(1, Tn, FEATURE_DIM).expand(B, Tn, FEATURE_DIM),
+        per_sample = Tn == B                                 # utils/inc_net.py:544-547
+        nt = 1 if per_sample else Tn
+        text_tok = xt.view(B, 1, FEATURE_DIM) if per_sample else xt.view(1, Tn, FEATURE_DIM).expand(B, Tn, FEATURE_DIM)
+        toks = torch.cat([xi.view(B, 1, FEATURE_DIM), text_tok,
                           xs.view(B, 1, FEATURE_DIM), xp.view(1, Cn, FEATURE_DIM).expand(B, Cn, FEATURE_DIM),
                           self.get_context_prompts().view(1, -1, FEATURE_DIM).expand(B, -1, FEATURE_DIM)], dim=1).contiguous()
         self.sel_attn.team_mode = self.team_mode
         f = self.sel_attn(toks, toks, toks)
-        o_txt = f[:, 1:1 + Tn]
-        o_pro = f[:, 2 + Tn:2 + Tn + Cn]
-        o_txt = head.mean_dim(o_txt.contiguous(), 1) if Tn > 1 else o_txt
+        o_txt = f[:, 1:1 + nt]
+        o_pro = f[:, 2 + nt:2 + nt + Cn]
+        o_txt = head.mean_dim(o_txt.contiguous(), 1) if nt > 1 else o_txt
         o_pro = head.mean_dim(o_pro.contiguous(), 1) if Cn > 1 else o_pro
-        return f[:, 0], o_txt, f[:, 1 + Tn], o_pro, self.convnet.logit_scale.exp()
+        return f[:, 0], o_txt, f[:, 1 + nt], o_pro, self.convnet.logit_scale.exp()
 
     def _proof_grad(self, xi, xt):
         """Differentiable PROOF fusion (utils/inc_net.py:447-462) on encoded rows: tokens = [image | Tn texts | C prototypes |
@@ -381,12 +391,11 @@ class Proof_Net(nn.Module):
         """PROOF fusion (utils/inc_net.py:436-463): (image [B,512], text [Tn,512] batch mean, exp(logit_scale),
         proto [C,512] batch mean).  Without autograd: one fused forward (team_head_proof_fwd); with autograd (a trainable
         parameter under enable_grad): the same function through the differentiable encode + standalone attention ops."""
-        self._check_dropout()
         img = self._img_feats(image)
         if isinstance(text, list):
             text = self.tokenizer(text)
         txt = self._txt_feats(text)
-        if self._wants_grad():
+        if self._wants_grad() or self._dropout_active():
             pack = self._pack()
             return self._proof_grad(head.encode_grad(pack, "image", img, normalize=True, mode=self.team_mode),
                                     head.encode_grad(pack, "text", txt, normalize=True, mode=self.team_mode))
@@ -399,8 +408,7 @@ class Proof_Net(nn.Module):
         encode_text with normalize=True); transformer=False returns the inputs and the encoded prototypes."""
         if not transformer:
             return image_features, text_features, self.convnet.logit_scale.exp(), self.encode_prototpyes(normalize=True)
-        self._check_dropout()
-        if self._wants_grad():
+        if self._wants_grad() or self._dropout_active():
             return self._proof_grad(image_features.to(self._device), text_features.to(self._device))
         with torch.no_grad():
             o = head.forward_proof(self._pack(), image_features.to(self._device), text_features.to(self._device),

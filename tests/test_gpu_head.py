@@ -148,7 +148,7 @@ def test_head_bf16_mode(T, B):
 
 @pytest.mark.parametrize("mode_name,T,B", [("f32", 3, 40), ("f32", 10, 300), ("bf16", 10, 512)])
 def test_gram_table_rows_match_the_oracle(mode_name, T, B, monkeypatch):
-    """The Gram formulation of the table-query rows (csrc/head_table_gram.cuh, the default from 32 768 samples per
+    """The Gram formulation of the table-query rows (csrc/head_table_gram.cuh, the default from 16 384 samples per
     GPU) forced on at small batches: the same parity bars as the default kernels - fp32 <= 1e-5 / 2e-5 against the
     fp64 oracle, bf16 against the model that rounds where the kernels round - and it must agree with the
     second-generation kernels on every output and gradient."""

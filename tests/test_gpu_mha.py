@@ -170,17 +170,91 @@ def test_state_embedding_lookup():
 
 
 def test_standalone_sel_attn_module():
-    """net.sel_attn(q, k, v) as a module call (the reference's own interface), train mode with p = 0."""
+    """net.sel_attn(q, k, v) as a module call (the reference's own interface), eval mode."""
     from team_b200 import inc_net
     dev = torch.device("cuda")
     m = inc_net.MultiHeadAttention(1, 512, 512, 512, dropout=0.1).to(dev)
     x = torch.randn(4, 6, 512, device=dev)
-    m.train()
-    with pytest.raises(NotImplementedError):
-        m(x, x, x)
-    m.dropout.p = 0.0
+    m.eval()
     y = m(x, x, x)
     p = {"sel_attn." + n: t.detach().double().cpu() for n, t in m.named_parameters()}
     assert rel(y, O.sel_attn(x.double().cpu(), p)) < 1e-5
     y.sum().backward()
     assert all(t.grad is not None for t in m.parameters())
+
+
+@pytest.mark.parametrize("B,Lq,Lk,pd", [(3, 5, 7, 0.1), (2, 141, 141, 0.1), (4, 17, 33, 0.5)])
+def test_mha_train_mode_dropout_vs_oracle(B, Lq, Lk, pd):
+    """Train mode: both dropouts of the block (convs/projections.py:35, :84) with the library's Philox masks, against the
+    reference math with the SAME masks (oracle.philox_keep_mask, an independent numpy Philox4x32-10): outputs 1e-5, every
+    input and parameter gradient 2e-5 - i.e. the masks are applied where the reference applies them, scaled by 1 / (1 - p),
+    and regenerated identically in the backward."""
+    from team_b200 import head
+    dev = torch.device("cuda")
+    gen = torch.Generator().manual_seed(B * 100 + Lq)
+    params = synth.make_params(1, seed=70 + B)
+    q, k, v, cot = (torch.randn(s, generator=gen) for s in ((B, Lq, 512), (B, Lk, 512), (B, Lk, 512), (B, Lq, 512)))
+    seed, offset = 0x1234567890ABCDEF, 2 * (2 ** 40 + 77)
+    p64 = {n: t.double().requires_grad_(True) for n, t in params.items() if n.startswith("sel_attn.")}
+    q64, k64, v64 = (t.double().requires_grad_(True) for t in (q, k, v))
+    ref = O.mha(q64, k64, v64, p64, drop=(pd, seed, offset))
+    gref = torch.autograd.grad(ref, [q64, k64, v64] + [p64["sel_attn." + n] for n in MHA_NAMES], grad_outputs=cot.double())
+    par = [params["sel_attn." + n].to(dev).requires_grad_(True) for n in MHA_NAMES]
+    qd, kd, vd = (t.to(dev).requires_grad_(True) for t in (q, k, v))
+    out = head.mha(qd, kd, vd, *par, mode=head.MODE_F32, dropout_p=pd, seed=seed, offset=offset)
+    grads = torch.autograd.grad(out, [qd, kd, vd] + par, grad_outputs=cot.to(dev))
+    assert rel(out, ref) < 1e-5, rel(out, ref)
+    for i, (a, b) in enumerate(zip(grads, gref)):
+        assert rel(a, b) < 2e-5, (i, rel(a, b))
+    # eval output differs (dropout really happened), another offset gives another mask
+    ev = head.mha(qd, kd, vd, *par, mode=head.MODE_F32)
+    other = head.mha(qd, kd, vd, *par, mode=head.MODE_F32, dropout_p=pd, seed=seed, offset=offset + 2)
+    assert rel(out, ev) > 1e-3 and rel(out, other) > 1e-3
+    again = head.mha(qd, kd, vd, *par, mode=head.MODE_F32, dropout_p=pd, seed=seed, offset=offset)
+    assert torch.equal(again, out)
+
+
+def test_dropout_mask_stream_statistics():
+    """The mask stream: equals the numpy Philox bit for bit, keep rate p within 4 sigma, no correlation between neighbours,
+    between consecutive offsets or between seeds."""
+    from team_b200 import head
+    n = 1 << 20
+    for pd in (0.1, 0.5):
+        m = head.dropout_keep_mask(n, pd, seed=42, offset=6).cpu().double()
+        assert torch.equal(m, O.philox_keep_mask(n, pd, 42, 6))
+        sigma = (pd * (1 - pd) / n) ** 0.5
+        assert abs(float(m.mean()) - (1 - pd)) < 4 * sigma
+        for other in (head.dropout_keep_mask(n, pd, seed=42, offset=7).cpu().double(),
+                      head.dropout_keep_mask(n, pd, seed=43, offset=6).cpu().double(), torch.roll(m, 1)):
+            corr = float(((m - m.mean()) * (other - other.mean())).mean() / (m.var() * other.var()).sqrt())
+            assert abs(corr) < 5 / n ** 0.5, corr
+
+
+def test_proof_net_train_mode_uses_dropout():
+    """Proof_Net in train mode with the reference's default p = 0.1: forward_tri_modal / forward run the token-tensor route with
+    dropout (no exception, outputs differ from eval mode and between calls, gradients flow); torch.manual_seed reproduces it;
+    p = 0 in train mode is the factorised path and equals eval mode."""
+    dev = torch.device("cuda")
+    ci = case_inputs(CASES["head_T2_B7_classtext"])
+    net = _net(ci["params"], ci["protos"], dev)
+    b = ci["batch"]
+    a = (b["image"].to(dev), b["text"].to(dev), b["state"].to(dev))
+    with torch.no_grad():
+        ev = net.forward_tri_modal(*a)
+    net.train()
+    torch.manual_seed(5)
+    t1 = net.forward_tri_modal(*a)
+    t2 = net.forward_tri_modal(*a)
+    torch.manual_seed(5)
+    t3 = net.forward_tri_modal(*a)
+    assert t1[1].shape == ev[1].shape == (7, 1, 512)
+    assert rel(t1[0], ev[0]) > 1e-3 and rel(t1[0], t2[0]) > 1e-3 and torch.equal(t1[0], t3[0])
+    loss = sum(o.square().sum() for o in t1[:4])
+    loss.backward()
+    assert net.sel_attn.w_qs.weight.grad is not None and net.projs_img[-1].MLP[0].weight.grad is not None
+    pf = net.forward(a[0], b["text_cls"].to(dev))
+    assert pf[0].requires_grad
+    net.sel_attn.dropout.p = 0.0
+    t0 = net.forward_tri_modal(*a)
+    for x, y in zip(t0[:4], ev[:4]):
+        assert rel(x, y) < 1e-6

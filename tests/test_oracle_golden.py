@@ -100,6 +100,18 @@ def test_mha_cross_attention(golden):
         assert rel_err(grad_subsample(gr), g["grad:" + n]) < 1e-5, n
 
 
+def test_philox_known_answers():
+    """Random123's known-answer vectors for philox4x32-10 (kat_vectors): the generator behind the library's dropout masks."""
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = O.philox4x32_10(*[np.array([w], dtype=np.uint64) for w in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == want, (ctr, [hex(int(g[0])) for g in got])
+    m = O.philox_keep_mask(1 << 16, 0.1, 42, 6)
+    assert abs(float(m.mean()) - 0.9) < 0.006
+
+
 def test_herding(golden):
     """Exemplar herding restatement vs the real BaseLearner._construct_exemplar (models/base.py:274-343): picks exact."""
     case, g = CASES["herding"], golden("herding")
