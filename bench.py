@@ -705,6 +705,44 @@ def run_team(a):
             proto_build = {"error": str(exc)[:300]}
             torch.cuda.empty_cache()
 
+    # ---- N > 1 (BASELINE configs[4]): the prototype build data-parallel - every rank sums its own shard of rows (4 M fp32 rows
+    # per GPU: weak scaling), then the two collectives of the path on it: NCCL all-reduce of the [K,512] sums and the int64 counts
+    # (parallel.allreduce_prototype_sums), then the means.  Max over ranks of the CUDA-event time, aggregate rows/s; counts checked.
+    proto_dp = None
+    if world > 1 and not a.no_scale:
+        try:
+            from team_b200 import ops, parallel
+            Np = 4 * 1024 * 1024
+            gdev = torch.Generator(device=dev).manual_seed(100 + rank)
+            xr = torch.randn((Np, 512), generator=gdev, device=dev, dtype=torch.float32)
+            yr = torch.randint(0, 20, (Np,), generator=gdev, device=dev)
+            sr = torch.randint(0, 10, (Np,), generator=gdev, device=dev)
+            proto_dp = {"rows_per_gpu": Np, "rows_total": Np * world, "hbm_peak_gbs_per_gpu": pk["hbm"]}
+            for key, st_, K_ in (("class_keys", None, 20), ("class_state_keys", sr, 200)):
+                def build():
+                    sums, counts = ops.keyed_sums(xr, yr, st_, num_classes=20)
+                    parallel.allreduce_prototype_sums(sums, counts)
+                    return ops.keyed_means(sums, counts), counts
+                _, counts = build()
+                torch.cuda.synchronize(); dist.barrier()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record()
+                for _ in range(5):
+                    build()
+                q1.record(); torch.cuda.synchronize()
+                tm = torch.tensor([q0.elapsed_time(q1) / 5], device=dev)
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                msq = float(tm.item())
+                by = 2048 + (16 if st_ is not None else 8)
+                proto_dp[key] = {"ms": msq, "rows_per_s": Np * world / msq * 1e3, "gbs_per_gpu": Np * by / msq / 1e6,
+                                 "frac_of_hbm_peak": Np * by / msq / 1e6 / pk["hbm"], "keys": K_,
+                                 "counts_exact": bool(int(counts.sum().item()) == Np * world)}
+            del xr
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            proto_dp = {"error": str(exc)[:300]}
+            torch.cuda.empty_cache()
+
     # ---- BASELINE configs[3] graph path: evolve_and_update (graph build on the host + temporal GCN + pairwise state
     # distances), evolve_state_prototypes (second GCN pass + prototype sync) and the state-distance EMA, wall clock with a
     # device sync per call (the learner calls them once per epoch, models/proof.py:463-513); native size (20 classes,
@@ -757,7 +795,7 @@ def run_team(a):
                 "run": {"grad_exchange": comm, "cuda_graphs": graphs is not None,
                         "l2": f"{rot} rotating input+cotangent sets ({rot * B * 512 * 4 * 6 / 2**20:.0f} MiB) larger than L2"},
                 "roofline": roof, "at_scale": at_scale, "train_step": train_step, "proto_build": proto_build, "graph": graph_path, "cpu_baseline": cb, "clocks": clocks, "e2e": e2e,
-                "grad_exchange_check": grad_check, "strong_scaling": strong,
+                "grad_exchange_check": grad_check, "strong_scaling": strong, "proto_build_dp": proto_dp,
                 "gpu_launches": int(launches_per_step) * a.steps,
                 "survey_falg_tflops": value * 55.07e6 / 1e12 / world}
         print(json.dumps(line), flush=True)
