@@ -392,3 +392,50 @@ def test_frozen_projection_sums_are_bit_identical():
         params["projs_img.0.MLP.0.weight"].div_(1.5)
     params["projs_text.1.MLP.0.bias"].requires_grad_(True)     # an old task that is trainable: no caching
     assert head.HeadStepRunner(pack, protos, B, C, head.MODE_F32).hw.num_frozen == 0
+
+
+def test_extra_cotangent_on_own_rows():
+    """team_head_grads.g_own_rows / team_head_own_rows_offset: the forward leaves normalize(encode_image(x)) |
+    normalize(encode_text(t)) in its workspace, and a cotangent on those rows joins the backward - equal to running the two
+    encodes and their backward separately (the ClipLoss branch of the training step, models/proof.py:428-431)."""
+    from team_b200 import head
+    dev = torch.device("cuda")
+    T, B = 3, 29
+    C = 2 * T
+    params = {k: v.to(dev) for k, v in synth.make_params(T, seed=92).items()}
+    pack = head.HeadParamPack.from_state_dict(params)
+    protos = synth.make_prototypes(C).to(dev)
+    b = {k: v.to(dev) for k, v in synth.make_batch(B, C, step=6).items()}
+    cots = [c.to(dev).reshape(B, 512) for c in synth.make_cotangents(B, step=6)]
+    tc = synth.make_text_class_features(20)[:C].contiguous().to(dev)
+    g = torch.randn(2, B, 512, generator=torch.Generator().manual_seed(3)).to(dev)
+    for mode, tol in ((head.MODE_F32, 2e-5), (head.MODE_BF16, 5e-3)):
+        r = head.HeadStepRunner(pack, protos, B, C, mode)
+        r.forward(b["image"], b["text"], b["state"], tc)
+        xo = r.own_rows().clone()
+        ei = head.encode(pack, "image", b["image"], normalize=True, mode=mode)
+        et = head.encode(pack, "text", b["text"], normalize=True, mode=mode)
+        assert rel(xo[:B], ei) < 1e-6 and rel(xo[B:], et) < 1e-6
+        r.backward(b["image"], b["text"], b["state"], cots)
+        base = {k: v.clone() for k, v in r.grad_views.items()}
+        r.forward(b["image"], b["text"], b["state"], tc)
+        r.backward(b["image"], b["text"], b["state"], cots, g_own_rows=g)
+        torch.cuda.synchronize()
+        leaf = {n: params[f"projs_{n}.{T - 1}.MLP.0.{w}"].clone().requires_grad_(True) for n in ("img", "text") for w in ("weight",)}
+        p2 = dict(params)
+        names = [f"projs_img.{T - 1}.MLP.0.weight", f"projs_img.{T - 1}.MLP.0.bias", f"projs_text.{T - 1}.MLP.0.weight", f"projs_text.{T - 1}.MLP.0.bias"]
+        for n in names:
+            p2[n] = params[n].clone().requires_grad_(True)
+        pk2 = head.HeadParamPack.from_state_dict(p2)
+        yi = head.encode_grad(pk2, "image", b["image"], normalize=True, mode=mode)
+        yt = head.encode_grad(pk2, "text", b["text"], normalize=True, mode=mode)
+        extra = torch.autograd.grad([yi, yt], [p2[n] for n in names], grad_outputs=[g[0], g[1]])
+        for key, e in zip(("w_img", "b_img", "w_text", "b_text"), extra):
+            if mode == head.MODE_F32:          # the increment itself
+                got = r.grad_views[key] - base[key]
+                assert rel(got.reshape(e.shape), e) < tol, (mode, key, rel(got.reshape(e.shape), e))
+            else:                              # bf16 operands round the SUM of the cotangents: compare the totals
+                want = base[key].reshape(e.shape) + e
+                assert rel(r.grad_views[key].reshape(e.shape), want) < tol, (mode, key, rel(r.grad_views[key].reshape(e.shape), want))
+        for key in ("w_q", "w_fc", "ln_g", "state_emb", "prompts"):
+            assert torch.equal(r.grad_views[key], base[key]), key          # nothing else sees the extra cotangent
