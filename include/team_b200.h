@@ -308,6 +308,12 @@ int team_mean_mid_bwd(const float* g, float* dx, int64_t outer, int64_t red, int
  *   temperature = the dynamic temperature of :111-116 (host scalar); losses[3] = {total, instance, category}.
  * team_clip_loss: image/text [B,512] as handed to ClipLoss (the learner normalises them first), logit_scale host scalar. */
 size_t team_loss_workspace_bytes(int64_t batch);
+/* Value of the classification cross-entropy (models/proof.py:417; mean over the batch of lse(logits) - logits[label]; no
+ * gradient: the logits are computed under no_grad, :411-416) and the learner's total loss (:442) in one launch:
+ * losses6 = [total, ce, clip, unicl, unicl_instance, unicl_category]; entries 2..5 are INPUTS (written before by
+ * team_clip_loss -> losses6 + 2 and team_unicl_loss(_evo) -> losses6 + 3); total = ce + w_clip * clip + w_unicl * unicl. */
+int team_ce_total(const float* logits, const int64_t* labels, int64_t batch, int64_t num_classes, float w_clip,
+                  float w_unicl, float* losses6, void* stream);
 int team_unicl_loss(int mode, const float* image, const float* text, const float* state, const int64_t* labels,
                     int64_t batch, float temperature, float grad_scale, float* losses,
                     float* g_image, float* g_text, float* g_state,

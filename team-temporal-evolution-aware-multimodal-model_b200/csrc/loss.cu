@@ -264,25 +264,59 @@ unicl_instance_kernel(int B, const float* __restrict__ Xi, const float* __restri
 // (deterministic).  State ids must lie in [0, 10) (they index the 10-row state embedding).
 constexpr int EVO_NS = 10;
 
+// One CTA per key.  Phase 1: all threads test 128 samples at a time and leave one ballot word per warp in shared memory
+// (the label / state loads of all chunks are independent); phase 2: every thread walks the set bits in index order and
+// adds its float4 column of each matching row - the same deterministic order as a serial scan, without its B dependent
+// iterations (the serial form took 64 us per call at B = 1 024: a quarter of the whole training step, tools/timeline_train.py).
 __global__ void __launch_bounds__(128)
 evo_keysum_kernel(int B, const float* __restrict__ rows, const unsigned char* __restrict__ rowmask,
                   const int64_t* __restrict__ labels, const int64_t* __restrict__ states, int num_evo,
                   const unsigned char* __restrict__ evo_mask, float* __restrict__ out, int* __restrict__ cnt) {
+    extern __shared__ unsigned int evo_bits[];               // [ceil(B / 32)]
     pdl_trigger();
     pdl_wait();
     const int key = blockIdx.x, c = key / EVO_NS, st = key - c * EVO_NS;
     if (!evo_mask[c]) return;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int n = 0;
-    for (int j = 0; j < B; ++j) {
-        if (labels[j] != c || clamp_state(states[j]) != st) continue;
-        ++n;
-        if (rowmask != nullptr && !rowmask[j]) continue;
-        const float4 v = reinterpret_cast<const float4*>(rows + (size_t)j * D)[threadIdx.x];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const int t = threadIdx.x, lane = t & 31;
+    const int nwords = (B + 31) / 32;
+#pragma unroll 4
+    for (int base = 0; base < nwords * 32; base += 128) {
+        const int j = base + t;
+        const bool hit = j < B && labels[j] == c && clamp_state(states[j]) == st;
+        const unsigned int m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0 && (j >> 5) < nwords) evo_bits[j >> 5] = m;
     }
-    reinterpret_cast<float4*>(out + (size_t)key * D)[threadIdx.x] = acc;
-    if (cnt != nullptr && threadIdx.x == 0) cnt[key] = n;
+    __syncthreads();
+    // phase 2: the matching rows in index order, four loads in flight (the bit walk itself is register arithmetic; a row
+    // load per set bit, one after the other, was a chain of dependent L2 round trips)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = 0, pend = 0;
+    int idx[4];
+    auto flush = [&]() {
+        float4 v[4];
+        bool use[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            use[q] = q < pend && (rowmask == nullptr || rowmask[idx[q]] != 0);
+            if (use[q]) v[q] = reinterpret_cast<const float4*>(rows + (size_t)idx[q] * D)[t];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (use[q]) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+        pend = 0;
+    };
+    for (int w = 0; w < nwords; ++w) {
+        unsigned int m = evo_bits[w];
+        n += __popc(m);
+        while (m) {
+            idx[pend++] = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            if (pend == 4) flush();
+        }
+    }
+    if (pend > 0) flush();
+    reinterpret_cast<float4*>(out + (size_t)key * D)[t] = acc;
+    if (cnt != nullptr && t == 0) cnt[key] = n;
     (void)num_evo;
 }
 
@@ -554,7 +588,7 @@ static int unicl_impl(int mode, const float* image, const float* text, const flo
                 bf ? w.X[0].h : nullptr, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, w.inv[0], w.inv[1], w.inv[2], 3, 1);
     if (ev != nullptr) {          // enhanced state rows (models/proof.py:51-106) replace the normalised ones in the instance term
         const int keys = ev->num_evo * EVO_NS;
-        TEAM_LAUNCH(evo_keysum_kernel, keys, 128, 0, st, B, w.X[2].f, (const unsigned char*)nullptr, labels, ev->state_ids, ev->num_evo, ev->evo_mask, SS, cnt);
+        TEAM_LAUNCH(evo_keysum_kernel, keys, 128, (size_t)((B + 31) / 32) * sizeof(unsigned int), st, B, w.X[2].f, (const unsigned char*)nullptr, labels, ev->state_ids, ev->num_evo, ev->evo_mask, SS, cnt);
         TEAM_LAUNCH(evo_fwd_kernel, (B + 7) / 8, 256, 0, st, B, w.X[2].f, labels, ev->state_ids, ev->num_evo, ev->evo, ev->evo_mask, SS, cnt, Xe, Mh, sc, rowmask);
     }
     {   // sim = Xi Xi^T
@@ -572,7 +606,7 @@ static int unicl_impl(int mode, const float* image, const float* text, const flo
     if (ev != nullptr) {
         const int keys = ev->num_evo * EVO_NS;
         TEAM_LAUNCH(evo_bwd1_kernel, (B + 7) / 8, 256, 0, st, B, Xe, Mh, sc, dXe, dMix);
-        TEAM_LAUNCH(evo_keysum_kernel, keys, 128, 0, st, B, dMix, rowmask, labels, ev->state_ids, ev->num_evo, ev->evo_mask, DM, (int*)nullptr);
+        TEAM_LAUNCH(evo_keysum_kernel, keys, 128, (size_t)((B + 31) / 32) * sizeof(unsigned int), st, B, dMix, rowmask, labels, ev->state_ids, ev->num_evo, ev->evo_mask, DM, (int*)nullptr);
         TEAM_LAUNCH(evo_bwd2_kernel, (B + 7) / 8, 256, 0, st, B, w.X[2].f, w.inv[2], labels, ev->state_ids, sc, DM, cnt, dXe, g_state);
     }
     TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, B, w.rloss + B, (const float*)nullptr, w.scal + 2);
@@ -585,6 +619,47 @@ extern "C" int team_unicl_loss(int mode, const float* image, const float* text, 
                                float* g_text, float* g_state, void* workspace, size_t workspace_bytes, void* stream) {
     return unicl_impl(mode, image, text, state, labels, nullptr, batch, temperature, grad_scale, losses, g_image, g_text,
                       g_state, workspace, workspace_bytes, stream);
+}
+
+// ---- cross-entropy VALUE of the classification logits (models/proof.py:417: the logits are computed under no_grad, so the
+// term carries no gradient) and the learner's total (:442), in one launch: losses6 = [total, ce, clip, unicl, unicl
+// instance, unicl category]; entries 2..5 must already hold the ClipLoss / unicl_loss values (their `losses` outputs).
+// One CTA, rows strided over the threads, block fold in a fixed order (deterministic).
+__global__ void __launch_bounds__(1024)
+ce_total_kernel(int B, int C, const float* __restrict__ logits, const int64_t* __restrict__ labels, float w_clip, float w_unicl,
+                float* __restrict__ losses6) {
+    __shared__ float part[1024];
+    pdl_trigger();
+    pdl_wait();
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 1024) {
+        const float* r = logits + (size_t)b * C;
+        float m = -INFINITY;
+        for (int c = 0; c < C; ++c) m = fmaxf(m, r[c]);
+        float z = 0.f;
+        for (int c = 0; c < C; ++c) z += expf(r[c] - m);
+        const int64_t y = labels[b];
+        s += (m + logf(z)) - ((y >= 0 && y < C) ? r[y] : 0.f);
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float ce = part[0] / (float)B;
+        losses6[1] = ce;
+        losses6[0] = ce + w_clip * losses6[2] + w_unicl * losses6[3];
+    }
+}
+
+extern "C" int team_ce_total(const float* logits, const int64_t* labels, int64_t batch, int64_t num_classes, float w_clip,
+                             float w_unicl, float* losses6, void* stream) {
+    TEAM_REQUIRE(logits && labels && losses6 && batch >= 1 && batch < (1ll << 31) && num_classes >= 1 && num_classes < (1 << 20),
+                 "ce_total: bad arguments");
+    TEAM_LAUNCH(ce_total_kernel, 1, 1024, 0, (cudaStream_t)stream, (int)batch, (int)num_classes, logits, labels, w_clip, w_unicl, losses6);
+    return TEAM_OK;
 }
 
 extern "C" size_t team_loss_evo_workspace_bytes(int64_t batch, int num_evo) {

@@ -23,12 +23,19 @@ struct OptList {
 __global__ void __launch_bounds__(256)
 adamw_kernel(const __grid_constant__ OptList L, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
              const long long* __restrict__ step_dev) {
+    __shared__ float bc[2];
     pdl_trigger();
     pdl_wait();
     if (step_dev != nullptr) {          // graph form: the step count lives on the device (adamw_tick_kernel advances it)
-        const double t = (double)(*step_dev + 1);
-        bc1 = (float)(1.0 - pow((double)b1, t));
-        bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+        // one thread per CTA: two double-precision pow() in EVERY thread made this kernel 26 us instead of 8 (tools/timeline_train.py)
+        if (threadIdx.x == 0) {
+            const double t = (double)(*step_dev + 1);
+            bc[0] = (float)(1.0 - pow((double)b1, t));
+            bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+        }
+        __syncthreads();
+        bc1 = bc[0];
+        bc2_sqrt = bc[1];
     }
     int t = 0;
     for (int i = 1; i < L.count; ++i)

@@ -161,7 +161,8 @@ def pack_evolution_features(evolution_features, device):
 
 def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, labels: torch.Tensor, *,
                state_ids: Optional[torch.Tensor] = None, evolution_features=None,
-               temperature: float = 0.07, epoch=None, max_epoch=None, grad_scale: float = 1.0, mode: int = capi.MODE_F32):
+               temperature: float = 0.07, epoch=None, max_epoch=None, grad_scale: float = 1.0, mode: int = capi.MODE_F32,
+               losses_out: Optional[torch.Tensor] = None):
     """unicl_loss (models/proof.py:21-191) forward + gradient in one call, including the ``evolution_features``
     branch (:51-106; pass the list the learner passes, or a ``(table, mask)`` pair from ``pack_evolution_features``).
     Returns (losses [3] = total / instance / category on the device, (g_image, g_text, g_state) [B,512] =
@@ -189,7 +190,9 @@ def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, lab
     if nbytes == 0:
         raise ValueError(f"unicl_loss: batch {B} out of range")
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-    losses = torch.empty((3,), dtype=torch.float32, device=dev)
+    losses = losses_out if losses_out is not None else torch.empty((3,), dtype=torch.float32, device=dev)
+    if losses.shape != (3,) or losses.dtype != torch.float32 or not losses.is_contiguous() or losses.device != dev:
+        raise ValueError("unicl_loss: losses_out must be a contiguous fp32 [3] tensor on the inputs' device")
     grads = torch.empty((3, B, capi.D), dtype=torch.float32, device=dev)
     tau = dynamic_temperature(temperature, epoch, max_epoch)
     if evo is None:
@@ -207,7 +210,7 @@ def unicl_loss(image: torch.Tensor, text: torch.Tensor, state: torch.Tensor, lab
 
 
 def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, grad_scale: float = 1.0,
-              mode: int = capi.MODE_F32, grads_out: Optional[torch.Tensor] = None):
+              mode: int = capi.MODE_F32, grads_out: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
     """ClipLoss.forward (utils/toolkit.py:128-141, world_size 1) forward + gradient: (loss [1], (g_image, g_text)).
     ``grads_out``: optional contiguous fp32 [2,B,512] buffer the two gradients are written to (image rows, then text rows -
     the layout of ``team_head_grads.g_own_rows``)."""
@@ -220,7 +223,9 @@ def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, gr
         raise ValueError(f"clip_loss: batch {B} out of range")
     dev = xi.device
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    loss = loss_out if loss_out is not None else torch.empty((1,), dtype=torch.float32, device=dev)
+    if loss.shape != (1,) or loss.dtype != torch.float32 or loss.device != dev:
+        raise ValueError("clip_loss: loss_out must be an fp32 [1] tensor on the inputs' device")
     grads = grads_out if grads_out is not None else torch.empty((2, B, capi.D), dtype=torch.float32, device=dev)
     if grads.shape != (2, B, capi.D) or grads.dtype != torch.float32 or not grads.is_contiguous() or grads.device != dev:
         raise ValueError("clip_loss: grads_out must be a contiguous fp32 [2,B,512] tensor on the inputs' device")
@@ -228,6 +233,19 @@ def clip_loss(image: torch.Tensor, text: torch.Tensor, logit_scale: float, *, gr
                                 loss.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(), ws.data_ptr(), nbytes,
                                 _stream_ptr()), "team_clip_loss")
     return loss, (grads[0], grads[1])
+
+
+def ce_total(logits: torch.Tensor, labels: torch.Tensor, losses6: torch.Tensor, w_clip: float = 1.0, w_unicl: float = 0.3):
+    """Cross-entropy VALUE of the no-grad classification logits (models/proof.py:417) and the learner's total (:442) written
+    into ``losses6`` = [total, ce, clip, unicl, unicl_instance, unicl_category] (entries 2.. are read): ``team_ce_total``."""
+    capi.require_device()
+    if losses6.shape != (6,) or losses6.dtype != torch.float32 or not losses6.is_contiguous():
+        raise ValueError("ce_total: losses6 must be a contiguous fp32 [6] tensor")
+    lg = logits.detach().float().contiguous()
+    y = labels.detach().to(device=lg.device, dtype=torch.int64).contiguous()
+    capi.check(capi.lib().team_ce_total(lg.data_ptr(), y.data_ptr(), lg.shape[0], lg.shape[1], float(w_clip), float(w_unicl),
+                                        losses6.data_ptr(), _stream_ptr()), "team_ce_total")
+    return losses6
 
 
 class FusedAdamW:

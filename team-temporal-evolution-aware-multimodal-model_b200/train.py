@@ -61,10 +61,13 @@ class TrainStep:
         # static inputs of the captured step
         self.image, self.text = mk(batch, D), mk(batch, D)
         self.state, self.labels = mk(batch, dt=torch.int64), mk(batch, dt=torch.int64)
-        self.losses = torch.zeros((5,), dtype=torch.float32, device=dev)     # total, ce, clip, unicl total, unicl instance
+        self._inputs = [self.image, self.text, self.state, self.labels]
+        self.losses6 = torch.zeros((6,), dtype=torch.float32, device=dev)    # total, ce, clip, unicl total, unicl instance, unicl category
+        self.losses = self.losses6[:5]
         self.g_own = torch.zeros((2, batch, D), dtype=torch.float32, device=dev)   # ClipLoss gradient w.r.t. the normalised own rows
         self._graphs: Dict[int, torch.cuda.CUDAGraph] = {}
         self._stream = torch.cuda.Stream(device=dev)
+        self._side = torch.cuda.Stream(device=dev)
 
     def lr_at(self, epoch: int) -> float:
         """CosineAnnealingLR(T_max=tuned_epoch, eta_min=min_lr) stepped once per epoch (models/proof.py:363, :447)."""
@@ -74,21 +77,23 @@ class TrainStep:
         r, mode = self.runner, self.mode
         img, txt, sid, y = self.image, self.text, self.state, self.labels
         r.forward(img, txt, sid, self.text_cls)                                   # cls logits + the four feature outputs
-        ce = torch.nn.functional.cross_entropy(r.logits, y)                       # value only: the logits carry no gradient (:411-417)
         un, cots = ops.unicl_loss(r.outs[0], r.outs[1], r.outs[2], y, state_ids=sid, evolution_features=self.evo,
-                                  epoch=epoch, max_epoch=self.tuned_epoch, grad_scale=0.3, mode=mode)
+                                  epoch=epoch, max_epoch=self.tuned_epoch, grad_scale=0.3, mode=mode, losses_out=self.losses6[3:6])
         # ClipLoss branch (:428-431): its inputs normalize(encode_text(..)) / normalize(encode_image(..)) ARE the normalised
         # own rows the head's forward just produced, so the loss reads them in place and its gradient joins the head's
         # backward as an extra cotangent on those rows (team_head_grads.g_own_rows) - no second pass through the projections
         xo = r.own_rows()
-        cl, _ = ops.clip_loss(xo[:self.B], xo[self.B:], self.logit_scale, mode=mode, grads_out=self.g_own)
+        ops.clip_loss(xo[:self.B], xo[self.B:], self.logit_scale, mode=mode, grads_out=self.g_own, loss_out=self.losses6[2:3])
+        # ce VALUE (the logits carry no gradient, :411-417) and total = ce + clip + 0.3 unicl (:442): one single-CTA launch on a
+        # side stream beside the backward (a parallel branch of the captured graph), no host sync
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            ops.ce_total(r.logits, y, self.losses6, w_clip=1.0, w_unicl=0.3)
         r.backward(img, txt, sid, [cots[0], cots[1], cots[2], None], g_own_rows=self.g_own)   # the losses never touch the prototype output
         self.opt.lr = self.lr_at(epoch)
         self.opt.step_graph([g for _, g in self.pairs])
-        self.losses[1] = ce
-        self.losses[2:3].copy_(cl)
-        self.losses[3:5].copy_(un[:2])
-        self.losses[0] = ce + cl[0] + 0.3 * un[0]
+        cur.wait_stream(self._side)
 
     def _capture(self, epoch: int):
         st = self._stream
@@ -114,8 +119,12 @@ class TrainStep:
 
     def load(self, image, text, state_ids, labels):
         """Copy one batch (host or device tensors) into the step's static input buffers on the current stream."""
-        self.image.copy_(image, non_blocking=True); self.text.copy_(text.reshape(self.B, capi.D), non_blocking=True)
-        self.state.copy_(state_ids, non_blocking=True); self.labels.copy_(labels, non_blocking=True)
+        src = [image, text.reshape(self.B, capi.D), state_ids, labels]
+        if all(t.is_cuda and t.dtype == d.dtype for t, d in zip(src, self._inputs)):
+            torch._foreach_copy_(self._inputs, src)          # device-resident batch: two multi-tensor launches instead of four copies
+        else:
+            for d, t in zip(self._inputs, src):
+                d.copy_(t, non_blocking=True)
 
     def step(self, epoch: int = 0):
         """One optimisation step on the loaded batch; returns the device tensor [total, ce, clip, unicl, unicl_instance]."""
