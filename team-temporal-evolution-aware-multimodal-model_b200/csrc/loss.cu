@@ -116,17 +116,44 @@ unicl_cat_stats_kernel(int B, int ld, const float* __restrict__ sim, const int64
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= B) return;
-    const float* row = sim + (size_t)i * ld;
+    // 128-bit loads, four of them in flight per lane (ld is a multiple of 4; columns >= B are masked): with scalar loads and
+    // the compiler's own unrolling the two passes were chains of L2 round trips (16 us at B = 1 024, tools/timeline_train.py)
+    const float4* row4 = reinterpret_cast<const float4*>(sim + (size_t)i * ld);
+    const longlong2* lab2 = reinterpret_cast<const longlong2*>(labels);
     const int64_t yi = labels[i];
+    const int n4 = (B + 3) >> 2;
     float mx = -INFINITY;
-    for (int j = lane; j < B; j += 32) mx = fmaxf(mx, row[j] * inv_tau);
+#pragma unroll 4
+    for (int q = lane; q < n4; q += 32) {
+        const float4 v = row4[q];
+        const int j = 4 * q;
+        mx = fmaxf(mx, v.x * inv_tau);
+        if (j + 1 < B) mx = fmaxf(mx, v.y * inv_tau);
+        if (j + 2 < B) mx = fmaxf(mx, v.z * inv_tau);
+        if (j + 3 < B) mx = fmaxf(mx, v.w * inv_tau);
+    }
     mx = warp_max(mx);
     float pos = 0.f, all = 0.f;
-    for (int j = lane; j < B; j += 32) {
-        if (j == i) continue;
-        const float e = expf(row[j] * inv_tau - mx);
-        all += e;
-        if (labels[j] == yi) pos += e;
+#pragma unroll 4
+    for (int q = lane; q < n4; q += 32) {
+        const float4 v = row4[q];
+        const int j = 4 * q;
+        long long y[4];
+        if (j + 3 < B) {
+            const longlong2 la = lab2[2 * q], lb = lab2[2 * q + 1];
+            y[0] = la.x; y[1] = la.y; y[2] = lb.x; y[3] = lb.y;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) y[u] = j + u < B ? labels[j + u] : -1;
+        }
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u >= B || j + u == i) continue;
+            const float e = expf(x[u] * inv_tau - mx);
+            all += e;
+            if (y[u] == yi) pos += e;
+        }
     }
     pos = warp_sum(pos); all = warp_sum(all);
     if (lane == 0) {
@@ -170,15 +197,35 @@ unicl_cat_grad_kernel(int B, int ld, const float* __restrict__ sim, const int64_
     const float k = valid ? weight * inv_tau / nvalid : 0.f;
     const float mx = rmax[i], ip = valid ? 1.0f / rpos[i] : 0.f, ia = valid ? 1.0f / (rall[i] + 1e-8f) : 0.f;
     const int64_t yi = labels[i];
-    const float* row = sim + (size_t)i * ld;
-    for (int j = lane; j < ld; j += 32) {
-        float g = 0.f;
-        if (j < B && j != i && valid) {
-            const float e = expf(row[j] * inv_tau - mx);
-            g = k * e * (ia - (labels[j] == yi ? ip : 0.f));
+    const float4* row4 = reinterpret_cast<const float4*>(sim + (size_t)i * ld);
+    const longlong2* lab2 = reinterpret_cast<const longlong2*>(labels);
+    float4* g4 = reinterpret_cast<float4*>(G + (size_t)i * ld);
+    uint2* h4 = Gh != nullptr ? reinterpret_cast<uint2*>(Gh + (size_t)i * ld) : nullptr;
+#pragma unroll 4
+    for (int q = lane; q < ld / 4; q += 32) {
+        const int j = 4 * q;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid && j < B) {
+            const float4 v = row4[q];
+            long long y[4];
+            if (j + 3 < B) {
+                const longlong2 la = lab2[2 * q], lb = lab2[2 * q + 1];
+                y[0] = la.x; y[1] = la.y; y[2] = lb.x; y[3] = lb.y;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = j + u < B ? labels[j + u] : -1;
+            }
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j + u >= B || j + u == i) continue;
+                const float e = expf(x[u] * inv_tau - mx);
+                g[u] = k * e * (ia - (y[u] == yi ? ip : 0.f));
+            }
         }
-        G[(size_t)i * ld + j] = g;
-        if (Gh != nullptr) Gh[(size_t)i * ld + j] = __float2bfloat16_rn(g);
+        const float4 o = make_float4(g[0], g[1], g[2], g[3]);
+        g4[q] = o;
+        if (h4 != nullptr) h4[q] = pack_bf16x4(o);
     }
 }
 
@@ -481,11 +528,29 @@ clip_stats_kernel(int B, int ld, const float* __restrict__ L, const float* __res
     if (r >= 2 * B) return;
     const int i = r < B ? r : r - B;
     const float* row = (r < B ? L : LT) + (size_t)i * ld;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int n4 = (B + 3) >> 2;
     float mx = -INFINITY;
-    for (int j = lane; j < B; j += 32) mx = fmaxf(mx, row[j] * scale);
+#pragma unroll 4
+    for (int q = lane; q < n4; q += 32) {
+        const float4 v = row4[q];
+        const int j = 4 * q;
+        mx = fmaxf(mx, v.x * scale);
+        if (j + 1 < B) mx = fmaxf(mx, v.y * scale);
+        if (j + 2 < B) mx = fmaxf(mx, v.z * scale);
+        if (j + 3 < B) mx = fmaxf(mx, v.w * scale);
+    }
     mx = warp_max(mx);
     float z = 0.f;
-    for (int j = lane; j < B; j += 32) z += expf(row[j] * scale - mx);
+#pragma unroll 4
+    for (int q = lane; q < n4; q += 32) {
+        const float4 v = row4[q];
+        const int j = 4 * q;
+        z += expf(v.x * scale - mx);
+        if (j + 1 < B) z += expf(v.y * scale - mx);
+        if (j + 2 < B) z += expf(v.z * scale - mx);
+        if (j + 3 < B) z += expf(v.w * scale - mx);
+    }
     z = warp_sum(z);
     if (lane == 0) {
         const float l = logf(z) + mx;
@@ -503,14 +568,23 @@ clip_grad_kernel(int B, int ld, const float* __restrict__ L, float scale, float 
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= B) return;
     const float li = lse[i];
-    for (int j = lane; j < ld; j += 32) {
-        float g = 0.f;
+    const float4* row4 = reinterpret_cast<const float4*>(L + (size_t)i * ld);
+    float4* g4 = reinterpret_cast<float4*>(G + (size_t)i * ld);
+    uint2* h4 = Gh != nullptr ? reinterpret_cast<uint2*>(Gh + (size_t)i * ld) : nullptr;
+#pragma unroll 4
+    for (int q = lane; q < ld / 4; q += 32) {
+        const int j = 4 * q;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
         if (j < B) {
-            const float x = L[(size_t)i * ld + j] * scale;
-            g = k * (expf(x - li) + expf(x - lse[B + j]) - (j == i ? 2.f : 0.f));
+            const float4 v = row4[q];
+            const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j + u < B) g[u] = k * (expf(x[u] - li) + expf(x[u] - lse[B + j + u]) - (j + u == i ? 2.f : 0.f));
         }
-        G[(size_t)i * ld + j] = g;
-        if (Gh != nullptr) Gh[(size_t)i * ld + j] = __float2bfloat16_rn(g);
+        const float4 o = make_float4(g[0], g[1], g[2], g[3]);
+        g4[q] = o;
+        if (h4 != nullptr) h4[q] = pack_bf16x4(o);
     }
 }
 __global__ void clip_finish_kernel(const float* __restrict__ scal, float inv_2B, float* __restrict__ loss) {
