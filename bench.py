@@ -436,7 +436,7 @@ def run_team(a):
                         if x.shape[0]:
                             spans.append(float(int(x[:, 7].max()) - int(x[:, 2].min())) * 1e-3)
                 del gs
-            if spans and world == 1:
+            if spans:
                 us = sum(spans) / len(spans)
                 fl = roof["algorithmic_flops_per_launch"]
                 # The launch duration INSIDE the timed graph is the roofline's denominator.  The event pair around an eager launch
