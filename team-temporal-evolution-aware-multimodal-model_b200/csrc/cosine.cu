@@ -57,20 +57,32 @@ cosine_logits_kernel(const T* __restrict__ x, int64_t n_rows, const float* __res
     const int c0 = blockIdx.y * COS_CCHUNK;
     const int nc = min(COS_CCHUNK, num_classes - c0);
     const int c_alloc = min(COS_CCHUNK, num_classes);
-    for (int c = warp; c < c_alloc; c += COS_WARPS) {
-        float4 r[4];
-        float ss = 0.f;
+    // class rows of this warp (c = warp, warp + 8, ...: at most COS_CCHUNK / COS_WARPS = 4): ALL their loads first, then the
+    // norms - one L2 round trip instead of one per class row (this prologue is most of the kernel at ~1 000 rows)
+    {
+        constexpr int CPW = (COS_CCHUNK + COS_WARPS - 1) / COS_WARPS;
+        float4 r[CPW][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            r[j] = (c < nc) ? reinterpret_cast<const float4*>(w + (size_t)(c0 + c) * D)[lane + 32 * j]
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            ss += dot4(r[j], r[j]);
+        for (int u = 0; u < CPW; ++u) {
+            const int c = warp + u * COS_WARPS;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                r[u][j] = (c < nc) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)(c0 + c) * D) + lane + 32 * j)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        ss = warp_sum(ss);
-        const float inv = 1.0f / fmaxf(sqrtf(ss), NORM_EPS);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            ws[c * (D / 4) + lane + 32 * j] = make_float4(r[j].x * inv, r[j].y * inv, r[j].z * inv, r[j].w * inv);
+        for (int u = 0; u < CPW; ++u) {
+            const int c = warp + u * COS_WARPS;
+            if (c >= c_alloc) continue;
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ss += dot4(r[u][j], r[u][j]);
+            ss = warp_sum(ss);
+            const float inv = 1.0f / fmaxf(sqrtf(ss), NORM_EPS);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                ws[c * (D / 4) + lane + 32 * j] = make_float4(r[u][j].x * inv, r[u][j].y * inv, r[u][j].z * inv, r[u][j].w * inv);
+        }
     }
     __syncthreads();
     const float sigma = sigma_dev ? __ldg(sigma_dev) : 1.0f;
