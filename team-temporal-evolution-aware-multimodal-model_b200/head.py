@@ -560,6 +560,10 @@ class HeadStepRunner:
             self.hw.w_frozen[k] = fw[k].data_ptr()
             self.hw.b_frozen[k] = fb[k].data_ptr()
         self.hw.num_frozen = T - 1
+        # the sums are consumed by steps that may run on OTHER streams (a capture stream, a pipeline's compute stream): make
+        # them visible now (once per task; not possible - and not needed, same stream - while that stream is being captured)
+        if not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream().synchronize()
 
     @staticmethod
     def grad_numel(pack: HeadParamPack) -> int:
