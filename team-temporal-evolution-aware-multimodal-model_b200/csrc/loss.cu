@@ -166,7 +166,8 @@ unicl_cat_stats_kernel(int B, int ld, const float* __restrict__ sim, const int64
 
 // single block: fixed-order sums of n values of a and (optionally) b -> out[0], out[1]
 __global__ void __launch_bounds__(1024)
-loss_fold2_kernel(int n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out) {
+loss_fold2_kernel(int n, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                  int finish = 0, float c = 0.f, const float* __restrict__ scal = nullptr, float* __restrict__ losses = nullptr) {
     pdl_trigger();
     pdl_wait();
     __shared__ float sa[1024], sb[1024];
@@ -178,7 +179,17 @@ loss_fold2_kernel(int n, const float* __restrict__ a, const float* __restrict__ 
         if ((int)threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out[0] = sa[0]; out[1] = sb[0]; }
+    if (threadIdx.x == 0) {
+        out[0] = sa[0]; out[1] = sb[0];
+        // the loss value(s) right here instead of in a one-thread kernel of their own (one launch less on the chain):
+        if (finish == 1) {                      // ClipLoss: sum of the 2B row losses / 2B
+            losses[0] = sa[0] * c;
+        } else if (finish == 2) {               // unicl: scal = {valid count, category sum}, this fold = instance sum; c = 1 / 3B
+            const float cat = scal[0] > 0.f ? scal[1] / scal[0] : 0.f;
+            const float inst = sa[0] * c;
+            losses[0] = inst + 0.5f * cat; losses[1] = inst; losses[2] = cat;
+        }
+    }
 }
 
 // G[i][j] = d(0.5 * grad_scale * category_loss) / d(sim_ij)   (scal[0] = valid count)
@@ -506,17 +517,6 @@ evo_bwd2_kernel(int B, const float* __restrict__ Xs, const float* __restrict__ i
     st_row(g_state + (size_t)b * D, lane, d);
 }
 
-// losses[0] = total, [1] = instance, [2] = category   (scal: 0 valid, 1 category sum, 2 instance sum)
-__global__ void unicl_finish_kernel(const float* __restrict__ scal, float inv_3B, float* __restrict__ losses) {
-    pdl_trigger();
-    pdl_wait();
-    if (threadIdx.x == 0) {
-        const float cat = scal[0] > 0.f ? scal[1] / scal[0] : 0.f;
-        const float inst = scal[2] * inv_3B;
-        losses[0] = inst + 0.5f * cat; losses[1] = inst; losses[2] = cat;
-    }
-}
-
 // ---- ClipLoss: per row of s * L (rows [0,B): image->text from L, rows [B,2B): text->image from L^T): lse and loss
 __global__ void __launch_bounds__(256)
 clip_stats_kernel(int B, int ld, const float* __restrict__ L, const float* __restrict__ LT, float scale,
@@ -587,12 +587,6 @@ clip_grad_kernel(int B, int ld, const float* __restrict__ L, float scale, float 
         if (h4 != nullptr) h4[q] = pack_bf16x4(o);
     }
 }
-__global__ void clip_finish_kernel(const float* __restrict__ scal, float inv_2B, float* __restrict__ loss) {
-    pdl_trigger();
-    pdl_wait();
-    if (threadIdx.x == 0) loss[0] = scal[0] * inv_2B;
-}
-
 static int loss_setup(LossWS& w, int64_t batch, void* workspace, size_t workspace_bytes, const char* who) {
     TEAM_REQUIRE(batch >= 1 && batch <= LOSS_MAX_BATCH, "%s: batch %lld out of [1, %lld]", who, (long long)batch, (long long)LOSS_MAX_BATCH);
     loss_plan(batch, workspace, &w);
@@ -670,7 +664,7 @@ static int unicl_impl(int mode, const float* image, const float* text, const flo
         if ((rc = loss_gemm(st, mode, w, B, B, w.sim, ld, &s, 1))) return rc;
     }
     TEAM_LAUNCH(unicl_cat_stats_kernel, (B + 7) / 8, 256, 0, st, B, ld, w.sim, labels, inv_tau, w.rmax, w.rpos, w.rall, w.rloss);
-    TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, B, w.rmax + B, w.rloss, w.scal);                 // valid count, category sum
+    TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, B, w.rmax + B, w.rloss, w.scal, 0, 0.f, (const float*)nullptr, (float*)nullptr);   // valid count, category sum
     TEAM_LAUNCH(unicl_cat_grad_kernel, (B + 7) / 8, 256, 0, st, B, ld, w.sim, labels, inv_tau, 0.5f * grad_scale, w.rmax, w.rpos, w.rall, w.scal, w.G.f, bf ? w.G.h : nullptr);
     {   // dcat = G Xi + G^T Xi
         LSeg s[2] = {{false, true, B, w.G, w.X[0]}, {true, true, B, w.G, w.X[0]}};
@@ -683,8 +677,7 @@ static int unicl_impl(int mode, const float* image, const float* text, const flo
         TEAM_LAUNCH(evo_keysum_kernel, keys, 128, (size_t)((B + 31) / 32) * sizeof(unsigned int), st, B, dMix, rowmask, labels, ev->state_ids, ev->num_evo, ev->evo_mask, DM, (int*)nullptr);
         TEAM_LAUNCH(evo_bwd2_kernel, (B + 7) / 8, 256, 0, st, B, w.X[2].f, w.inv[2], labels, ev->state_ids, sc, DM, cnt, dXe, g_state);
     }
-    TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, B, w.rloss + B, (const float*)nullptr, w.scal + 2);
-    TEAM_LAUNCH(unicl_finish_kernel, 1, 32, 0, st, w.scal, 1.0f / (3.0f * (float)B), losses);
+    TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, B, w.rloss + B, (const float*)nullptr, w.scal + 2, 2, 1.0f / (3.0f * (float)B), w.scal, losses);
     return TEAM_OK;
 }
 
@@ -774,7 +767,7 @@ extern "C" int team_clip_loss(int mode, const float* image, const float* text, i
         if ((rc = loss_gemm(st, mode, w, B, B, w.simT, ld, &t, 1))) return rc;                   // L^T = T I^T
     }
     TEAM_LAUNCH(clip_stats_kernel, (2 * B + 7) / 8, 256, 0, st, B, ld, w.sim, w.simT, logit_scale, w.rmax, w.rloss);
-    TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, 2 * B, w.rloss, (const float*)nullptr, w.scal);
+    TEAM_LAUNCH(loss_fold2_kernel, 1, 1024, 0, st, 2 * B, w.rloss, (const float*)nullptr, w.scal, 1, 1.0f / (2.0f * (float)B), (const float*)nullptr, loss);
     TEAM_LAUNCH(clip_grad_kernel, (B + 7) / 8, 256, 0, st, B, ld, w.sim, logit_scale, logit_scale * grad_scale / (2.0f * (float)B), w.rmax, w.G.f, bf ? w.G.h : nullptr);
     {
         LSeg s{false, true, B, w.G, w.X[1]};
@@ -782,6 +775,5 @@ extern "C" int team_clip_loss(int mode, const float* image, const float* text, i
         LSeg t{true, true, B, w.G, w.X[0]};
         if ((rc = loss_gemm(st, mode, w, B, D, g_text, D, &t, 1))) return rc;                    // dT = G^T I
     }
-    TEAM_LAUNCH(clip_finish_kernel, 1, 32, 0, st, w.scal, 1.0f / (2.0f * (float)B), loss);
     return TEAM_OK;
 }
