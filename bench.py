@@ -579,11 +579,11 @@ def run_team(a):
     at_scale = None
     if world == 1 and not a.no_scale:
         at_scale = []
-        for Bs in (4096, 16384, 65536):
+        for Bs in (256, 4096, 16384, 65536):         # BASELINE configs[4]: 256 ... 65 536 (1 024 is the headline itself)
             try:
                 gen = torch.Generator(device="cpu").manual_seed(Bs)
                 sets = []
-                for i in range(2 if Bs > 4096 else 8):
+                for i in range(2 if Bs > 4096 else (8 if Bs >= 4096 else 64)):
                     si = torch.nn.functional.normalize(torch.randn(Bs, 512, generator=gen), dim=-1).to(dev)
                     stx = torch.nn.functional.normalize(torch.randn(Bs, 512, generator=gen), dim=-1).to(dev)
                     ss = torch.tensor([1, 3, 4])[torch.randint(0, 3, (Bs,), generator=gen)].to(dev)
