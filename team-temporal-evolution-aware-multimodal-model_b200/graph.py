@@ -346,14 +346,31 @@ def evolve_state_prototypes(p: Dict[str, torch.Tensor], img_prototypes: torch.Te
         return None
     res = evolve_and_update(p, by_state, lifecycle_types)
     L = capi.lib()
+    # The rows the GCN wrote are views of ONE [nodes, 512] buffer (evolve_and_update): normalise that buffer with one launch
+    # instead of one launch per (class, state) row - 466 launches at 200 classes; rows that are tensors of their own
+    # (classes with a single state are not part of the graph) keep a launch each.
+    whole: Dict[int, list] = {}
     for c, sp in res["prototypes"].items():
         for s, ev in sp.items():
             if c in by_state and s in by_state[c]:
                 row = by_state[c][s]
-                if row.is_cuda and row.dtype == torch.float32 and row.is_contiguous():
-                    capi.check(L.team_rows_normalize(row.data_ptr(), 1, _stream_ptr()), "team_rows_normalize")
-                else:
+                if not (row.is_cuda and row.dtype == torch.float32 and row.is_contiguous()):
                     raise capi.TeamB200Error("state prototypes must be contiguous fp32 CUDA rows")
+                base = row._base
+                if (base is not None and base.dim() == 2 and base.shape[1] == row.shape[0] and base.is_contiguous()
+                        and base.dtype == torch.float32):
+                    whole.setdefault(id(base), [base, 0])[1] += 1
+                else:
+                    capi.check(L.team_rows_normalize(row.data_ptr(), 1, _stream_ptr()), "team_rows_normalize")
+    for base, n in whole.values():
+        if n == base.shape[0]:                 # every row of the buffer is a prototype: one launch
+            capi.check(L.team_rows_normalize(base.data_ptr(), base.shape[0], _stream_ptr()), "team_rows_normalize")
+        else:                                  # a buffer only partly referenced: row by row, touching nothing else
+            for c, sp in res["prototypes"].items():
+                for s, ev in sp.items():
+                    row = by_state.get(c, {}).get(s)
+                    if row is not None and row._base is base:
+                        capi.check(L.team_rows_normalize(row.data_ptr(), 1, _stream_ptr()), "team_rows_normalize")
     sync_class_prototypes(img_prototypes, by_state)
     return res["embeddings"]
 

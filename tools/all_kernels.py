@@ -22,12 +22,13 @@ protos = synth.make_prototypes(C).to(dev)
 text_cls = synth.make_text_class_features(20)[:C].contiguous().to(dev)
 b = {k: v.to(dev) for k, v in synth.make_batch(B, C, step=0).items()}
 cots = [c.to(dev).reshape(B, 512) for c in synth.make_cotangents(B, step=0)]
+ONLY = os.environ.get("ALLK_ONLY", "")            # "graph": only the graph / state-distance kernels (a short second capture)
 gen = torch.Generator(device=dev).manual_seed(0)
-big = int(os.environ.get('ALLK_BIG', '8192'))   # run with TEAM_TABLE_GRAM_MIN_B <= this to reach the Gram table-row kernels
+big = 8 if ONLY == "graph" else int(os.environ.get('ALLK_BIG', '8192'))   # run with TEAM_TABLE_GRAM_MIN_B <= this to reach the Gram table-row kernels
 bigx = [torch.nn.functional.normalize(torch.randn(big, 512, generator=gen, device=dev), dim=-1) for _ in range(2)]
 bigs = torch.randint(1, 5, (big,), generator=gen, device=dev)
 bigc = [torch.randn(big, 512, generator=gen, device=dev) for _ in range(4)]
-N = 1 << 19
+N = 1024 if ONLY == "graph" else 1 << 19
 xr = torch.randn(N, 512, generator=gen, device=dev)
 yr = torch.randint(0, 20, (N,), generator=gen, device=dev)
 sr = torch.randint(0, 10, (N,), generator=gen, device=dev)
@@ -46,7 +47,22 @@ hx = torch.randn(4096, 512, generator=gen, device=dev)
 f = graph.prior_distance_factors(device=dev)
 
 
+def graph_part():
+    r = graph.evolve_and_update(gp, bs, {})
+    graph.evolve_state_prototypes(gp, torch.zeros(200, 512, device=dev), bs, {})
+    graph.update_state_distance_matrix(f, r["distances"])
+    graph.state_distance_forward(f, b["image"], b["state"], 0, training=True)
+    graph.get_distance_matrix(f)
+    g12 = torch.Generator().manual_seed(1)
+    x12 = torch.randn(12, 512, generator=g12).to(dev)
+    layers = [tuple(t.to(dev) for t in (torch.randn(o, i, generator=g12) * 0.05, torch.zeros(o), torch.ones(o), torch.zeros(o)))
+              for i, o in ((512, 256), (256, 512))]
+    graph.dynamic_gcn(x12, torch.randint(0, 12, (2, 30), generator=g12).to(dev), torch.rand(30, generator=g12).to(dev), layers)
+
+
 def everything():
+    if ONLY == "graph":
+        return graph_part()
     runner.step(b["image"], b["text"], b["state"], text_cls, cots)                      # head fwd + bwd, bf16 (tcgen05)
     runner32.step(b["image"], b["text"], b["state"], text_cls, cots)                    # fp32 parity mode (FFMA GEMM)
     runner_big.step(bigx[0], bigx[1], bigs, text_cls, bigc)                             # persistent GEMM, Gram table rows
@@ -62,16 +78,7 @@ def everything():
     ops.cosine_logits(xr, Wr, want_argmax=True)
     ops.cosine_logits(xr[:300], Wr, want_argmax=True)
     ops.herding_select(hx, 20, [1024] * 4)
-    r = graph.evolve_and_update(gp, bs, {})
-    graph.evolve_state_prototypes(gp, torch.zeros(200, 512, device=dev), bs, {})
-    graph.update_state_distance_matrix(f, r["distances"])
-    graph.state_distance_forward(f, b["image"], b["state"], 0, training=True)
-    graph.get_distance_matrix(f)
-    g12 = torch.Generator().manual_seed(1)
-    x12 = torch.randn(12, 512, generator=g12).to(dev)
-    layers = [tuple(t.to(dev) for t in (torch.randn(o, i, generator=g12) * 0.05, torch.zeros(o), torch.ones(o), torch.zeros(o)))
-              for i, o in ((512, 256), (256, 512))]
-    graph.dynamic_gcn(x12, torch.randint(0, 12, (2, 30), generator=g12).to(dev), torch.rand(30, generator=g12).to(dev), layers)
+    graph_part()
 
 
 everything()
