@@ -69,6 +69,7 @@ def test_cosine_linear_vs_golden(golden):
     (1, 3, False, False, torch.float32), (7, 2, False, True, torch.float32),
     (4099, 20, True, False, torch.float32), (65536, 20, False, True, torch.float32),
     (30001, 20, True, False, torch.bfloat16), (5000, 70, False, False, torch.float32),
+    (70001, 20, True, False, torch.bfloat16), (66000, 6, False, True, torch.bfloat16),      # bf16 rows, few keys: key-partitioned path
 ])
 def test_keyed_sums_vs_oracle(n, C, zipf, norm, dtype):
     from team_b200 import ops
