@@ -148,6 +148,8 @@ def _declare(lib):
         lib.team_adamw_step_graph.restype = i32
         lib.team_adamw_step_graph.argtypes = [i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64),
                                               C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, i32, vp]
+        lib.team_copy_batch.restype = i32
+        lib.team_copy_batch.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]
         lib.team_ce_total.restype = i32
         lib.team_ce_total.argtypes = [vp, vp, i64, i64, C.c_float, C.c_float, vp, vp]
         lib.team_loss_workspace_bytes.restype = sz
