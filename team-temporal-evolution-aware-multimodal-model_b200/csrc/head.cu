@@ -463,10 +463,10 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
     {   // the two softmax kernels (step-row table, own rows) are independent
         const cudaStream_t tst = fork_side(cx.st, &side);
         const bool gram = use_table_gram(d);
-        const int xwarps = gram ? TG_RP : 0;                 // + the s rows of the Gram formulation (head_table_gram.cuh)
+        const int xwarps = TG_RP;                            // + the s rows S_r + b_fc (bulk-copy source of the table-row kernels; Gram operand)
         TEAM_LAUNCH(table_prep_kernel, (d.Nsp + xwarps + 7) / 8, 256, 0, tst, w.TT, d.M, d.Nsp, w.mt, w.Zt, w.Pt.f, w.Pt.h, w.S.f, hw->b_fc,
                     w.VFs.f, (const __nv_bfloat16*)w.VFs.h, d.C, TG_RP,
-                    gram ? w.VFs.f + (size_t)d.Nsp * D : (float*)nullptr, gram && w.VFs.h ? w.VFs.h + (size_t)d.Nsp * D : (__nv_bfloat16*)nullptr);
+                    w.VFs.f + (size_t)d.Nsp * D, w.VFs.h ? w.VFs.h + (size_t)d.Nsp * D : (__nv_bfloat16*)nullptr);
         if (gram)             // ... and its n rows
             TEAM_LAUNCH(table_nf_kernel, d.Rt, 256, ((d.M + 3) / 4 * 4 + 512) * sizeof(float), tst, w.TT, d.M, d.Nsp, d.C, w.VFs.f, (const __nv_bfloat16*)w.VFs.h,
                         w.VFs.f + (size_t)(d.Nsp + TG_RP) * D, w.VFs.h ? w.VFs.h + (size_t)(d.Nsp + TG_RP) * D : (__nv_bfloat16*)nullptr);
@@ -505,7 +505,7 @@ extern "C" int team_head_tri_fwd(const team_head_weights* hw, int mode, int64_t 
         const int groups = (d.B + TW - 1) / TW;
         const size_t tsm = table2_fwd_smem_floats(d) * sizeof(float);
         TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-        TEAM_LAUNCH(table_rows_fwd2_kernel, groups < NUM_SMS ? groups : NUM_SMS, TW * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
+        TEAM_LAUNCH(table_rows_fwd2_kernel, groups < NUM_SMS ? groups : NUM_SMS, TW * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state, w.VFs.f + (size_t)d.Nsp * D);
     } else {
         const int tgrid = d.B < 6 * NUM_SMS ? d.B : 6 * NUM_SMS;
         TEAM_LAUNCH(table_rows_fwd_kernel, tgrid, TQ_WARPS * 32, 0, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, hw->ln_b, state_ids, out_proto, out_state);
@@ -561,7 +561,7 @@ extern "C" int team_head_tri_bwd(const team_head_weights* hw, int mode, int64_t 
         tgrid = groups < NUM_SMS ? groups : NUM_SMS;
         const size_t tsm = table2_bwd_smem_floats(d) * sizeof(float);
         TEAM_CUDA_CHECK(cudaFuncSetAttribute(table_rows_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-        TEAM_LAUNCH(table_rows_bwd2_kernel, tgrid, TW * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials);
+        TEAM_LAUNCH(table_rows_bwd2_kernel, tgrid, TW * 32, tsm, cx.st, d, w.SK, w.TT, w.mt, w.Zt, w.NFt, w.VFo.f, w.VFs.f, w.S.f, hw->b_fc, hw->ln_g, state_ids, g_proto, g_state, w.dSK.f, w.dSK.h, w.dVFo.f, w.GG.f, w.GG.h, w.A1.f, w.A1.h, w.A23.f, w.A23.h, w.ldA, w.tab_partials, w.VFs.f + (size_t)d.Nsp * D);
     } else {
         TEAM_REQUIRE(g_proto != nullptr, "head bwd: g_proto = NULL needs the warp-per-sample table-row kernel (C <= 22)");
         tgrid = d.B < d.nctas ? d.B : d.nctas;

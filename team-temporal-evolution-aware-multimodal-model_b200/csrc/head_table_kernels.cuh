@@ -21,40 +21,44 @@ constexpr int TW = 8;               // warps per CTA = samples per round
 constexpr int TB_NRS = 12;          // per-row scalar contributions handed to the fold (see table_rows_bwd_kernel: scal)
 
 __host__ __device__ inline bool table2_supported(const HeadDims& d) { return d.C + 1 <= 32 && d.Rt <= 32; }
-__host__ __device__ inline size_t table2_fwd_smem_floats(const HeadDims& d) { return (size_t)2 * d.Rt * D; }
+constexpr int T2_BAR_FLOATS = 4;    // 16 bytes in front of the tables: the mbarrier of the bulk table load
+__host__ __device__ inline size_t table2_fwd_smem_floats(const HeadDims& d) { return (size_t)T2_BAR_FLOATS + (size_t)2 * d.Rt * D; }
 __host__ __device__ inline size_t table2_bwd_smem_floats(const HeadDims& d) {
-    return (size_t)2 * d.Rt * D + (size_t)TW * 3 * D + (size_t)10 * D + (size_t)d.Rt * TQ_NSC + (size_t)TW * 32 * TB_NRS + D + 16;
+    return (size_t)T2_BAR_FLOATS + (size_t)2 * d.Rt * D + (size_t)TW * 3 * D + (size_t)10 * D + (size_t)d.Rt * TQ_NSC + (size_t)TW * 32 * TB_NRS + D + 16;
 }
 
-// tabN[tr] = NF_r, tabS[tr] = S_r + bfc;  tr < C: r = tr (prototype row), tr >= C: r = M + tr - C (state-table row)
-__device__ __forceinline__ void table2_load(const HeadDims& d, const float* __restrict__ NFt, const float* __restrict__ S,
-                                            const float* __restrict__ bfc, float* tabN, float* tabS) {
-    // Six float4 pairs in flight per thread: with a plain loop every iteration is one dependent L2 round trip (all CTAs read
-    // the same 120 KB at the same moment), 15 of them back to back before the first row can start.
-    const int n4 = d.Rt * (D / 4);
-    constexpr int UB = 6;
-    const float4 bias = reinterpret_cast<const float4*>(bfc)[threadIdx.x & 127];      // column of i = tid + k * blockDim.x (blockDim.x % 128 == 0)
-    for (int i0 = threadIdx.x; i0 < n4; i0 += UB * blockDim.x) {
-        float4 a[UB], s[UB];
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-            const int i = i0 + u * (int)blockDim.x;
-            if (i < n4) {
-                const int tr = i >> 7, c = i & 127;
-                const int r = tr < d.C ? tr : d.M + tr - d.C;
-                a[u] = __ldg(reinterpret_cast<const float4*>(NFt + (size_t)r * D) + c);
-                s[u] = __ldg(reinterpret_cast<const float4*>(S + (size_t)r * D) + c);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UB; ++u) {
-            const int i = i0 + u * (int)blockDim.x;
-            if (i < n4) {
-                s[u].x += bias.x; s[u].y += bias.y; s[u].z += bias.z; s[u].w += bias.w;
-                reinterpret_cast<float4*>(tabN)[i] = a[u];
-                reinterpret_cast<float4*>(tabS)[i] = s[u];
-            }
-        }
+// tabN[tr] = NF_r, tabS[tr] = S_r + bfc;  tr < C: r = tr (prototype row), tr >= C: r = M + tr - C (state-table row).
+// The 120 KB come in as THREE bulk copies of the TMA engine (cp.async.bulk, completion on an mbarrier): the prototype rows and
+// the state-table rows of NFt, and the s rows Sb = S_r + b_fc that table_prep_kernel writes once per step.  One thread issues
+// them, every warp goes on with its sample's own loads and softmax weights and only waits (table2_wait) before the first table
+// row is read.  The register-staged load this replaces was a quarter of the kernel at 1 024 samples (ncu stall samples,
+// profiles/r2ab_table_rows_bwd2_stall_regions.md) - every CTA reads the same lines at the same moment.
+__device__ __forceinline__ uint32_t t2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void table2_load_async(const HeadDims& d, const float* __restrict__ NFt, const float* __restrict__ Sb,
+                                                  float* tabN, float* tabS, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        const uint32_t b = t2_smem_u32(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t n1 = (uint32_t)d.C * D * 4, n2 = 10u * D * 4, n3 = (uint32_t)d.Rt * D * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(n1 + n2 + n3) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(t2_smem_u32(tabN)), "l"(NFt), "r"(n1), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(t2_smem_u32(tabN + (size_t)d.C * D)), "l"(NFt + (size_t)d.M * D), "r"(n2), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(t2_smem_u32(tabS)), "l"(Sb), "r"(n3), "r"(b) : "memory");
+    }
+}
+// bounded wait for the tables (phase 0 of the barrier; returns at once on every later call)
+__device__ __forceinline__ void table2_wait(uint64_t* bar) {
+    const uint32_t b = t2_smem_u32(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(b) : "memory");
+        if (ok) return;
+        if (spin > (1u << 24)) __trap();
     }
 }
 
@@ -65,15 +69,17 @@ table_rows_fwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
                        const float* __restrict__ VFo, const float* __restrict__ VFs, const float* __restrict__ S,
                        const float* __restrict__ bfc, const float* __restrict__ gamma, const float* __restrict__ beta,
                        const int64_t* __restrict__ state_ids, float* __restrict__ out_proto,
-                       float* __restrict__ out_state) {
+                       float* __restrict__ out_state, const float* __restrict__ Sb) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) float t2_smem[];
-    float* tabN = t2_smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(t2_smem);
+    float* tabN = t2_smem + T2_BAR_FLOATS;
     float* tabS = tabN + (size_t)d.Rt * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    table2_load(d, NFt, S, bfc, tabN, tabS);
-    __syncthreads();
+    table2_load_async(d, NFt, Sb, tabN, tabS, bar);
+    __syncthreads();                                      // the barrier is initialised before anybody polls it
+    (void)S; (void)bfc;
     const float invC = 1.0f / (float)d.C;
     for (int b = blockIdx.x * TW + warp; b < d.B; b += gridDim.x * TW) {
         const int sid = clamp_state(state_ids[b]);
@@ -86,6 +92,7 @@ table_rows_fwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
         TableRowW mine;
         mine.c_w = mine.a_i = mine.a_t = mine.a_s = 0.f; mine.r = 0;
         if (lane <= d.C) mine = table_row_weights(d, b, lane, srow, SK, TT, mt, Zt);
+        table2_wait(bar);
         // Prototype rows two at a time: a row is one dependent chain (shared-memory loads -> 512-wide sums -> five shuffle
         // rounds -> rsqrt -> accumulate) and at 1 024 samples a warp owns one sample, so the kernel's time is C + 1 of
         // those chains back to back; two independent rows in flight overlap their shuffle / load latencies.
@@ -166,11 +173,12 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
                        const float* __restrict__ g_state, float* __restrict__ dSK, __nv_bfloat16* __restrict__ dSKh,
                        float* __restrict__ dVFo, float* __restrict__ GG, __nv_bfloat16* __restrict__ GGh,
                        float* __restrict__ A1, __nv_bfloat16* __restrict__ A1h, float* __restrict__ A23,
-                       __nv_bfloat16* __restrict__ A23h, int ldA, float* __restrict__ partials) {
+                       __nv_bfloat16* __restrict__ A23h, int ldA, float* __restrict__ partials, const float* __restrict__ Sb) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) float t2_smem[];
-    float* tabN = t2_smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(t2_smem);
+    float* tabN = t2_smem + T2_BAR_FLOATS;
     float* tabS = tabN + (size_t)d.Rt * D;
     float* slots = tabS + (size_t)d.Rt * D;                  // [TW][3][D]
     float* dvfst = slots + (size_t)TW * 3 * D;               // [10][D]
@@ -181,7 +189,8 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TabOff off = tab_offsets(d);
     const int gcol = ldA / 2;
-    table2_load(d, NFt, S, bfc, tabN, tabS);
+    table2_load_async(d, NFt, Sb, tabN, tabS, bar);
+    (void)S; (void)bfc;
     for (int i = tid; i < 10 * D; i += blockDim.x) dvfst[i] = 0.f;
     for (int i = tid; i < d.Rt * TQ_NSC; i += blockDim.x) scal[i] = 0.f;
     for (int i = tid; i < D; i += blockDim.x) gam[i] = gamma[i];
@@ -230,6 +239,7 @@ table_rows_bwd2_kernel(HeadDims d, const float* __restrict__ SK, const float* __
             TableRowW mine;
             mine.c_w = mine.a_i = mine.a_t = mine.a_s = 0.f; mine.r = 0;
             if (lane <= d.C) mine = table_row_weights(d, b, lane, srow, SK, TT, mt, Zt);
+            table2_wait(bar);
             float4 acc_i[4], acc_t[4], acc_s[4], xs[4];
             zero_row(acc_i); zero_row(acc_t); zero_row(acc_s); zero_row(xs);
             float k_alpha = 0.f, k_beta = 0.f, k_mean = 0.f, k_m1 = 0.f, k_yy = 0.f, k_i = 0.f, k_t = 0.f, k_s = 0.f;
