@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "team-temporal-evolution-aware-multimodal-model_b200", "libteam_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
-KEYS = (("UTC*MMA (tcgen05.mma)", r"\bUTC\w*MMA"), ("LDTM/STTM (tcgen05.ld/st)", r"\b(LDTM|STTM)"), ("UTMALDG/UTMASTG (TMA)", r"\bUTMA(LDG|STG)"),
+KEYS = (("UTC*MMA (tcgen05.mma)", r"\bUTC\w*MMA"), ("LDTM/STTM (tcgen05.ld/st)", r"\b(LDTM|STTM)"), ("UTMALDG/UTMASTG/UBLKCP (TMA)", r"\b(UTMA(LDG|STG)|UBLKCP)"),
         ("UTCBAR / SYNCS (mbarrier)", r"\b(UTCBAR|SYNCS)"), ("multimem / LDGMC", r"\b(LDGMC|REDGMC|STGMC|multimem)"), ("HMMA (mma.sync)", r"\bHMMA"),
         ("SHFL", r"\bSHFL"), ("LDG.128 / STG.128", r"\b(LDG|STG)\.E\.(\w+\.)*128"))
 cur, rows = None, collections.OrderedDict()
