@@ -37,6 +37,20 @@ def _tower_state(params) -> tuple:
     return frozen, ver
 
 
+def _match_rows(rows: torch.Tensor, table: torch.Tensor, max_cells: int = 1 << 26) -> torch.Tensor:
+    """Index of every row of ``rows`` [u, L] in ``table`` [U, L] (exact match), -1 where absent.  The [u, U, L] comparison
+    is done in slabs of at most ``max_cells`` elements so that a full table never costs more than 64 MB of scratch."""
+    u, L = rows.shape
+    U = table.shape[0]
+    slot = torch.full((u,), -1, dtype=torch.int64, device=rows.device)
+    step = max(1, max_cells // max(1, U * L))
+    for lo in range(0, u, step):
+        eq = (rows[lo:lo + step].unsqueeze(1) == table.unsqueeze(0)).all(dim=2)     # [step, U]
+        hit = eq.any(dim=1)
+        slot[lo:lo + step] = torch.where(hit, eq.to(torch.int64).argmax(dim=1), slot[lo:lo + step])
+    return slot
+
+
 class TowerCache:
     def __init__(self, convnet, max_text_rows: int = 65536):
         self.convnet = convnet
@@ -88,8 +102,7 @@ class TowerCache:
         if self._tok_table is None:
             slot = torch.full((uniq.shape[0],), -1, dtype=torch.int64, device=uniq.device)
         else:
-            eq = (uniq.unsqueeze(1) == self._tok_table.unsqueeze(0)).all(dim=2)     # [u, U] exact row matches
-            slot = torch.where(eq.any(dim=1), eq.to(torch.int64).argmax(dim=1), torch.full((uniq.shape[0],), -1, dtype=torch.int64, device=uniq.device))
+            slot = _match_rows(uniq, self._tok_table)
         new = (slot < 0).nonzero().flatten()
         if new.numel() > 0:
             with torch.no_grad():

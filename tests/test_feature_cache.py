@@ -81,3 +81,14 @@ def test_indexed_store():
     st.clear()
     st.get(torch.arange(10), data[:10])
     assert t.image_rows == 110
+
+
+def test_row_match_in_slabs_equals_one_shot():
+    from team_b200.feature_cache import _match_rows
+    g = torch.Generator().manual_seed(3)
+    table = torch.randint(0, 50, (37, 7), generator=g)
+    rows = torch.cat([table[torch.randperm(37, generator=g)[:20]], torch.randint(50, 60, (9, 7), generator=g)])
+    want = torch.tensor([next((j for j in range(37) if torch.equal(table[j], r)), -1) for r in rows])
+    assert torch.equal(_match_rows(rows, table), want)
+    assert torch.equal(_match_rows(rows, table, max_cells=37 * 7 * 3), want)        # 3 rows per slab
+    assert torch.equal(_match_rows(rows, table, max_cells=1), want)                  # 1 row per slab
