@@ -21,5 +21,5 @@ for f in *.cu; do
 done
 for p in $pids; do wait $p; done
 # shared cudart: only the runtime symbols actually used are imported (the static runtime carries every entry point)
-$NVCC -shared --cudart=shared -Xlinker -rpath=/usr/local/cuda/lib64 -o $OUT $objs -lcuda
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared --cudart=shared -Xlinker -rpath=/usr/local/cuda/lib64 -o $OUT $objs -lcuda
 echo "built $(realpath $OUT)"
